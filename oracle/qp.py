@@ -1,0 +1,181 @@
+"""Dense float64 convex-QP solver with a KKT certificate (oracle side; TEST INFRASTRUCTURE ONLY).
+
+Stands in for ``prob.solve(solver=cvxpy.ECOS)`` at ``main/lib/mpc.py:196-197`` of the reference.
+cvxpy (>=1.2.0, pyproject.toml:13) and ECOS (>=2.0.0, requirements.txt:9) are third-party, not
+vendored and not installable offline, so this file restates the *published* algorithm class ECOS
+belongs to -- a Mehrotra predictor-corrector primal-dual interior-point method -- for
+
+    minimise   1/2 z'Pz + q'z + c0     subject to   A z = b,   G z <= h
+
+followed by an active-set polish, and reports the KKT residuals of what it returns.  Because the MPC
+QP is strictly convex in its free directions the optimiser is unique, so any solver whose answer passes
+the certificate is a valid stand-in to far inside the parity tolerances (1e-4 abs / 1e-3 rel).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class QPResult:
+    z: np.ndarray            # primal solution
+    nu: np.ndarray           # equality multipliers
+    lam: np.ndarray          # inequality multipliers (>= 0)
+    obj: float               # 1/2 z'Pz + q'z + c0
+    iters: int               # interior-point iterations used
+    polished: bool           # True when the active-set polish produced the returned point
+    kkt: dict                # residuals: stat, eq, ineq, dual, comp (all scaled, see kkt_residuals)
+    ok: bool                 # kkt certificate passed at `tol`
+
+
+def kkt_residuals(P, q, A, b, G, h, z, nu, lam) -> dict:
+    """Scaled KKT residuals of (z, nu, lam).  Every entry is relative to the size of the terms it
+    is made of, so that 1e-9 means nine correct digits regardless of the cost scaling."""
+    Pz = P @ z
+    Atn = A.T @ nu if A.size else np.zeros_like(z)
+    Gtl = G.T @ lam if G.size else np.zeros_like(z)
+    s_scale = 1.0 + max(np.abs(Pz).max(initial=0.0), np.abs(q).max(initial=0.0),
+                        np.abs(Atn).max(initial=0.0), np.abs(Gtl).max(initial=0.0))
+    stat = np.abs(Pz + q + Atn + Gtl).max(initial=0.0) / s_scale
+    eq = 0.0
+    if A.size:
+        Az = A @ z
+        eq = np.abs(Az - b).max(initial=0.0) / (1.0 + max(np.abs(Az).max(initial=0.0), np.abs(b).max(initial=0.0)))
+    ineq = dual = comp = 0.0
+    if G.size:
+        Gz = G @ z
+        slack = h - Gz
+        p_scale = 1.0 + max(np.abs(Gz).max(initial=0.0), np.abs(h).max(initial=0.0))
+        ineq = max(0.0, (-slack).max(initial=0.0)) / p_scale
+        dual = max(0.0, (-lam).max(initial=0.0)) / s_scale
+        comp = np.abs(lam * slack).max(initial=0.0) / (p_scale * s_scale)
+    return dict(stat=float(stat), eq=float(eq), ineq=float(ineq), dual=float(dual), comp=float(comp))
+
+
+def _solve_sym(K, rhs):
+    """Solve a symmetric (possibly indefinite / mildly singular) system with one refinement step."""
+    try:
+        x = np.linalg.solve(K, rhs)
+    except np.linalg.LinAlgError:
+        x = np.linalg.lstsq(K, rhs, rcond=None)[0]
+    r = rhs - K @ x
+    try:
+        x = x + np.linalg.solve(K, r)
+    except np.linalg.LinAlgError:
+        pass
+    return x
+
+
+def _polish(P, q, A, b, G, h, z, lam, s):
+    """Solve the equality-constrained QP on the active set {i : lam_i > s_i}."""
+    n = P.shape[0]
+    act = np.nonzero(lam > s)[0]
+    Ga = G[act]
+    # drop active rows that are linearly dependent on [A; previously kept rows]
+    keep = []
+    basis = A.copy() if A.size else np.zeros((0, n))
+    rank = np.linalg.matrix_rank(basis) if basis.size else 0
+    for k, row in enumerate(Ga):
+        trial = np.vstack([basis, row[None, :]])
+        r2 = np.linalg.matrix_rank(trial)
+        if r2 > rank:
+            basis, rank = trial, r2
+            keep.append(k)
+    act = act[keep]
+    Ga = G[act]
+    me, ma = A.shape[0], len(act)
+    K = np.zeros((n + me + ma, n + me + ma))
+    K[:n, :n] = P
+    K[:n, n:n + me] = A.T
+    K[n:n + me, :n] = A
+    K[:n, n + me:] = Ga.T
+    K[n + me:, :n] = Ga
+    rhs = np.concatenate([-q, b, h[act]])
+    sol = _solve_sym(K, rhs)
+    zp = sol[:n]
+    nup = sol[n:n + me]
+    lamp = np.zeros(G.shape[0])
+    lamp[act] = sol[n + me:]
+    return zp, nup, lamp
+
+
+def solve_qp(P, q, A, b, G, h, c0: float = 0.0, tol: float = 1e-9, max_iter: int = 60) -> QPResult:
+    P = np.asarray(P, float)
+    q = np.asarray(q, float)
+    n = P.shape[0]
+    A = np.asarray(A, float).reshape(-1, n)
+    b = np.asarray(b, float).reshape(-1)
+    G = np.asarray(G, float).reshape(-1, n)
+    h = np.asarray(h, float).reshape(-1)
+    me, mi = A.shape[0], G.shape[0]
+
+    def aug_solve(W, r1, r2):
+        H = P + G.T @ (W[:, None] * G)
+        K = np.zeros((n + me, n + me))
+        K[:n, :n] = H
+        K[:n, n:] = A.T
+        K[n:, :n] = A
+        sol = _solve_sym(K, np.concatenate([r1, r2]))
+        return sol[:n], sol[n:]
+
+    # --- initial point: equality-constrained least-squares start, slacks/multipliers pushed interior
+    z, nu = aug_solve(np.ones(mi), -q + G.T @ h, b)
+    s = h - G @ z
+    shift = max(0.0, -s.min(initial=0.0)) + 1.0 if (s.min(initial=1.0) <= 1e-8) else 0.0
+    s = s + shift
+    lam = np.ones(mi)
+
+    it = 0
+    for it in range(1, max_iter + 1):
+        r_d = P @ z + q + A.T @ nu + G.T @ lam
+        r_e = A @ z - b
+        r_p = G @ z + s - h
+        mu = float(lam @ s) / max(mi, 1)
+        scale_d = 1.0 + max(np.abs(q).max(initial=0.0), np.abs(P @ z).max(initial=0.0))
+        scale_p = 1.0 + np.abs(h).max(initial=0.0)
+        if (np.abs(r_d).max(initial=0.0) <= 1e-11 * scale_d and np.abs(r_e).max(initial=0.0) <= 1e-11 * scale_p
+                and np.abs(r_p).max(initial=0.0) <= 1e-11 * scale_p and mu <= 1e-13 * scale_d * scale_p):
+            break
+        W = lam / s
+
+        def newton(r_c):
+            t = (-r_c + lam * r_p) / s
+            dz, dnu = aug_solve(W, -r_d - G.T @ t, -r_e)
+            ds = -r_p - G @ dz
+            dlam = (-r_c - lam * ds) / s
+            return dz, dnu, ds, dlam
+
+        def max_step(v, dv):
+            neg = dv < 0
+            return min(1.0, float((-v[neg] / dv[neg]).min(initial=np.inf)))
+
+        # predictor
+        dz_a, dnu_a, ds_a, dlam_a = newton(lam * s)
+        alpha_a = min(max_step(s, ds_a), max_step(lam, dlam_a))
+        mu_a = float((lam + alpha_a * dlam_a) @ (s + alpha_a * ds_a)) / max(mi, 1)
+        sigma = (mu_a / mu) ** 3 if mu > 0 else 0.0
+        # corrector
+        dz, dnu, ds, dlam = newton(lam * s + ds_a * dlam_a - sigma * mu)
+        alpha_p = min(1.0, 0.995 * max_step(s, ds) if np.any(ds < 0) else 1.0)
+        alpha_d = min(1.0, 0.995 * max_step(lam, dlam) if np.any(dlam < 0) else 1.0)
+        alpha = min(alpha_p, alpha_d)
+        z = z + alpha * dz
+        nu = nu + alpha * dnu
+        s = s + alpha * ds
+        lam = lam + alpha * dlam
+
+    best = (z, nu, lam, False)
+    res = kkt_residuals(P, q, A, b, G, h, z, nu, lam)
+    try:
+        zp, nup, lamp = _polish(P, q, A, b, G, h, z, lam, s)
+        resp = kkt_residuals(P, q, A, b, G, h, zp, nup, lamp)
+        if max(resp.values()) < max(res.values()):
+            best, res = (zp, nup, lamp, True), resp
+    except np.linalg.LinAlgError:
+        pass
+    z, nu, lam, polished = best
+    obj = float(0.5 * z @ P @ z + q @ z + c0)
+    return QPResult(z=z, nu=nu, lam=lam, obj=obj, iters=it, polished=polished, kkt=res,
+                    ok=max(res.values()) <= tol)
