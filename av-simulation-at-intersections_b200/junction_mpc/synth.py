@@ -1,0 +1,152 @@
+"""Seeded synthetic workloads for the batched MPC step.
+
+Host-side numpy only; the same frozen inputs feed the CUDA path, the CPU oracle and the reference arm.
+A workload is a dict of numpy arrays in the layout the C ABI takes (include/jmpc.h):
+
+    state      [4, B] float64   rows x, y, v, yaw
+    course_id  [B]    int32     index into the course table
+    course_len [B]    int32     effective course length N' (prefix truncation, mpc_intersection.py:138)
+    target_ind [B]    int32     search start for the nearest-index rule
+    oa, od     [T, B] float64   previous solution = linearisation point (zeros when there is none)
+    params     [NPARAM, B] float64 or None   per-instance parameter overrides (config 5)
+    obstacles  [n_obs, 6, B] float64 or None (x, y, v, yaw, a, steer) for the flag kernel
+    agent_idx  [B] int32        ego index on the full course for the flag kernel
+
+The index-rule validity filter of the generator (instances for which trajectories.py:120 would raise are
+redrawn) is a pure numpy restatement of the 3-nearest rule and is part of input generation, not of the
+product path.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from .config import MPCConfig, PARAM_INDEX, NPARAM
+
+_COURSE_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "courses.npz")
+
+
+def smooth_yaw_inplace(yaw: np.ndarray) -> np.ndarray:
+    """Yaw unwrapping of the course (reference main/lib/mpc.py:46-58), done once per course on the host."""
+    for k in range(1, len(yaw)):
+        while yaw[k] - yaw[k - 1] >= math.pi / 2.0:
+            yaw[k] -= 2.0 * math.pi
+        while yaw[k] - yaw[k - 1] <= -math.pi / 2.0:
+            yaw[k] += 2.0 * math.pi
+    return yaw
+
+
+def load_course(name: str) -> np.ndarray:
+    """Planner output (N x 3 float64: x, y, yaw) of the reference's A* search for the three scenario families,
+    recorded by tests/golden/make_golden.py; yaw is returned smoothed, as MPC.__init__ leaves it."""
+    with np.load(_COURSE_FILE) as z:
+        c = np.array(z[name], dtype=np.float64)
+    smooth_yaw_inplace(c[:, 2])
+    return c
+
+
+def _index_rule_ok(x, y, cx, cy, start, n):
+    d = np.hypot(cx[start:n] - x, cy[start:n] - y)
+    if len(d) < 3:
+        return True
+    o = np.argsort(d, kind="stable")[:3]
+    return abs(int(o[1]) - int(o[2])) == 2 or abs(int(o[0]) - int(o[1])) == 1
+
+
+def make_states(rng, course: np.ndarray, B: int, T: int, cut_fraction: float = 0.3) -> Dict[str, np.ndarray]:
+    N = len(course)
+    state = np.zeros((4, B))
+    target = np.zeros(B, np.int32)
+    clen = np.zeros(B, np.int32)
+    agent = np.zeros(B, np.int32)
+    k = 0
+    while k < B:
+        s = int(rng.integers(0, N - 60))
+        x = course[s, 0] + rng.uniform(-0.5, 0.5)
+        y = course[s, 1] + rng.uniform(-0.5, 0.5)
+        yaw = course[s, 2] + rng.uniform(-0.1, 0.1)
+        v = rng.uniform(0.0, 30.0 / 3.6)
+        n = N if rng.random() >= cut_fraction else int(rng.integers(s + 2, min(N, s + 300) + 1))
+        t0 = max(s - 3, 0)
+        if not _index_rule_ok(x, y, course[:, 0], course[:, 1], t0, n):
+            continue
+        state[:, k] = (x, y, v, yaw)
+        target[k], clen[k], agent[k] = t0, n, s
+        k += 1
+    cold = rng.random(B) < 0.25
+    oa = rng.uniform(-1.0, 2.0, (T, B))
+    od = np.clip(np.cumsum(rng.uniform(-0.05, 0.05, (T, B)), axis=0) + rng.uniform(-0.2, 0.2, B), -0.7, 0.7)
+    oa[:, cold] = 0.0
+    od[:, cold] = 0.0
+    return dict(state=state, target_ind=target, course_len=clen, agent_idx=agent, oa=oa, od=od,
+                course_id=np.zeros(B, np.int32))
+
+
+def make_obstacles(rng, B: int, n_obs: int) -> np.ndarray:
+    obs = np.zeros((n_obs, 6, B))
+    obs[:, 0] = rng.uniform(-35, 35, (n_obs, B))
+    obs[:, 1] = rng.uniform(-35, 35, (n_obs, B))
+    obs[:, 2] = rng.uniform(0, 30 / 3.6, (n_obs, B))
+    obs[:, 3] = rng.uniform(-math.pi, math.pi, (n_obs, B))
+    obs[:, 5] = rng.uniform(-0.4, 0.4, (n_obs, B))
+    return obs
+
+
+def make_workload(config: int, B: Optional[int] = None, cfg: Optional[MPCConfig] = None) -> Dict[str, object]:
+    """Configs 2-5 of BASELINE.json (config 1 is the recorded golden episode under tests/golden/)."""
+    cfg = cfg or MPCConfig.default()
+    rng = np.random.default_rng(config)
+    if config == 2:
+        B = B or 4096
+        T = 20
+        course = load_course("intersection")
+        w = make_states(rng, course, B, T)
+        w.update(T=T, courses=[course], params=None, obstacles=None, frame_window=10, name="intersection_T20")
+    elif config in (3, 4):
+        B = B or (65536 if config == 3 else 262144)
+        T = 13
+        course = load_course("roundabout" if config == 3 else "multilane")
+        w = make_states(rng, course, B, T, cut_fraction=0.0)
+        w.update(T=T, courses=[course], params=None, obstacles=make_obstacles(rng, B, 2 if config == 3 else 4),
+                 frame_window=20, name="roundabout_T13" if config == 3 else "multilane_T13")
+    elif config == 5:
+        raise ValueError("config 5 is horizon-heterogeneous: use make_sweep()")
+    else:
+        raise ValueError(f"unknown config {config}")
+    w["dl"] = float(np.linalg.norm(w["courses"][0][0, :2] - w["courses"][0][1, :2]))
+    w["B"] = B
+    return w
+
+
+SWEEP_AXES = dict(
+    T=[8, 13, 20, 25], dt=[0.1, 0.2], w_perp=[1., 10., 20., 50.], w_para=[0.1, 1., 5., 10.],
+    R_acc=[.01, .1, 1., 10.], R_steer=[.01, .1, 1., 10.], Rd_acc=[1., 5., 10., 20.], Rd_steer=[.01, .1, 1., 10.])
+
+
+def make_sweep(T: int, states_per_point: int = 32, max_points: Optional[int] = None,
+               cfg: Optional[MPCConfig] = None, seed: int = 5) -> Dict[str, object]:
+    """Config 5 restricted to one horizon (each launch is horizon-homogeneous): the full factorial grid of
+    the reference's own sweep lists (mpc_sensitivity_analysis_comulative.py:103-128, zeros excluded) over
+    dt x w_perp x w_para x R x Rd, `states_per_point` random states per grid point."""
+    cfg = cfg or MPCConfig.default()
+    rng = np.random.default_rng(seed * 1000 + T)
+    axes = [SWEEP_AXES[k] for k in ["dt", "w_perp", "w_para", "R_acc", "R_steer", "Rd_acc", "Rd_steer"]]
+    grid = np.array(np.meshgrid(*axes, indexing="ij")).reshape(len(axes), -1)      # [7, 8192]
+    if max_points is not None and max_points < grid.shape[1]:
+        grid = grid[:, rng.choice(grid.shape[1], max_points, replace=False)]
+    P = grid.shape[1]
+    B = P * states_per_point
+    course = load_course("intersection")
+    w = make_states(rng, course, B, T)
+    base = cfg.with_T(T).param_vector(dl=float(np.linalg.norm(course[0, :2] - course[1, :2])), dt=0.2,
+                                      L=2.86, speed=30 / 3.6)
+    params = np.repeat(base[:, None], B, axis=1)
+    rep = np.repeat(grid, states_per_point, axis=1)
+    for row, key in zip(rep, ["dt", "w_perp", "w_para", "R_a", "R_d", "Rd_a", "Rd_d"]):
+        params[PARAM_INDEX[key]] = row
+    w.update(T=T, courses=[course], params=params, obstacles=None, frame_window=10, name=f"sweep_T{T}", B=B,
+             dl=float(base[PARAM_INDEX["dl"]]))
+    return w

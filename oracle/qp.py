@@ -50,7 +50,9 @@ def kkt_residuals(P, q, A, b, G, h, z, nu, lam) -> dict:
         p_scale = 1.0 + max(np.abs(Gz).max(initial=0.0), np.abs(h).max(initial=0.0))
         ineq = max(0.0, (-slack).max(initial=0.0)) / p_scale
         dual = max(0.0, (-lam).max(initial=0.0)) / s_scale
-        comp = np.abs(lam * slack).max(initial=0.0) / (p_scale * s_scale)
+        # per row, either the multiplier or the slack must vanish (a product would hide a wrong active set
+        # behind the cost scaling: with flat cost directions that costs digits in the controls)
+        comp = np.minimum(np.abs(lam) / s_scale, np.abs(slack) / p_scale).max(initial=0.0)
     return dict(stat=float(stat), eq=float(eq), ineq=float(ineq), dual=float(dual), comp=float(comp))
 
 
@@ -68,22 +70,20 @@ def _solve_sym(K, rhs):
     return x
 
 
-def _polish(P, q, A, b, G, h, z, lam, s):
-    """Solve the equality-constrained QP on the active set {i : lam_i > s_i}."""
+def _eqp(P, q, A, b, G, h, act):
+    """Solve the equality-constrained QP with the inequality rows `act` held at their bounds."""
     n = P.shape[0]
-    act = np.nonzero(lam > s)[0]
-    Ga = G[act]
-    # drop active rows that are linearly dependent on [A; previously kept rows]
+    # drop active rows that are linearly dependent on [A; rows kept so far]
     keep = []
     basis = A.copy() if A.size else np.zeros((0, n))
     rank = np.linalg.matrix_rank(basis) if basis.size else 0
-    for k, row in enumerate(Ga):
-        trial = np.vstack([basis, row[None, :]])
+    for k in act:
+        trial = np.vstack([basis, G[k][None, :]])
         r2 = np.linalg.matrix_rank(trial)
         if r2 > rank:
             basis, rank = trial, r2
             keep.append(k)
-    act = act[keep]
+    act = np.array(keep, dtype=int)
     Ga = G[act]
     me, ma = A.shape[0], len(act)
     K = np.zeros((n + me + ma, n + me + ma))
@@ -99,6 +99,26 @@ def _polish(P, q, A, b, G, h, z, lam, s):
     lamp = np.zeros(G.shape[0])
     lamp[act] = sol[n + me:]
     return zp, nup, lamp
+
+
+def _polish(P, q, A, b, G, h, z, lam, s, rounds: int = 25):
+    """Active-set refinement started from the interior-point guess {i : lam_i > s_i}: solve the
+    equality-constrained problem, add the violated rows, drop rows whose multiplier came out negative,
+    repeat until the set is stable (a primal-dual active-set iteration)."""
+    act = set(np.nonzero(lam > s)[0].tolist())
+    best = None
+    for _ in range(rounds):
+        zp, nup, lamp = _eqp(P, q, A, b, G, h, sorted(act))
+        slack = h - G @ zp
+        scale = 1.0 + np.abs(h).max(initial=0.0)
+        lscale = 1.0 + np.abs(lamp).max(initial=0.0)
+        add = set(np.nonzero(slack < -1e-12 * scale)[0].tolist()) - act
+        drop = {k for k in act if lamp[k] < -1e-12 * lscale}
+        best = (zp, nup, lamp)
+        if not add and not drop:
+            break
+        act = (act | add) - drop
+    return best
 
 
 def solve_qp(P, q, A, b, G, h, c0: float = 0.0, tol: float = 1e-9, max_iter: int = 60) -> QPResult:
@@ -136,7 +156,7 @@ def solve_qp(P, q, A, b, G, h, c0: float = 0.0, tol: float = 1e-9, max_iter: int
         scale_d = 1.0 + max(np.abs(q).max(initial=0.0), np.abs(P @ z).max(initial=0.0))
         scale_p = 1.0 + np.abs(h).max(initial=0.0)
         if (np.abs(r_d).max(initial=0.0) <= 1e-11 * scale_d and np.abs(r_e).max(initial=0.0) <= 1e-11 * scale_p
-                and np.abs(r_p).max(initial=0.0) <= 1e-11 * scale_p and mu <= 1e-13 * scale_d * scale_p):
+                and np.abs(r_p).max(initial=0.0) <= 1e-11 * scale_p and mu <= 1e-13):
             break
         W = lam / s
 
