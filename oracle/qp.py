@@ -16,6 +16,12 @@ from __future__ import annotations
 from dataclasses import dataclass
 
 import numpy as np
+from scipy.linalg import lu_factor, lu_solve
+
+try:
+    from threadpoolctl import threadpool_limits as _limits
+except Exception:          # pragma: no cover
+    _limits = None
 
 
 @dataclass
@@ -73,17 +79,7 @@ def _solve_sym(K, rhs):
 def _eqp(P, q, A, b, G, h, act):
     """Solve the equality-constrained QP with the inequality rows `act` held at their bounds."""
     n = P.shape[0]
-    # drop active rows that are linearly dependent on [A; rows kept so far]
-    keep = []
-    basis = A.copy() if A.size else np.zeros((0, n))
-    rank = np.linalg.matrix_rank(basis) if basis.size else 0
-    for k in act:
-        trial = np.vstack([basis, G[k][None, :]])
-        r2 = np.linalg.matrix_rank(trial)
-        if r2 > rank:
-            basis, rank = trial, r2
-            keep.append(k)
-    act = np.array(keep, dtype=int)
+    act = np.array(sorted(act), dtype=int)
     Ga = G[act]
     me, ma = A.shape[0], len(act)
     K = np.zeros((n + me + ma, n + me + ma))
@@ -92,8 +88,17 @@ def _eqp(P, q, A, b, G, h, act):
     K[n:n + me, :n] = A
     K[:n, n + me:] = Ga.T
     K[n + me:, :n] = Ga
+    # a tiny dual regularisation keeps the system solvable when active rows are linearly dependent
+    # (e.g. a steer box and the neighbouring rate rows); refinement against the unregularised matrix
+    # removes its effect on the primal solution
+    Kreg = K.copy()
+    idx = np.arange(n, n + me + ma)
+    Kreg[idx, idx] -= 1e-10
     rhs = np.concatenate([-q, b, h[act]])
-    sol = _solve_sym(K, rhs)
+    lu = lu_factor(Kreg, check_finite=False)
+    sol = lu_solve(lu, rhs, check_finite=False)
+    for _ in range(3):
+        sol = sol + lu_solve(lu, rhs - K @ sol, check_finite=False)
     zp = sol[:n]
     nup = sol[n:n + me]
     lamp = np.zeros(G.shape[0])
@@ -122,6 +127,14 @@ def _polish(P, q, A, b, G, h, z, lam, s, rounds: int = 25):
 
 
 def solve_qp(P, q, A, b, G, h, c0: float = 0.0, tol: float = 1e-9, max_iter: int = 60) -> QPResult:
+    # the matrices are ~200 x 200: multi-threaded BLAS only adds contention (10-20x slower here)
+    if _limits is not None:
+        with _limits(limits=1):
+            return _solve_qp(P, q, A, b, G, h, c0, tol, max_iter)
+    return _solve_qp(P, q, A, b, G, h, c0, tol, max_iter)
+
+
+def _solve_qp(P, q, A, b, G, h, c0, tol, max_iter) -> QPResult:
     P = np.asarray(P, float)
     q = np.asarray(q, float)
     n = P.shape[0]
@@ -131,17 +144,22 @@ def solve_qp(P, q, A, b, G, h, c0: float = 0.0, tol: float = 1e-9, max_iter: int
     h = np.asarray(h, float).reshape(-1)
     me, mi = A.shape[0], G.shape[0]
 
-    def aug_solve(W, r1, r2):
-        H = P + G.T @ (W[:, None] * G)
+    def aug_factor(W):
         K = np.zeros((n + me, n + me))
-        K[:n, :n] = H
+        K[:n, :n] = P + G.T @ (W[:, None] * G)
         K[:n, n:] = A.T
         K[n:, :n] = A
-        sol = _solve_sym(K, np.concatenate([r1, r2]))
+        return K, lu_factor(K, check_finite=False)
+
+    def aug_solve(fac, r1, r2):
+        K, lu = fac
+        rhs = np.concatenate([r1, r2])
+        sol = lu_solve(lu, rhs, check_finite=False)
+        sol = sol + lu_solve(lu, rhs - K @ sol, check_finite=False)      # one refinement step
         return sol[:n], sol[n:]
 
     # --- initial point: equality-constrained least-squares start, slacks/multipliers pushed interior
-    z, nu = aug_solve(np.ones(mi), -q + G.T @ h, b)
+    z, nu = aug_solve(aug_factor(np.ones(mi)), -q + G.T @ h, b)
     s = h - G @ z
     shift = max(0.0, -s.min(initial=0.0)) + 1.0 if (s.min(initial=1.0) <= 1e-8) else 0.0
     s = s + shift
@@ -158,11 +176,11 @@ def solve_qp(P, q, A, b, G, h, c0: float = 0.0, tol: float = 1e-9, max_iter: int
         if (np.abs(r_d).max(initial=0.0) <= 1e-11 * scale_d and np.abs(r_e).max(initial=0.0) <= 1e-11 * scale_p
                 and np.abs(r_p).max(initial=0.0) <= 1e-11 * scale_p and mu <= 1e-13):
             break
-        W = lam / s
+        fac = aug_factor(lam / s)
 
         def newton(r_c):
             t = (-r_c + lam * r_p) / s
-            dz, dnu = aug_solve(W, -r_d - G.T @ t, -r_e)
+            dz, dnu = aug_solve(fac, -r_d - G.T @ t, -r_e)
             ds = -r_p - G @ dz
             dlam = (-r_c - lam * ds) / s
             return dz, dnu, ds, dlam
