@@ -1,0 +1,467 @@
+// jmpc.cu -- C ABI of libjmpc.so (see include/jmpc.h): handle management, launches, host staging.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/jmpc.h"
+#include "jmpc_collision.cuh"
+#include "jmpc_step.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof buf, "%s", what);
+  g_err = buf;
+  return -1;
+}
+
+#define CK(call)                                          \
+  do {                                                    \
+    cudaError_t e_ = (call);                              \
+    if (e_ != cudaSuccess) return fail(#call, e_);        \
+  } while (0)
+
+}  // namespace
+
+struct jmpc_handle_s {
+  int device = 0;
+  int max_B = 0, max_T = 0, max_N = 0, max_courses = 0;
+  int sm_count = 0;
+  jmpc_options opt{};
+  double defaults[JMPC_NPARAM];
+  // courses
+  double *d_cx = nullptr, *d_cy = nullptr, *d_cyaw = nullptr;
+  double *d_ccfx = nullptr, *d_ccfy = nullptr, *d_ccrx = nullptr, *d_ccry = nullptr;   // collision-circle tables
+  double off_front = 2.86 / 2 + (3.5 / 2 - 1.0), off_rear = 2.86 / 2 - (3.5 / 2 - 1.0), radius = 2.0 / 1.4142135623730951;
+  int* d_course_n = nullptr;
+  int n_courses = 0, course_stride = 0;
+  std::vector<int> course_n;
+  // solver scratch
+  double* d_pscratch = nullptr;
+  size_t pscratch_doubles = 0;
+  unsigned int* d_counter = nullptr;
+  // staging for the *_host entry points
+  char* d_stage = nullptr; size_t d_stage_bytes = 0;
+  char* h_stage = nullptr; size_t h_stage_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+
+// launch geometry of the step kernel for horizon T
+struct StepGeom { int blocks, threads; size_t smem; int warps; };
+
+int step_geometry(jmpc_handle h, int B, int T, StepGeom* g) {
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * jmpc::warp_smem_doubles(T) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(jmpc::mpc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jmpc::mpc_step_kernel, wpb * 32, smem));
+  if (per_sm < 1) return fail("step kernel does not fit on an SM for this horizon");
+  if (h->opt.warps_per_sm > 0) per_sm = std::max(1, std::min(per_sm, h->opt.warps_per_sm / wpb));
+  int blocks = h->sm_count * per_sm;
+  const int need = (B + wpb - 1) / wpb;
+  if (blocks > need) blocks = need;
+  g->blocks = blocks; g->threads = wpb * 32; g->smem = smem; g->warps = blocks * wpb;
+  return 0;
+}
+
+int ensure_scratch(jmpc_handle h, size_t doubles) {
+  if (doubles <= h->pscratch_doubles) return 0;
+  if (h->d_pscratch) cudaFree(h->d_pscratch);
+  h->d_pscratch = nullptr; h->pscratch_doubles = 0;
+  CK(cudaMalloc(&h->d_pscratch, doubles * sizeof(double)));
+  h->pscratch_doubles = doubles;
+  return 0;
+}
+
+int ensure_stage(jmpc_handle h, size_t bytes) {
+  if (bytes > h->d_stage_bytes) {
+    if (h->d_stage) cudaFree(h->d_stage);
+    h->d_stage = nullptr; h->d_stage_bytes = 0;
+    CK(cudaMalloc(&h->d_stage, bytes));
+    h->d_stage_bytes = bytes;
+  }
+  if (bytes > h->h_stage_bytes) {
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr; h->h_stage_bytes = 0;
+    CK(cudaMallocHost(&h->h_stage, bytes));
+    h->h_stage_bytes = bytes;
+  }
+  return 0;
+}
+
+// ---- small kernels that live here -----------------------------------------------------------------------
+
+// Simulation.step (simulation.py:35-47) + Bicycle.step (bicycle/main.py:28-41), one thread per instance.
+__global__ void plant_step_kernel(int B, double* __restrict__ state, const double* __restrict__ a,
+                                  const double* __restrict__ delta, const double* __restrict__ params,
+                                  jmpc::ParamBlock defaults) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* prm = params ? params + (size_t)b * JMPC_NPARAM : defaults.v;
+  const double dt = prm[JMPC_P_DT], L = prm[JMPC_P_L], ms = prm[JMPC_P_MAX_STEER];
+  double x = state[4 * b], y = state[4 * b + 1], v = state[4 * b + 2], yaw = state[4 * b + 3];
+  const double d = fmax(fmin(delta[b], ms), -ms);
+  const double xd = __dmul_rn(v, cos(yaw)), yd = __dmul_rn(v, sin(yaw)), td = __dmul_rn(v / L, tan(d));
+  x = __dadd_rn(x, __dmul_rn(xd, dt));
+  y = __dadd_rn(y, __dmul_rn(yd, dt));
+  yaw = __dadd_rn(yaw, __dmul_rn(td, dt));
+  v = __dadd_rn(v, __dmul_rn(a[b], dt));
+  v = fmax(fmin(v, prm[JMPC_P_SIM_MAX_SPEED]), prm[JMPC_P_MIN_SPEED]);
+  state[4 * b] = x; state[4 * b + 1] = y; state[4 * b + 2] = v; state[4 * b + 3] = yaw;
+}
+
+int refresh_circle_tables(jmpc_handle h) {
+  CK(cudaSetDevice(h->device));
+  for (int c = 0; c < h->n_courses; ++c) {
+    const size_t off = (size_t)c * h->course_stride;
+    const int n = h->course_n[c];
+    jmpc::circle_table_kernel<<<(n + 127) / 128, 128, 0, h->own_stream>>>(
+        n, h->d_cx + off, h->d_cy + off, h->d_cyaw + off, h->off_front, h->off_rear, h->d_ccfx + off,
+        h->d_ccfy + off, h->d_ccrx + off, h->d_ccry + off);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
+  CK(cudaStreamSynchronize(h->own_stream));
+  return 0;
+}
+
+template <typename F>
+__global__ void fma_peak_kernel(F* out, int iters) {
+  F a0 = (F)threadIdx.x * (F)1e-3, a1 = a0 + (F)1, a2 = a0 + (F)2, a3 = a0 + (F)3;
+  F a4 = a0 + (F)4, a5 = a0 + (F)5, a6 = a0 + (F)6, a7 = a0 + (F)7;
+  const F m = (F)0.999, c = (F)1e-3;
+  for (int i = 0; i < iters; ++i) {
+    a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+    a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+template <typename F>
+int measure_fma(jmpc_handle h, double* tflops) {
+  const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 14;
+  F* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(F)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0, h->own_stream));
+    fma_peak_kernel<F><<<blocks, threads, 0, h->own_stream>>>(d, iters);
+    CK(cudaEventRecord(e1, h->own_stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    h->launches++;
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t jmpc_abi_version(void) { return JMPC_ABI_VERSION; }
+int32_t jmpc_nparam(void) { return JMPC_NPARAM; }
+const char* jmpc_last_error(void) { return g_err.c_str(); }
+
+int32_t jmpc_create(int32_t device, int32_t max_B, int32_t max_T, int32_t max_N, int32_t max_courses,
+                    const double* default_params, const jmpc_options* options, jmpc_handle* out) {
+  if (!out) return fail("jmpc_create: out is NULL");
+  *out = nullptr;
+  if (max_T < 2 || max_T > JMPC_MAX_T) return fail("jmpc_create: max_T must be in [2, JMPC_MAX_T]");
+  if (max_B < 1 || max_N < 1 || max_courses < 1) return fail("jmpc_create: sizes must be positive");
+  if (!default_params) return fail("jmpc_create: default_params is NULL");
+  int count = 0;
+  CK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail("jmpc_create: no such CUDA device");
+  CK(cudaSetDevice(device));
+  jmpc_handle h = new (std::nothrow) jmpc_handle_s();
+  if (!h) return fail("jmpc_create: out of host memory");
+  h->device = device; h->max_B = max_B; h->max_T = max_T; h->max_N = max_N; h->max_courses = max_courses;
+  h->opt.max_solver_iters = 40; h->opt.linearisation_iters = 1; h->opt.mu_tol = 1e-13; h->opt.warps_per_sm = 0;
+  if (options) {
+    if (options->max_solver_iters > 0) h->opt.max_solver_iters = options->max_solver_iters;
+    if (options->linearisation_iters > 0) h->opt.linearisation_iters = options->linearisation_iters;
+    if (options->mu_tol > 0) h->opt.mu_tol = options->mu_tol;
+    if (options->warps_per_sm > 0) h->opt.warps_per_sm = options->warps_per_sm;
+  }
+  memcpy(h->defaults, default_params, sizeof h->defaults);
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete h; return fail("cudaGetDeviceProperties", e); }
+  h->sm_count = prop.multiProcessorCount;
+  h->course_stride = max_N;
+  const size_t cbytes = (size_t)max_courses * max_N * sizeof(double);
+  if ((e = cudaMalloc(&h->d_cx, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_cy, cbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_cyaw, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_ccfx, cbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_ccfy, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_ccrx, cbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_ccry, cbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_course_n, max_courses * sizeof(int))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_counter, 64)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    jmpc_destroy(h);
+    return fail("jmpc_create: device allocation failed", e);
+  }
+  *out = h;
+  return 0;
+}
+
+int32_t jmpc_destroy(jmpc_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_cx); cudaFree(h->d_cy); cudaFree(h->d_cyaw); cudaFree(h->d_course_n);
+  cudaFree(h->d_ccfx); cudaFree(h->d_ccfy); cudaFree(h->d_ccrx); cudaFree(h->d_ccry);
+  cudaFree(h->d_pscratch); cudaFree(h->d_counter); cudaFree(h->d_stage);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int32_t jmpc_set_default_params(jmpc_handle h, const double* p) {
+  if (!h || !p) return fail("jmpc_set_default_params: NULL argument");
+  memcpy(h->defaults, p, sizeof h->defaults);
+  return 0;
+}
+
+int32_t jmpc_set_courses(jmpc_handle h, int32_t n_courses, int32_t stride, const int32_t* len, const double* cx,
+                         const double* cy, const double* cyaw) {
+  if (!h || !len || !cx || !cy || !cyaw) return fail("jmpc_set_courses: NULL argument");
+  if (n_courses < 1 || n_courses > h->max_courses) return fail("jmpc_set_courses: n_courses out of range");
+  CK(cudaSetDevice(h->device));
+  h->course_n.assign(len, len + n_courses);
+  for (int c = 0; c < n_courses; ++c) {
+    if (len[c] < 1 || len[c] > h->max_N || len[c] > stride) return fail("jmpc_set_courses: course length out of range");
+    const size_t off = (size_t)c * h->course_stride, src = (size_t)c * stride, nb = (size_t)len[c] * sizeof(double);
+    CK(cudaMemcpy(h->d_cx + off, cx + src, nb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_cy + off, cy + src, nb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_cyaw + off, cyaw + src, nb, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(h->d_course_n, len, n_courses * sizeof(int), cudaMemcpyHostToDevice));
+  h->n_courses = n_courses;
+  return refresh_circle_tables(h);
+}
+
+int32_t jmpc_set_car_geometry(jmpc_handle h, double front_offset, double rear_offset, double radius) {
+  if (!h) return fail("jmpc_set_car_geometry: NULL handle");
+  if (!(radius > 0)) return fail("jmpc_set_car_geometry: radius must be positive");
+  h->off_front = front_offset; h->off_rear = rear_offset; h->radius = radius;
+  return h->n_courses ? refresh_circle_tables(h) : 0;
+}
+
+int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
+                  const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa, double* od,
+                  const double* params, double* ox, double* oy, double* ov, double* oyaw, double* xref,
+                  double* cost, int32_t* status, int32_t* iters, void* stream) {
+  if (!h) return fail("jmpc_step: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_step: B out of range");
+  if (T < 2 || T > h->max_T) return fail("jmpc_step: T out of range");
+  if (!state || !target_ind || !oa || !od || !ox || !oy || !ov || !oyaw || !xref || !cost || !status)
+    return fail("jmpc_step: NULL array");
+  if (h->n_courses < 1) return fail("jmpc_step: no courses uploaded (jmpc_set_courses)");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  StepGeom g;
+  if (step_geometry(h, B, T, &g)) return -1;
+  const int n = 2 * T;
+  if (ensure_scratch(h, (size_t)g.warps * (n * (n + 1) / 2))) return -1;
+  jmpc::StepArgs a;
+  a.B = B; a.T = T; a.lin_iters = h->opt.linearisation_iters; a.max_iters = h->opt.max_solver_iters;
+  a.mu_tol = h->opt.mu_tol;
+  a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
+  a.course_stride = h->course_stride; a.n_courses = h->n_courses;
+  a.state = state; a.course_id = course_id; a.course_len = course_len; a.warm = warm; a.params = params;
+  memcpy(a.defaults, h->defaults, sizeof a.defaults);
+  a.target_ind = target_ind; a.oa = oa; a.od = od; a.ox = ox; a.oy = oy; a.ov = ov; a.oyaw = oyaw; a.xref = xref;
+  a.cost = cost; a.status = status; a.iters = iters;
+  a.pscratch = h->d_pscratch; a.counter = h->d_counter;
+  CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
+  jmpc::mpc_step_kernel<<<g.blocks, g.threads, g.smem, s>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
+                       const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
+                       double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
+                       double* xref, double* cost, int32_t* status, int32_t* iters) {
+  if (!h) return fail("jmpc_step_host: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_step_host: B out of range");
+  if (T < 2 || T > h->max_T) return fail("jmpc_step_host: T out of range");
+  if (!state || !target_ind || !oa || !od || !ox || !oy || !ov || !oyaw || !xref || !cost || !status)
+    return fail("jmpc_step_host: NULL array");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  const size_t T1 = T + 1, b = (size_t)B;
+  // one contiguous staging block: [inputs | in-out | outputs], 8-byte fields first
+  struct Seg { size_t off, bytes; };
+  size_t off = 0;
+  auto seg = [&](size_t bytes) { Seg s{off, bytes}; off += (bytes + 15) & ~size_t(15); return s; };
+  const Seg s_state = seg(b * 4 * 8), s_params = seg(params ? b * JMPC_NPARAM * 8 : 0);
+  const Seg s_cid = seg(course_id ? b * 4 : 0), s_clen = seg(course_len ? b * 4 : 0), s_warm = seg(warm ? b * 4 : 0);
+  const size_t in_end = off;
+  const Seg s_oa = seg(b * T * 8), s_od = seg(b * T * 8), s_tgt = seg(b * 4);
+  const size_t inout_end = off;
+  const Seg s_ox = seg(b * T1 * 8), s_oy = seg(b * T1 * 8), s_ov = seg(b * T1 * 8), s_oyaw = seg(b * T1 * 8);
+  const Seg s_xref = seg(b * 4 * T1 * 8), s_cost = seg(b * 8), s_status = seg(b * 4), s_iters = seg(b * 4);
+  const size_t total = off;
+  if (ensure_stage(h, total)) return -1;
+  char* hs = h->h_stage; char* ds = h->d_stage;
+  memcpy(hs + s_state.off, state, s_state.bytes);
+  if (params) memcpy(hs + s_params.off, params, s_params.bytes);
+  if (course_id) memcpy(hs + s_cid.off, course_id, s_cid.bytes);
+  if (course_len) memcpy(hs + s_clen.off, course_len, s_clen.bytes);
+  if (warm) memcpy(hs + s_warm.off, warm, s_warm.bytes);
+  memcpy(hs + s_oa.off, oa, s_oa.bytes);
+  memcpy(hs + s_od.off, od, s_od.bytes);
+  memcpy(hs + s_tgt.off, target_ind, s_tgt.bytes);
+  (void)in_end;
+  cudaStream_t st = h->own_stream;
+  CK(cudaMemcpyAsync(ds, hs, inout_end, cudaMemcpyHostToDevice, st));
+  int rc = jmpc_step(h, B, T, (const double*)(ds + s_state.off), course_id ? (const int*)(ds + s_cid.off) : nullptr,
+                     course_len ? (const int*)(ds + s_clen.off) : nullptr, (int*)(ds + s_tgt.off),
+                     warm ? (const int*)(ds + s_warm.off) : nullptr, (double*)(ds + s_oa.off), (double*)(ds + s_od.off),
+                     params ? (const double*)(ds + s_params.off) : nullptr, (double*)(ds + s_ox.off),
+                     (double*)(ds + s_oy.off), (double*)(ds + s_ov.off), (double*)(ds + s_oyaw.off),
+                     (double*)(ds + s_xref.off), (double*)(ds + s_cost.off), (int*)(ds + s_status.off),
+                     (int*)(ds + s_iters.off), (void*)st);
+  if (rc) return rc;
+  // results: everything from the in-out block to the end.  Instances that fail the index rule or are
+  // infeasible keep their input values in the in-out block, so copying it back wholesale is safe.
+  CK(cudaMemcpyAsync(hs + s_oa.off, ds + s_oa.off, total - s_oa.off, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(oa, hs + s_oa.off, s_oa.bytes);
+  memcpy(od, hs + s_od.off, s_od.bytes);
+  memcpy(target_ind, hs + s_tgt.off, s_tgt.bytes);
+  memcpy(ox, hs + s_ox.off, s_ox.bytes); memcpy(oy, hs + s_oy.off, s_oy.bytes);
+  memcpy(ov, hs + s_ov.off, s_ov.bytes); memcpy(oyaw, hs + s_oyaw.off, s_oyaw.bytes);
+  memcpy(xref, hs + s_xref.off, s_xref.bytes);
+  memcpy(cost, hs + s_cost.off, s_cost.bytes);
+  memcpy(status, hs + s_status.off, s_status.bytes);
+  if (iters) memcpy(iters, hs + s_iters.off, s_iters.bytes);
+  return 0;
+}
+
+int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const int32_t* agent_idx,
+                       const double* v, const double* obstacles, int32_t n_obs, int32_t frame_window,
+                       int32_t margin, double horizon_s, const double* params, int32_t* flag,
+                       int32_t* course_len_out, void* stream) {
+  if (!h) return fail("jmpc_collision: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_collision: B out of range");
+  if (!agent_idx || !v || !flag || !course_len_out) return fail("jmpc_collision: NULL array");
+  if (n_obs < 0 || n_obs > jmpc::kMaxObstacles) return fail("jmpc_collision: n_obs out of range");
+  if (n_obs > 0 && !obstacles) return fail("jmpc_collision: obstacles is NULL");
+  if (frame_window < 0 || frame_window > jmpc::kMaxFrameWindow) return fail("jmpc_collision: frame_window out of range");
+  if (h->n_courses < 1) return fail("jmpc_collision: no courses uploaded (jmpc_set_courses)");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  jmpc::CollisionArgs a;
+  a.B = B; a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
+  a.ccfx = h->d_ccfx; a.ccfy = h->d_ccfy; a.ccrx = h->d_ccrx; a.ccry = h->d_ccry;
+  a.off_front = h->off_front; a.off_rear = h->off_rear; a.radius = h->radius; a.arc_cap = h->max_N;
+  a.course_stride = h->course_stride; a.course_id = course_id; a.agent_idx = agent_idx; a.v = v;
+  a.obstacles = obstacles; a.n_obs = n_obs; a.frame_window = frame_window; a.margin = margin;
+  a.horizon_s = horizon_s; a.params = params;
+  memcpy(a.defaults.v, h->defaults, sizeof h->defaults);
+  a.flag = flag; a.course_len_out = course_len_out;
+  const int wpb = 4;
+  const int blocks = (B + wpb - 1) / wpb;
+  const size_t smem = wpb * jmpc::collision_warp_smem_bytes(h->max_N, n_obs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(jmpc::collision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return fail("jmpc_collision: course too long for the shared-memory arc scan");
+  jmpc::collision_kernel<<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int32_t jmpc_collision_host(jmpc_handle h, int32_t B, const int32_t* course_id, const int32_t* agent_idx,
+                            const double* v, const double* obstacles, int32_t n_obs, int32_t frame_window,
+                            int32_t margin, double horizon_s, const double* params, int32_t* flag,
+                            int32_t* course_len_out) {
+  if (!h) return fail("jmpc_collision_host: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_collision_host: B out of range");
+  if (!agent_idx || !v || !flag || !course_len_out) return fail("jmpc_collision_host: NULL array");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  const size_t b = (size_t)B;
+  size_t off = 0;
+  auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+  const size_t o_v = seg(b * 8), o_obs = seg(b * n_obs * 6 * 8), o_prm = seg(params ? b * JMPC_NPARAM * 8 : 0);
+  const size_t o_cid = seg(course_id ? b * 4 : 0), o_idx = seg(b * 4);
+  const size_t in_end = off;
+  const size_t o_flag = seg(b * 4), o_len = seg(b * 4);
+  if (ensure_stage(h, off)) return -1;
+  char* hs = h->h_stage; char* ds = h->d_stage;
+  memcpy(hs + o_v, v, b * 8);
+  if (n_obs) memcpy(hs + o_obs, obstacles, b * n_obs * 6 * 8);
+  if (params) memcpy(hs + o_prm, params, b * JMPC_NPARAM * 8);
+  if (course_id) memcpy(hs + o_cid, course_id, b * 4);
+  memcpy(hs + o_idx, agent_idx, b * 4);
+  cudaStream_t st = h->own_stream;
+  CK(cudaMemcpyAsync(ds, hs, in_end, cudaMemcpyHostToDevice, st));
+  int rc = jmpc_collision(h, B, course_id ? (const int*)(ds + o_cid) : nullptr, (const int*)(ds + o_idx),
+                          (const double*)(ds + o_v), (const double*)(ds + o_obs), n_obs, frame_window, margin,
+                          horizon_s, params ? (const double*)(ds + o_prm) : nullptr, (int*)(ds + o_flag),
+                          (int*)(ds + o_len), (void*)st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(hs + o_flag, ds + o_flag, off - o_flag, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(flag, hs + o_flag, b * 4);
+  memcpy(course_len_out, hs + o_len, b * 4);
+  return 0;
+}
+
+int32_t jmpc_plant_step(jmpc_handle h, int32_t B, double* state, const double* a, const double* delta,
+                        const double* params, void* stream) {
+  if (!h) return fail("jmpc_plant_step: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_plant_step: B out of range");
+  if (!state || !a || !delta) return fail("jmpc_plant_step: NULL array");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  jmpc::ParamBlock d;
+  memcpy(d.v, h->defaults, sizeof h->defaults);
+  plant_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, state, a, delta, params, d);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int64_t jmpc_launch_count(jmpc_handle h) { return h ? h->launches : 0; }
+
+int32_t jmpc_measure_fma_peak(jmpc_handle h, double* fp64_tflops, double* fp32_tflops) {
+  if (!h || !fp64_tflops || !fp32_tflops) return fail("jmpc_measure_fma_peak: NULL argument");
+  CK(cudaSetDevice(h->device));
+  if (measure_fma<double>(h, fp64_tflops)) return -1;
+  if (measure_fma<float>(h, fp32_tflops)) return -1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,694 @@
+// jmpc_step.cuh -- the fused MPC-step kernel: one warp owns one instance.
+//
+// Pipeline per instance (reference lines relative to SaeedRahmani/AV-Simulation-at-Intersections):
+//   1. nearest forward index on the course        main/lib/trajectories.py:100-126
+//   2. reference sampling xref / reaches_end      main/lib/mpc.py:89-112
+//   3. operating-point rollout xbar               main/lib/mpc.py:115-129, main/lib/simulation.py:35-47,
+//                                                 main/bicycle/main.py:28-41
+//   4. linearisation + exact condensing           main/lib/mpc.py:61-82,132-138,151-194  (states eliminated)
+//   5. QP solve: Mehrotra predictor-corrector interior point on the n = 2T condensed problem; the normal
+//      matrix K = P + A' diag(w) A lives in shared memory, its Cholesky factor overwrites it in place
+//      (replaces cvxpy + ECOS, mpc.py:196-197)
+//   6. outputs: controls, predicted states, cost, status             main/lib/mpc.py:199-209
+//
+// All arithmetic is float64: the index decisions (rint, 3-nearest rule) must match numpy bit for bit, and
+// the condensed Hessians have cond ~1e6..1e7, far outside what fp32 factors resolve
+// at the 1e-4 control tolerance.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/jmpc.h"
+
+namespace jmpc {
+
+constexpr int kMaxT = JMPC_MAX_T;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct StepArgs {
+  int B, T;
+  int lin_iters;            // MAX_ITER of the reference config
+  int max_iters;            // interior-point iteration cap
+  double mu_tol;
+  // course tables
+  const double* cx; const double* cy; const double* cyaw;
+  const int* course_n; int course_stride; int n_courses;
+  // inputs
+  const double* state; const int* course_id; const int* course_len; const int* warm;
+  const double* params;     // [B][NPARAM] or nullptr
+  double defaults[JMPC_NPARAM];
+  // in-out / outputs
+  int* target_ind; double* oa; double* od;
+  double* ox; double* oy; double* ov; double* oyaw; double* xref; double* cost; int* status; int* iters;
+  // scratch
+  double* pscratch;         // [resident warps][n(n+1)/2] condensed Hessian, L2 resident
+  unsigned int* counter;    // dynamic work queue
+};
+
+// shared-memory doubles one warp needs for horizon T
+__host__ __device__ inline int warp_smem_doubles(int T) {
+  const int n = 2 * T;
+  return n * (n + 1) / 2        // K / L packed lower, row major
+         + 5 * n                // invd, u, q, rhs, grad
+         + 4 * (T + 1)          // prefix sums ca, cb, cc, ck
+         + 5 * (T + 1)          // stage weights W11, W12, W22, qv, qpsi
+         + 3 * (T + 1)          // WeX, WeY, epsi
+         + 4 * T                // per-iteration row weights wA, wD, wR, SW
+         + 2;                   // pad
+}
+
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+// inclusive prefix sum over lanes 0..31
+__device__ __forceinline__ double warp_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+// inclusive suffix sum: out[lane] = sum_{l >= lane} v[l]
+__device__ __forceinline__ double warp_rscan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_down_sync(kFull, v, o);
+    if (lane + o < 32) v += t;
+  }
+  return v;
+}
+
+// ---- candidate list for the 3-nearest rule: ascending by (d2, index) --------------------------------
+struct Near3 {
+  double d0, d1, d2; int i0, i1, i2;
+};
+__device__ __forceinline__ bool closer(double da, int ia, double db, int ib) {
+  return (da < db) || (da == db && ia < ib);
+}
+__device__ __forceinline__ void near3_insert(Near3& s, double d, int i) {
+  if (closer(d, i, s.d2, s.i2)) {
+    if (closer(d, i, s.d1, s.i1)) {
+      s.d2 = s.d1; s.i2 = s.i1;
+      if (closer(d, i, s.d0, s.i0)) { s.d1 = s.d0; s.i1 = s.i0; s.d0 = d; s.i0 = i; }
+      else { s.d1 = d; s.i1 = i; }
+    } else { s.d2 = d; s.i2 = i; }
+  }
+}
+
+// Nearest forward index (trajectories.py:100-126).  Returns -1 when the rule raises.
+// Distances are compared squared (monotone in the reference's sqrt); products are kept unfused so the
+// ordering matches numpy's dx*dx + dy*dy.  Ties break towards the lower index.
+__device__ inline int nearest_index(const double* __restrict__ cx, const double* __restrict__ cy, int n_course,
+                                    int start, double x, double y, int lane) {
+  const int m = n_course - start;
+  if (m <= 1) return start;
+  if (m == 2) return start + 1;
+  Near3 s;
+  s.d0 = s.d1 = s.d2 = INFINITY;
+  s.i0 = s.i1 = s.i2 = 0x7fffffff;
+  for (int j = start + lane; j < n_course; j += 32) {
+    const double ex = cx[j] - x, ey = cy[j] - y;
+    const double d = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+    near3_insert(s, d, j - start);
+  }
+  int res[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    // global best among the lanes' heads
+    double bd = s.d0; int bi = s.i0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(kFull, bd, o);
+      const int oi = __shfl_xor_sync(kFull, bi, o);
+      if (closer(od, oi, bd, bi)) { bd = od; bi = oi; }
+    }
+    res[r] = bi;
+    if (s.i0 == bi) {   // the owner pops its head
+      s.d0 = s.d1; s.i0 = s.i1; s.d1 = s.d2; s.i1 = s.i2; s.d2 = INFINITY; s.i2 = 0x7fffffff;
+    }
+  }
+  if (abs(res[1] - res[2]) == 2) return res[0] + start;
+  if (abs(res[0] - res[1]) == 1) return max(res[0], res[1]) + start;
+  return -1;
+}
+
+// ---- per-warp shared-memory views --------------------------------------------------------------------
+struct WarpMem {
+  double *K, *invd, *u, *q, *rhs, *grad;
+  double *ca, *cb, *cc, *ck;
+  double *W11, *W12, *W22, *qv, *qpsi;
+  double *WeX, *WeY, *epsi;
+  double *wA, *wD, *wR, *SW;
+  __device__ WarpMem(double* base, int T) {
+    const int n = 2 * T, T1 = T + 1;
+    double* p = base;
+    K = p; p += n * (n + 1) / 2;
+    invd = p; p += n; u = p; p += n; q = p; p += n; rhs = p; p += n; grad = p; p += n;
+    ca = p; p += T1; cb = p; p += T1; cc = p; p += T1; ck = p; p += T1;
+    W11 = p; p += T1; W12 = p; p += T1; W22 = p; p += T1; qv = p; p += T1; qpsi = p; p += T1;
+    WeX = p; p += T1; WeY = p; p += T1; epsi = p; p += T1;
+    wA = p; p += T; wD = p; p += T; wR = p; p += T; SW = p; p += T;
+  }
+};
+
+// In-place Cholesky of the packed lower matrix K (n x n): column by column, a lane owns a row and forms
+// the dot product of its row with row j.  Returns false when a pivot is not positive.
+__device__ inline bool cholesky_packed(double* __restrict__ K, double* __restrict__ invd, int n, int lane) {
+  bool ok = true;
+  for (int j = 0; j < n; ++j) {
+    const double* rowj = K + tri(j);
+    double s0 = 0.0, s1 = 0.0;
+    const int i0 = j + lane, i1 = j + lane + 32;
+    if (i0 < n) {
+      const double* rowi = K + tri(i0);
+      double a0 = rowi[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = 0;
+      for (; k + 3 < j; k += 4) {
+        a0 = fma(-rowi[k], rowj[k], a0);
+        a1 = fma(-rowi[k + 1], rowj[k + 1], a1);
+        a2 = fma(-rowi[k + 2], rowj[k + 2], a2);
+        a3 = fma(-rowi[k + 3], rowj[k + 3], a3);
+      }
+      for (; k < j; ++k) a0 = fma(-rowi[k], rowj[k], a0);
+      s0 = (a0 + a1) + (a2 + a3);
+    }
+    if (i1 < n) {
+      const double* rowi = K + tri(i1);
+      double a0 = rowi[j], a1 = 0.0;
+      int k = 0;
+      for (; k + 1 < j; k += 2) {
+        a0 = fma(-rowi[k], rowj[k], a0);
+        a1 = fma(-rowi[k + 1], rowj[k + 1], a1);
+      }
+      for (; k < j; ++k) a0 = fma(-rowi[k], rowj[k], a0);
+      s1 = a0 + a1;
+    }
+    const double d = __shfl_sync(kFull, s0, 0);
+    if (!(d > 0.0)) { ok = false; break; }
+    const double inv = 1.0 / sqrt(d);
+    __syncwarp();
+    if (i0 < n) K[tri(i0) + j] = (lane == 0) ? d * inv : s0 * inv;
+    if (i1 < n) K[tri(i1) + j] = s1 * inv;
+    if (lane == 0) invd[j] = inv;
+    __syncwarp();
+  }
+  return ok;
+}
+
+// Solve L L' x = b in place (b in shared memory).
+__device__ inline void chol_solve(const double* __restrict__ K, const double* __restrict__ invd,
+                                  double* __restrict__ b, int n, int lane) {
+  // forward: L y = b
+  for (int j = 0; j < n; ++j) {
+    const double yj = b[j] * invd[j];
+    __syncwarp();
+    for (int i = j + 1 + lane; i < n; i += 32) b[i] = fma(-K[tri(i) + j], yj, b[i]);
+    if (lane == 0) b[j] = yj;
+    __syncwarp();
+  }
+  // backward: L' x = y
+  for (int j = n - 1; j >= 0; --j) {
+    const double xj = b[j] * invd[j];
+    __syncwarp();
+    const double* rowj = K + tri(j);
+    for (int i = lane; i < j; i += 32) b[i] = fma(-rowj[i], xj, b[i]);
+    if (lane == 0) b[j] = xj;
+    __syncwarp();
+  }
+}
+
+// y = K x for the packed symmetric K; a lane owns rows lane and lane + 32.  Result returned in registers.
+__device__ inline void symv_packed(const double* __restrict__ K, const double* __restrict__ x, int n, int lane,
+                                   double& y0, double& y1) {
+  y0 = 0.0; y1 = 0.0;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int i = lane + 32 * pass;
+    if (i < n) {
+      const double* rowi = K + tri(i);
+      double a0 = 0.0, a1 = 0.0;
+      int j = 0;
+      for (; j + 1 <= i; j += 2) { a0 = fma(rowi[j], x[j], a0); a1 = fma(rowi[j + 1], x[j + 1], a1); }
+      for (; j <= i; ++j) a0 = fma(rowi[j], x[j], a0);
+      for (j = i + 1; j < n; ++j) a1 = fma(K[tri(j) + i], x[j], a1);
+      if (pass == 0) y0 = a0 + a1; else y1 = a0 + a1;
+    }
+  }
+}
+
+struct StageRows {   // the four two-sided rows of stage k = lane: accel box, steer box, steer rate k->k+1, speed t=k+1
+  double hi[4], lo[4], sh[4], sl[4], lh[4], ll[4];
+  bool live[4];
+};
+
+// z = A u for the stage rows (u in shared memory)
+__device__ __forceinline__ void rows_apply(const double* __restrict__ u, int T, int lane, double z[4]) {
+  const double a = (lane < T) ? u[lane] : 0.0;
+  const double d = (lane < T) ? u[T + lane] : 0.0;
+  const double dn = __shfl_down_sync(kFull, d, 1);
+  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = warp_scan(a, lane);
+}
+// (A' t): this lane's entries for a_k (ra) and delta_k (rd); dead rows must carry t = 0
+__device__ __forceinline__ void rows_apply_T(const double t[4], int lane, double& ra, double& rd) {
+  ra = t[0] + warp_rscan(t[3], lane);
+  double up = __shfl_up_sync(kFull, t[2], 1);
+  if (lane == 0) up = 0.0;
+  rd = t[1] - t[2] + up;
+}
+
+__device__ __forceinline__ double step_to_boundary(double v, double dv) {
+  return (dv < 0.0) ? (-v / dv) : INFINITY;
+}
+
+// The fused step for one instance, executed by one warp.
+__device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane) {
+  const int T = A.T, n = 2 * T, T1 = T + 1;
+  WarpMem M(smem_base, T);
+  const double* prm = A.params ? (A.params + (size_t)b * JMPC_NPARAM) : nullptr;
+  auto P = [&](int k) -> double { return prm ? prm[k] : A.defaults[k]; };
+
+  const int cid = A.course_id ? A.course_id[b] : 0;
+  const double* cx = A.cx + (size_t)cid * A.course_stride;
+  const double* cy = A.cy + (size_t)cid * A.course_stride;
+  const double* cyaw = A.cyaw + (size_t)cid * A.course_stride;
+  int n_course = A.course_n[cid];
+  if (A.course_len) n_course = min(n_course, max(A.course_len[b], 1));
+
+  const double x0 = A.state[(size_t)b * 4 + 0], y0 = A.state[(size_t)b * 4 + 1];
+  const double v0 = A.state[(size_t)b * 4 + 2], yaw0 = A.state[(size_t)b * 4 + 3];
+  const double dt = P(JMPC_P_DT), dl = P(JMPC_P_DL), Lw = P(JMPC_P_L), speed = P(JMPC_P_SPEED);
+  const double min_speed = P(JMPC_P_MIN_SPEED);
+
+  // warm start = linearisation point (mpc.py:225-227: None -> zeros)
+  const bool use_warm = A.warm ? (A.warm[b] != 0) : true;
+  double oa_k = 0.0, od_k = 0.0;
+  if (use_warm && lane < T) { oa_k = A.oa[(size_t)b * T + lane]; od_k = A.od[(size_t)b * T + lane]; }
+
+  int target = A.target_ind[b];
+  target = min(max(target, 0), n_course);          // numpy slicing clamps an out-of-range start
+  double ov_k = 0.0;                               // |ov| feedback for lin_iters > 1 (lane k <-> horizon point k)
+  int status = JMPC_OPTIMAL;
+  int total_iters = 0;
+
+  for (int lin = 0; lin < A.lin_iters; ++lin) {
+    // ---------------- 1. nearest index --------------------------------------------------------------
+    const int near = nearest_index(cx, cy, n_course, target, x0, y0, lane);
+    if (near < 0) {
+      if (lane == 0) { A.status[b] = JMPC_INDEX_RULE; if (A.iters) A.iters[b] = total_iters; }
+      return;
+    }
+    target = near;
+
+    // ---------------- 2. reference sampling ---------------------------------------------------------
+    // travel = cumsum(|ov| dt): sequential float64 adds, reproduced literally (lane k owns point k)
+    double sp_k;
+    if (lin == 0) sp_k = fabs(fmax(v0, P(JMPC_P_V_REF_MIN))) * dt; else sp_k = fabs(ov_k) * dt;
+    double travel = 0.0;
+    {
+      double acc = 0.0;
+      for (int j = 0; j <= T; ++j) {          // uniform trip count: every lane takes part in the shuffle
+        const double sj = __shfl_sync(kFull, sp_k, j);
+        if (j <= lane) acc = (j == 0) ? sj : __dadd_rn(acc, sj);
+      }
+      travel = acc;
+    }
+    int idx = 0;
+    bool at_end = false;
+    double xr = 0.0, yr = 0.0, psir = 0.0;
+    if (lane <= T) {
+      const long long hop = (long long)rint(travel / dl);
+      long long id = hop + (long long)target;
+      if (id > (long long)(n_course - 1)) id = n_course - 1;
+      if (id < 0) id = 0;
+      idx = (int)id;
+      at_end = (idx == n_course - 1);
+      xr = cx[idx]; yr = cy[idx]; psir = cyaw[idx];
+    }
+    const unsigned end_mask = __ballot_sync(kFull, at_end);    // bit t = reaches_end[t]
+
+    // ---------------- 3. operating-point rollout ----------------------------------------------------
+    // theta and v recurrences need no trigonometry of the state, so every lane walks them redundantly,
+    // then lane t evaluates sin/cos(theta_t) once and the positions are accumulated in sequence.
+    const double max_steer = P(JMPC_P_MAX_STEER), vmax_sim = P(JMPC_P_SIM_MAX_SPEED);
+    const double tan_k = tan(fmax(fmin(od_k, max_steer), -max_steer));
+    double vb = v0, th = yaw0;          // lane t ends up holding vbar_t, phibar_t
+    {
+      double v = v0, ang = yaw0;
+      for (int t = 0; t < T; ++t) {
+        const double a_t = __shfl_sync(kFull, oa_k, t);
+        const double tn_t = __shfl_sync(kFull, tan_k, t);
+        const double yaw_dot = __dmul_rn(v / Lw, tn_t);
+        ang = __dadd_rn(ang, __dmul_rn(yaw_dot, dt));
+        v = __dadd_rn(v, __dmul_rn(a_t, dt));
+        v = fmax(fmin(v, vmax_sim), min_speed);
+        if (lane == t + 1) { vb = v; th = ang; }
+      }
+    }
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    // (x, y) are only reported (xbar rows 0,1 do not enter the QP); the QP needs vbar, phibar.
+    // ---------------- 4. linearisation + condensing -------------------------------------------------
+    // per-stage coefficients (stage t = lane, t < T)
+    double al = 0.0, be = 0.0, ga = 0.0, ka = 0.0, gk = 0.0;
+    if (lane < T) {
+      al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw;
+    }
+    // exclusive prefix sums c*[t] = sum_{j<t} (.)  for t = 0..T  (lane t)
+    const double ca_t = warp_scan(al, lane) - al, cb_t = warp_scan(be, lane) - be;
+    const double cc_t = warp_scan(ga, lane) - ga, ck_t = warp_scan(ka, lane) - ka;
+    // free response (u = 0): v = v0, psi = yaw0
+    const double fx_term = (lane < T) ? (al * v0 - be * (yaw0 - th)) : 0.0;
+    const double fy_term = (lane < T) ? (ga * v0 + ka * (yaw0 - th)) : 0.0;
+    const double xf_t = x0 + (warp_scan(fx_term, lane) - fx_term);
+    const double yf_t = y0 + (warp_scan(fy_term, lane) - fy_term);
+    // stage weights (t = lane, meaningful for 1 <= t <= T)
+    double w11 = 0.0, w12 = 0.0, w22 = 0.0, wv = 0.0, wpsi = 0.0;
+    if (lane >= 1 && lane <= T) {
+      if (at_end) {
+        w11 = P(JMPC_P_QF_X); w22 = P(JMPC_P_QF_Y); wv = P(JMPC_P_QF_V); wpsi = P(JMPC_P_QF_YAW);
+      } else {
+        double s1, c1, s2, c2;
+        sincos(psir + 0.5 * M_PI, &s1, &c1);
+        sincos(psir, &s2, &c2);
+        const double wp = P(JMPC_P_W_PERP), wl = P(JMPC_P_W_PARA);
+        w11 = (c1 * c1) * wp + (c2 * c2) * wl;
+        w12 = (c1 * s1) * wp + (c2 * s2) * wl;
+        w22 = (s1 * s1) * wp + (s2 * s2) * wl;
+        wv = P(JMPC_P_Q_V); wpsi = P(JMPC_P_Q_YAW);
+      }
+    }
+    const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 /* xref speed row is 0 */, eps = yaw0 - psir;
+    if (lane <= T) {
+      M.ca[lane] = ca_t; M.cb[lane] = cb_t; M.cc[lane] = cc_t; M.ck[lane] = ck_t;
+      M.W11[lane] = w11; M.W12[lane] = w12; M.W22[lane] = w22; M.qv[lane] = wv; M.qpsi[lane] = wpsi;
+      M.WeX[lane] = w11 * ex + w12 * ey; M.WeY[lane] = w12 * ex + w22 * ey; M.epsi[lane] = eps;
+    }
+    if (lane < T) M.wA[lane] = gk;      // borrow wA for g_k during condensing
+    __syncwarp();
+
+    const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
+    const double Rea = P(JMPC_P_REND_A), Red = P(JMPC_P_REND_D);
+    const double dt2 = dt * dt;
+    // Hessian, packed lower, variable order [a_0..a_{T-1}, delta_0..delta_{T-1}]
+    {
+      int i = 0, j = lane;
+      while (j > i) { j -= i + 1; ++i; }
+      for (int e = lane; e < n * (n + 1) / 2; e += 32) {
+        const bool id = i >= T, jd = j >= T;
+        const int ki = id ? i - T : i, kj = jd ? j - T : j;
+        const int t0 = max(ki, kj) + 1;
+        double acc = 0.0;
+        if (!id) {                       // accel x accel
+          const double ai = M.ca[ki + 1], ci = M.cc[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
+          for (int t = t0; t <= T; ++t) {
+            const double dAi = M.ca[t] - ai, dCi = M.cc[t] - ci, dAj = M.ca[t] - aj, dCj = M.cc[t] - cj;
+            acc += dAi * (M.W11[t] * dAj + M.W12[t] * dCj) + dCi * (M.W12[t] * dAj + M.W22[t] * dCj) + M.qv[t];
+          }
+          acc *= dt2;
+        } else if (!jd) {                // steer (row) x accel (col)
+          const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
+          for (int t = t0; t <= T; ++t) {
+            const double sx = -(M.cb[t] - bi), sy = M.ck[t] - kki, dAj = M.ca[t] - aj, dCj = M.cc[t] - cj;
+            acc += sx * (M.W11[t] * dAj + M.W12[t] * dCj) + sy * (M.W12[t] * dAj + M.W22[t] * dCj);
+          }
+          acc *= M.wA[ki] * dt;
+        } else {                         // steer x steer
+          const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], bj = M.cb[kj + 1], kkj = M.ck[kj + 1];
+          for (int t = t0; t <= T; ++t) {
+            const double sxi = -(M.cb[t] - bi), syi = M.ck[t] - kki, sxj = -(M.cb[t] - bj), syj = M.ck[t] - kkj;
+            acc += sxi * (M.W11[t] * sxj + M.W12[t] * syj) + syi * (M.W12[t] * sxj + M.W22[t] * syj) + M.qpsi[t];
+          }
+          acc *= M.wA[ki] * M.wA[kj];
+        }
+        acc *= 2.0;
+        if (id == jd) {                  // input and input-rate weights (mpc.py:180-187)
+          const double rd_w = id ? Rdd : Rda;
+          if (ki == kj) {
+            const bool e_t = (end_mask >> ki) & 1u;
+            const double r = id ? (e_t ? Red : Rd_) : (e_t ? Rea : Ra);
+            const int nb = (T >= 2) ? ((ki == 0 || ki == T - 1) ? 1 : 2) : 0;
+            acc += 2.0 * r + 2.0 * rd_w * nb;
+          } else if (ki == kj + 1) {
+            acc -= 2.0 * rd_w;
+          }
+        }
+        pscr[e] = acc;
+        j += 32;
+        while (j > i) { j -= i + 1; ++i; }
+      }
+    }
+    // linear term and the constant
+    double c0 = 0.0;
+    if (lane >= 1 && lane <= T) c0 = ex * M.WeX[lane] + ey * M.WeY[lane] + wv * ev * ev + wpsi * eps * eps;
+    c0 = warp_sum(c0);
+    if (lane < T) {
+      const int k = lane;
+      const double ai = M.ca[k + 1], ci = M.cc[k + 1], bi = M.cb[k + 1], kki = M.ck[k + 1];
+      double qa = 0.0, qd = 0.0;
+      for (int t = k + 1; t <= T; ++t) {
+        qa += dt * ((M.ca[t] - ai) * M.WeX[t] + (M.cc[t] - ci) * M.WeY[t]) + dt * M.qv[t] * ev;
+        qd += gk * (-(M.cb[t] - bi) * M.WeX[t] + (M.ck[t] - kki) * M.WeY[t]) + gk * M.qpsi[t] * M.epsi[t];
+      }
+      M.q[k] = 2.0 * qa; M.q[T + k] = 2.0 * qd;
+      M.u[k] = 0.0; M.u[T + k] = 0.0;
+    }
+    __syncwarp();
+
+    // feasibility predicate: the t = 0 speed rows act on the fixed v0
+    if (!(min_speed <= v0 && v0 <= speed)) {
+      status = JMPC_INFEASIBLE;
+      // xref / target are still reported, as the reference assigns them before the solve result
+      if (lane <= T) {
+        double* xo = A.xref + (size_t)b * 4 * T1;
+        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = 0.0; xo[3 * T1 + lane] = psir;
+      }
+      if (lane == 0) { A.status[b] = status; A.target_ind[b] = target; if (A.iters) A.iters[b] = total_iters;
+                       A.cost[b] = nan(""); }
+      return;
+    }
+
+    // ---------------- 5. interior-point solve -------------------------------------------------------
+    StageRows R;
+    {
+      const double lim = P(JMPC_P_MAX_DSTEER) * dt;
+      R.hi[0] = P(JMPC_P_MAX_ACCEL); R.lo[0] = P(JMPC_P_MAX_DECEL);
+      R.hi[1] = max_steer;           R.lo[1] = -max_steer;
+      R.hi[2] = lim;                 R.lo[2] = -lim;
+      R.hi[3] = (speed - v0) / dt;   R.lo[3] = (min_speed - v0) / dt;
+      R.live[0] = R.live[1] = R.live[3] = lane < T;
+      R.live[2] = lane < T - 1;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        // u = 0 -> z = 0
+        R.sh[r] = fmax(R.hi[r], 1e-2); R.sl[r] = fmax(-R.lo[r], 1e-2);
+        R.lh[r] = R.live[r] ? 1.0 : 0.0; R.ll[r] = R.lh[r];
+      }
+    }
+    const double inv_rows = 1.0 / (double)(2 * (4 * T - 1));
+    double gscale = 0.0;
+    if (lane < T) gscale = fmax(fabs(M.q[lane]), fabs(M.q[T + lane]));
+    gscale = 1.0 + warp_max(gscale);
+    const int npk = n * (n + 1) / 2;
+    bool converged = false;
+    int it = 0;
+    for (it = 0; it < A.max_iters; ++it) {
+      double z[4], rph[4], rpl[4], w[4], t4[4];
+      rows_apply(M.u, T, lane, z);
+      double mu = 0.0, rpmax = 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        rph[r] = R.live[r] ? (z[r] + R.sh[r] - R.hi[r]) : 0.0;
+        rpl[r] = R.live[r] ? (-z[r] + R.sl[r] + R.lo[r]) : 0.0;
+        w[r] = R.live[r] ? (R.lh[r] / R.sh[r] + R.ll[r] / R.sl[r]) : 0.0;
+        mu += R.lh[r] * R.sh[r] + R.ll[r] * R.sl[r];
+        rpmax = fmax(rpmax, fmax(fabs(rph[r]), fabs(rpl[r])));
+      }
+      mu = warp_sum(mu) * inv_rows;
+      rpmax = warp_max(rpmax);
+      // row weights -> shared, K = P + A' diag(w) A
+      {
+        double wup = __shfl_up_sync(kFull, w[2], 1);
+        if (lane == 0) wup = 0.0;
+        const double sw = warp_rscan(w[3], lane);
+        if (lane < T) { M.wA[lane] = w[0]; M.wD[lane] = w[1] + w[2] + wup; M.wR[lane] = w[2]; M.SW[lane] = sw; }
+      }
+      __syncwarp();
+      {
+        int i = 0, j = lane;
+        while (j > i) { j -= i + 1; ++i; }
+        for (int e = lane; e < npk; e += 32) {
+          double val = pscr[e];
+          if (i < T) { val += M.SW[i]; if (i == j) val += M.wA[i]; }
+          else if (j >= T) {
+            if (i == j) val += M.wD[i - T];
+            else if (i == j + 1) val -= M.wR[j - T];
+          }
+          M.K[e] = val;
+          j += 32;
+          while (j > i) { j -= i + 1; ++i; }
+        }
+      }
+      __syncwarp();
+      // dual residual: P u + q + A'(lh - ll) = K u + q + A'(lh - ll - w z)
+      double ku0, ku1;
+      symv_packed(M.K, M.u, n, lane, ku0, ku1);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) t4[r] = R.live[r] ? (R.lh[r] - R.ll[r] - w[r] * z[r]) : 0.0;
+      double ra, rd;
+      rows_apply_T(t4, lane, ra, rd);
+      if (lane < n) M.grad[lane] = ku0 + M.q[lane];
+      if (lane + 32 < n) M.grad[lane + 32] = ku1 + M.q[lane + 32];
+      __syncwarp();
+      double rdmax = 0.0;
+      if (lane < T) {
+        const double g0 = M.grad[lane] + ra, g1 = M.grad[T + lane] + rd;
+        M.grad[lane] = g0; M.grad[T + lane] = g1;
+        rdmax = fmax(fabs(g0), fabs(g1));
+      }
+      rdmax = warp_max(rdmax);
+      __syncwarp();
+      if (mu <= A.mu_tol && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) { converged = true; break; }
+
+      if (!cholesky_packed(M.K, M.invd, n, lane)) break;
+
+      double dsh[4], dsl[4], dlh[4], dll[4];
+      double sigma_mu = 0.0;
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) {
+        // complementarity targets: predictor rc = l s ; corrector rc = l s + ds_aff dl_aff - sigma mu
+        double th[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          double rch = R.lh[r] * R.sh[r], rcl = R.ll[r] * R.sl[r];
+          if (phase == 1) { rch += dsh[r] * dlh[r] - sigma_mu; rcl += dsl[r] * dll[r] - sigma_mu; }
+          const double a_h = (-rch + R.lh[r] * rph[r]) / R.sh[r];
+          const double a_l = (-rcl + R.ll[r] * rpl[r]) / R.sl[r];
+          th[r] = R.live[r] ? (a_h - a_l) : 0.0;
+          // stash rc in dlh/dll for the direction recovery below
+          dlh[r] = rch; dll[r] = rcl;
+        }
+        rows_apply_T(th, lane, ra, rd);
+        if (lane < T) { M.rhs[lane] = -M.grad[lane] - ra; M.rhs[T + lane] = -M.grad[T + lane] - rd; }
+        __syncwarp();
+        chol_solve(M.K, M.invd, M.rhs, n, lane);
+        double dz[4];
+        rows_apply(M.rhs, T, lane, dz);
+        double amax = INFINITY;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double rch = dlh[r], rcl = dll[r];
+          dsh[r] = R.live[r] ? (-rph[r] - dz[r]) : 0.0;
+          dsl[r] = R.live[r] ? (-rpl[r] + dz[r]) : 0.0;
+          dlh[r] = R.live[r] ? ((-rch - R.lh[r] * dsh[r]) / R.sh[r]) : 0.0;
+          dll[r] = R.live[r] ? ((-rcl - R.ll[r] * dsl[r]) / R.sl[r]) : 0.0;
+          if (R.live[r]) {
+            amax = fmin(amax, fmin(step_to_boundary(R.sh[r], dsh[r]), step_to_boundary(R.sl[r], dsl[r])));
+            amax = fmin(amax, fmin(step_to_boundary(R.lh[r], dlh[r]), step_to_boundary(R.ll[r], dll[r])));
+          }
+        }
+        amax = warp_min(amax);
+        if (phase == 0) {
+          const double aa = fmin(1.0, amax);
+          double mu_aff = 0.0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            mu_aff += (R.lh[r] + aa * dlh[r]) * (R.sh[r] + aa * dsh[r]) + (R.ll[r] + aa * dll[r]) * (R.sl[r] + aa * dsl[r]);
+          mu_aff = warp_sum(mu_aff) * inv_rows;
+          const double ratio = mu_aff / mu;
+          sigma_mu = ratio * ratio * ratio * mu;
+        } else {
+          const double alpha = fmin(1.0, 0.99 * amax);
+          if (lane < T) { M.u[lane] = fma(alpha, M.rhs[lane], M.u[lane]); M.u[T + lane] = fma(alpha, M.rhs[T + lane], M.u[T + lane]); }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            R.sh[r] = fma(alpha, dsh[r], R.sh[r]); R.sl[r] = fma(alpha, dsl[r], R.sl[r]);
+            R.lh[r] = fma(alpha, dlh[r], R.lh[r]); R.ll[r] = fma(alpha, dll[r], R.ll[r]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    total_iters += it;
+    status = converged ? JMPC_OPTIMAL : JMPC_MAX_ITER;
+
+    // ---------------- 6. states of the linearised model for the solution ---------------------------
+    const double a_sol = (lane < T) ? M.u[lane] : 0.0, d_sol = (lane < T) ? M.u[T + lane] : 0.0;
+    const double v_t = v0 + dt * (warp_scan(a_sol, lane) - a_sol);                  // lane t: v_t
+    const double gd = gk * d_sol;
+    const double psi_t = yaw0 + (warp_scan(gd, lane) - gd);
+    const double tx = (lane < T) ? (al * v_t - be * (psi_t - th)) : 0.0;
+    const double ty = (lane < T) ? (ga * v_t + ka * (psi_t - th)) : 0.0;
+    const double X_t = x0 + (warp_scan(tx, lane) - tx);
+    const double Y_t = y0 + (warp_scan(ty, lane) - ty);
+
+    const bool last = (lin == A.lin_iters - 1);
+    if (last) {
+      // objective value, evaluated term by term as mpc.py:159-187 writes it
+      double cterm = 0.0;
+      if (lane >= 1 && lane <= T) {
+        const double dx = xr - X_t, dy = yr - Y_t, dv = 0.0 - v_t, dp = psir - psi_t;
+        cterm = dx * (w11 * dx + w12 * dy) + dy * (w12 * dx + w22 * dy) + wv * dv * dv + wpsi * dp * dp;
+      }
+      if (lane < T) {
+        const bool e_t = (end_mask >> lane) & 1u;
+        cterm += (e_t ? Rea : Ra) * a_sol * a_sol + (e_t ? Red : Rd_) * d_sol * d_sol;
+      }
+      const double a_next = __shfl_down_sync(kFull, a_sol, 1), d_next = __shfl_down_sync(kFull, d_sol, 1);
+      if (lane < T - 1) cterm += Rda * (a_next - a_sol) * (a_next - a_sol) + Rdd * (d_next - d_sol) * (d_next - d_sol);
+      const double cost = warp_sum(cterm);
+      (void)c0;
+      if (lane < T) { A.oa[(size_t)b * T + lane] = a_sol; A.od[(size_t)b * T + lane] = d_sol; }
+      if (lane <= T) {
+        A.ox[(size_t)b * T1 + lane] = X_t; A.oy[(size_t)b * T1 + lane] = Y_t;
+        A.ov[(size_t)b * T1 + lane] = v_t; A.oyaw[(size_t)b * T1 + lane] = psi_t;
+        double* xo = A.xref + (size_t)b * 4 * T1;
+        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = 0.0; xo[3 * T1 + lane] = psir;
+      }
+      if (lane == 0) {
+        A.cost[b] = cost; A.status[b] = status; A.target_ind[b] = target;
+        if (A.iters) A.iters[b] = total_iters;
+      }
+    } else {
+      // feed the solution back as the next linearisation point (mpc.py:231-236)
+      oa_k = a_sol; od_k = d_sol; ov_k = v_t;
+    }
+    __syncwarp();
+  }
+}
+
+// Persistent kernel: every resident warp pulls instances from a global counter.
+__global__ void __launch_bounds__(128) mpc_step_kernel(const StepArgs A) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  double* base = smem + (size_t)wib * warp_smem_doubles(A.T);
+  const int gw = blockIdx.x * warps_per_block + wib;
+  const int n = 2 * A.T;
+  double* pscr = A.pscratch + (size_t)gw * (n * (n + 1) / 2);
+  for (;;) {
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(A.counter, 1u);
+    b = __shfl_sync(kFull, b, 0);
+    if (b >= (unsigned)A.B) break;
+    mpc_step_instance(A, (int)b, base, pscr, lane);
+    __syncwarp();
+  }
+}
+
+}  // namespace jmpc

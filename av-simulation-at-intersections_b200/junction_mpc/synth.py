@@ -3,13 +3,13 @@
 Host-side numpy only; the same frozen inputs feed the CUDA path, the CPU oracle and the reference arm.
 A workload is a dict of numpy arrays in the layout the C ABI takes (include/jmpc.h):
 
-    state      [4, B] float64   rows x, y, v, yaw
+    state      [B, 4] float64   columns x, y, v, yaw
     course_id  [B]    int32     index into the course table
     course_len [B]    int32     effective course length N' (prefix truncation, mpc_intersection.py:138)
     target_ind [B]    int32     search start for the nearest-index rule
-    oa, od     [T, B] float64   previous solution = linearisation point (zeros when there is none)
-    params     [NPARAM, B] float64 or None   per-instance parameter overrides (config 5)
-    obstacles  [n_obs, 6, B] float64 or None (x, y, v, yaw, a, steer) for the flag kernel
+    oa, od     [B, T] float64   previous solution = linearisation point (zeros when there is none)
+    params     [B, NPARAM] float64 or None   per-instance parameter overrides (config 5)
+    obstacles  [B, n_obs, 6] float64 or None (x, y, v, yaw, a, steer) for the flag kernel
     agent_idx  [B] int32        ego index on the full course for the flag kernel
 
 The index-rule validity filter of the generator (instances for which trajectories.py:120 would raise are
@@ -58,7 +58,7 @@ def _index_rule_ok(x, y, cx, cy, start, n):
 
 def make_states(rng, course: np.ndarray, B: int, T: int, cut_fraction: float = 0.3) -> Dict[str, np.ndarray]:
     N = len(course)
-    state = np.zeros((4, B))
+    state = np.zeros((B, 4))
     target = np.zeros(B, np.int32)
     clen = np.zeros(B, np.int32)
     agent = np.zeros(B, np.int32)
@@ -73,25 +73,25 @@ def make_states(rng, course: np.ndarray, B: int, T: int, cut_fraction: float = 0
         t0 = max(s - 3, 0)
         if not _index_rule_ok(x, y, course[:, 0], course[:, 1], t0, n):
             continue
-        state[:, k] = (x, y, v, yaw)
+        state[k] = (x, y, v, yaw)
         target[k], clen[k], agent[k] = t0, n, s
         k += 1
     cold = rng.random(B) < 0.25
-    oa = rng.uniform(-1.0, 2.0, (T, B))
-    od = np.clip(np.cumsum(rng.uniform(-0.05, 0.05, (T, B)), axis=0) + rng.uniform(-0.2, 0.2, B), -0.7, 0.7)
-    oa[:, cold] = 0.0
-    od[:, cold] = 0.0
+    oa = rng.uniform(-1.0, 2.0, (B, T))
+    od = np.clip(np.cumsum(rng.uniform(-0.05, 0.05, (B, T)), axis=1) + rng.uniform(-0.2, 0.2, (B, 1)), -0.7, 0.7)
+    oa[cold] = 0.0
+    od[cold] = 0.0
     return dict(state=state, target_ind=target, course_len=clen, agent_idx=agent, oa=oa, od=od,
                 course_id=np.zeros(B, np.int32))
 
 
 def make_obstacles(rng, B: int, n_obs: int) -> np.ndarray:
-    obs = np.zeros((n_obs, 6, B))
-    obs[:, 0] = rng.uniform(-35, 35, (n_obs, B))
-    obs[:, 1] = rng.uniform(-35, 35, (n_obs, B))
-    obs[:, 2] = rng.uniform(0, 30 / 3.6, (n_obs, B))
-    obs[:, 3] = rng.uniform(-math.pi, math.pi, (n_obs, B))
-    obs[:, 5] = rng.uniform(-0.4, 0.4, (n_obs, B))
+    obs = np.zeros((B, n_obs, 6))
+    obs[:, :, 0] = rng.uniform(-35, 35, (B, n_obs))
+    obs[:, :, 1] = rng.uniform(-35, 35, (B, n_obs))
+    obs[:, :, 2] = rng.uniform(0, 30 / 3.6, (B, n_obs))
+    obs[:, :, 3] = rng.uniform(-math.pi, math.pi, (B, n_obs))
+    obs[:, :, 5] = rng.uniform(-0.4, 0.4, (B, n_obs))
     return obs
 
 
@@ -134,19 +134,19 @@ def make_sweep(T: int, states_per_point: int = 32, max_points: Optional[int] = N
     cfg = cfg or MPCConfig.default()
     rng = np.random.default_rng(seed * 1000 + T)
     axes = [SWEEP_AXES[k] for k in ["dt", "w_perp", "w_para", "R_acc", "R_steer", "Rd_acc", "Rd_steer"]]
-    grid = np.array(np.meshgrid(*axes, indexing="ij")).reshape(len(axes), -1)      # [7, 8192]
-    if max_points is not None and max_points < grid.shape[1]:
-        grid = grid[:, rng.choice(grid.shape[1], max_points, replace=False)]
-    P = grid.shape[1]
+    grid = np.array(np.meshgrid(*axes, indexing="ij")).reshape(len(axes), -1).T      # [8192, 7]
+    if max_points is not None and max_points < grid.shape[0]:
+        grid = grid[rng.choice(grid.shape[0], max_points, replace=False)]
+    P = grid.shape[0]
     B = P * states_per_point
     course = load_course("intersection")
     w = make_states(rng, course, B, T)
     base = cfg.with_T(T).param_vector(dl=float(np.linalg.norm(course[0, :2] - course[1, :2])), dt=0.2,
                                       L=2.86, speed=30 / 3.6)
-    params = np.repeat(base[:, None], B, axis=1)
-    rep = np.repeat(grid, states_per_point, axis=1)
-    for row, key in zip(rep, ["dt", "w_perp", "w_para", "R_a", "R_d", "Rd_a", "Rd_d"]):
-        params[PARAM_INDEX[key]] = row
+    params = np.repeat(base[None, :], B, axis=0)
+    rep = np.repeat(grid, states_per_point, axis=0)
+    for col, key in enumerate(["dt", "w_perp", "w_para", "R_a", "R_d", "Rd_a", "Rd_d"]):
+        params[:, PARAM_INDEX[key]] = rep[:, col]
     w.update(T=T, courses=[course], params=params, obstacles=None, frame_window=10, name=f"sweep_T{T}", B=B,
              dl=float(base[PARAM_INDEX["dl"]]))
     return w

@@ -1,0 +1,157 @@
+/*
+ * jmpc.h -- C ABI of libjmpc.so: the batched JunctionSim MPC step on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the per-timestep controller hot path of
+ * SaeedRahmani/AV-Simulation-at-Intersections (paths below are relative to that repository).  The reference
+ * has no FFI of its own (it is pure Python); the entry points here are what a ctypes binding placed behind
+ * `lib.mpc.MPC` binds (INTEGRATION.md shows that stub).  Plain pointers and sizes only; no C++ or torch
+ * types cross this boundary; no C++ exception escapes it.
+ *
+ * Memory convention
+ *   - `jmpc_step` / `jmpc_collision` take DEVICE pointers (e.g. torch tensors' data_ptr()) and only enqueue
+ *     work on `stream`; they never synchronise.
+ *   - `jmpc_step_host` / `jmpc_collision_host` take HOST pointers, stage through pinned buffers owned by the
+ *     handle, run the same kernels and return after the results are back on the host.
+ *   - Arrays are instance-major ("batch first"), float64 / int32, densely packed:
+ *       state      [B][4]         x, y, v, yaw            (main/lib/mpc.py:291)
+ *       oa, od     [B][T]         accelerations / steering angles; in: previous solution (the linearisation
+ *                                 point, mpc.py:225-227,293-296; zeros when there is none), out: new solution
+ *       ox,oy,ov,oyaw [B][T+1]    predicted states          (mpc.py:199-205)
+ *       xref       [B][4][T+1]    sampled reference         (mpc.py:89-112)
+ *       params     [B][JMPC_NPARAM]  optional per-instance parameters (NULL -> handle defaults)
+ *       obstacles  [B][n_obs][6]  x, y, v, yaw, a, steer    (main/lib/moving_obstacles.py:229-232 `get()`)
+ *   - A warp owns an instance, so instance-major rows are what it reads coalesced.
+ *
+ * Threading: one handle per (host thread, device); calls on one handle must be serialised by the caller.
+ */
+#ifndef JMPC_H_
+#define JMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMPC_ABI_VERSION 1
+#define JMPC_MAX_T 31           /* horizon limit of the warp-per-instance kernels (reference GUI range 5..25) */
+
+/* Row order of a parameter vector.  Derivations as in main/lib/mpc.py:14-39 and main/lib/simulation.py:23-25:
+ * Qf_* already multiplied by T (mpc.py:28), max_dsteer in rad/s (mpc.py:37). */
+enum jmpc_param {
+  JMPC_P_DT = 0,        /* sample time [s]                          MPC(..., dt)            mpc.py:247 */
+  JMPC_P_DL,            /* course tick [m]                          MPC(..., dl)                       */
+  JMPC_P_L,             /* wheelbase                                car_dimensions.py:84               */
+  JMPC_P_SPEED,         /* speed cap of the QP                      MPC(..., speed)         mpc.py:190 */
+  JMPC_P_W_PERP, JMPC_P_W_PARA,                     /* mpc.py:23-24                                    */
+  JMPC_P_R_A, JMPC_P_R_D,                           /* R  = diag(.,.)                        mpc.py:25 */
+  JMPC_P_RD_A, JMPC_P_RD_D,                         /* Rd = diag(.,.)                        mpc.py:26 */
+  JMPC_P_Q_V, JMPC_P_Q_YAW,                         /* Q_v_yaw                               mpc.py:27 */
+  JMPC_P_QF_X, JMPC_P_QF_Y, JMPC_P_QF_V, JMPC_P_QF_YAW,  /* Qf * T                           mpc.py:28 */
+  JMPC_P_REND_A, JMPC_P_REND_D,                     /* input weight once the course end is reached, mpc.py:181 */
+  JMPC_P_MAX_DSTEER,    /* rad/s                                                             mpc.py:37 */
+  JMPC_P_MAX_ACCEL, JMPC_P_MAX_DECEL,               /*                                       mpc.py:38-39 */
+  JMPC_P_MAX_STEER,     /* Simulation.MAX_STEER                                        simulation.py:23 */
+  JMPC_P_SIM_MAX_SPEED, /* Simulation.MAX_SPEED (rollout clamp, not the QP cap)        simulation.py:24 */
+  JMPC_P_MIN_SPEED,     /* Simulation.MIN_SPEED                                        simulation.py:25 */
+  JMPC_P_V_REF_MIN,     /* 10/3.6: floor of the reference-sampling speed                     mpc.py:99 */
+  JMPC_NPARAM
+};
+
+/* Per-instance status word. */
+enum jmpc_status {
+  JMPC_OPTIMAL = 0,      /* cvxpy OPTIMAL / OPTIMAL_INACCURATE branch                     mpc.py:199-205 */
+  JMPC_MAX_ITER = 1,     /* iteration cap hit; outputs hold the last iterate                             */
+  JMPC_INFEASIBLE = 2,   /* v0 outside [MIN_SPEED, speed]: reference prints "Cannot solve mpc", mpc.py:207-209;
+                            control outputs are left untouched, xref/target_ind are valid                */
+  JMPC_INDEX_RULE = 3    /* nearest-index rule failed: reference raises at trajectories.py:120;
+                            nothing is written for the instance                                          */
+};
+
+typedef struct jmpc_handle_s* jmpc_handle;
+
+/* Solver options (all have defaults; pass NULL to jmpc_create). */
+typedef struct {
+  int32_t max_solver_iters;   /* interior-point iteration cap (default 40)                                 */
+  int32_t linearisation_iters;/* MAX_ITER of mpc_config.json (default 1)                     mpc.py:231   */
+  double  mu_tol;             /* complementarity target (default 1e-13)                                    */
+  int32_t warps_per_sm;       /* resident solver warps per SM, 0 = auto                                   */
+} jmpc_options;
+
+/* Library / ABI introspection. */
+int32_t     jmpc_abi_version(void);
+int32_t     jmpc_nparam(void);
+const char* jmpc_last_error(void);          /* thread-local message of the last failing call */
+
+/* Create a handle on CUDA device `device` able to run batches of up to `max_B` instances with horizon up to
+ * `max_T` (<= JMPC_MAX_T) over courses of up to `max_N` points.  `default_params` is a JMPC_NPARAM vector used
+ * when a call passes params == NULL.  Replaces the module-level configuration of mpc.py:14-39 and the
+ * constructor state of `class MPC` (mpc.py:245-277).  Returns 0 on success, <0 on error. */
+int32_t jmpc_create(int32_t device, int32_t max_B, int32_t max_T, int32_t max_N, int32_t max_courses,
+                    const double* default_params, const jmpc_options* options, jmpc_handle* out);
+int32_t jmpc_destroy(jmpc_handle h);
+
+/* Replace the default parameter vector. */
+int32_t jmpc_set_default_params(jmpc_handle h, const double* default_params);
+
+/* Upload course tables (HOST pointers): course c has len[c] points, stored at cx + c*stride etc.  Yaw must
+ * already be smoothed (mpc.py:46-58 is a once-per-course scan the Python wrapper does in place, as
+ * MPC.__init__ does at mpc.py:260).  Replaces MPC.__init__/set_trajectory_fromarray (mpc.py:279-282): a
+ * truncated course `trajectory_full[:k]` is expressed per instance by `course_len` in jmpc_step. */
+int32_t jmpc_set_courses(jmpc_handle h, int32_t n_courses, int32_t stride, const int32_t* len,
+                         const double* cx, const double* cy, const double* cyaw);
+
+/* Collision-circle geometry of the car (main/lib/car_dimensions.py:62-79): x offsets of the front and rear
+ * circle centres from the rear axle and the circle radius.  Defaults are BicycleModelDimensions
+ * (car_dimensions.py:82-90): 2.18, 0.68, 2/sqrt(2). */
+int32_t jmpc_set_car_geometry(jmpc_handle h, double front_offset, double rear_offset, double radius);
+
+/* One MPC step (mpc.py:284-303 -> _iterative_linear_mpc_control :214-242) for B instances with horizon T.
+ * DEVICE pointers; enqueues on `stream` (a cudaStream_t passed as void*).
+ *   course_id  [B] or NULL (all course 0);  course_len [B] or NULL (full length)
+ *   target_ind [B] in: search start, out: new nearest index            (mpc.py:94, :298)
+ *   warm       [B] or NULL: 0 -> treat oa/od as zeros (mpc.py:225-227), 1 -> use them
+ *   cost       [B]: objective value at the optimum, constants included (what `prob.value` would be)
+ *   iters      [B] or NULL: solver iterations used */
+int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
+                  const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa, double* od,
+                  const double* params, double* ox, double* oy, double* ov, double* oyaw, double* xref,
+                  double* cost, int32_t* status, int32_t* iters, void* stream);
+
+/* Same with HOST pointers: copies in, runs, copies out, synchronises. */
+int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
+                       const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
+                       double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
+                       double* xref, double* cost, int32_t* status, int32_t* iters);
+
+/* Collision flag + cut index for B instances (mpc_intersection.py:111-140, collision_avoidance.py:85-124,
+ * 168-180, moving_obstacles_prediction.py:21-47, trajectories.py:58-86).  DEVICE pointers.
+ *   agent_idx [B]: ego index on the full course (traj_agent_idx);  v [B]: ego speed
+ *   obstacles [B][n_obs][6];  frame_window: FRAME_WINDOW;  margin: EXTRA_CUTOFF_MARGIN (in course points)
+ *   flag [B]: 1 when a collision is predicted;  course_len_out [B]: effective course length to feed
+ *   jmpc_step (full length when flag == 0) */
+int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const int32_t* agent_idx,
+                       const double* v, const double* obstacles, int32_t n_obs, int32_t frame_window,
+                       int32_t margin, double horizon_s, const double* params, int32_t* flag,
+                       int32_t* course_len_out, void* stream);
+int32_t jmpc_collision_host(jmpc_handle h, int32_t B, const int32_t* course_id, const int32_t* agent_idx,
+                            const double* v, const double* obstacles, int32_t n_obs, int32_t frame_window,
+                            int32_t margin, double horizon_s, const double* params, int32_t* flag,
+                            int32_t* course_len_out);
+
+/* Plant step for B instances (Simulation.step, simulation.py:35-47 -> Bicycle.step, bicycle/main.py:28-41).
+ * DEVICE pointers; state [B][4] is advanced in place with (a, delta). */
+int32_t jmpc_plant_step(jmpc_handle h, int32_t B, double* state, const double* a, const double* delta,
+                        const double* params, void* stream);
+
+/* Number of kernel launches issued through this handle since creation (for bench.py's gpu_launches). */
+int64_t jmpc_launch_count(jmpc_handle h);
+
+/* Measured FP64 / FP32 FMA throughput of the device in TFLOP/s (a register-resident FMA loop on every SM);
+ * the denominator of the solver kernel's roofline, which is CUDA-core bound. */
+int32_t jmpc_measure_fma_peak(jmpc_handle h, double* fp64_tflops, double* fp32_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMPC_H_ */

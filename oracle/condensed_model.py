@@ -103,3 +103,104 @@ def states_from_controls(c: CondensedQP, u: np.ndarray) -> np.ndarray:
 
 def objective(c: CondensedQP, u: np.ndarray) -> float:
     return float(0.5 * u @ c.P @ u + c.q @ u + c.c0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Model of the solver the CUDA kernel runs: Mehrotra predictor-corrector on the condensed QP with the
+# constraint rows grouped per stage k (accel box, steer box, steer-rate row k -> k+1, speed row t = k+1).
+# K = P + A' diag(w) A is assembled from that structure exactly as the kernel does it.
+# ----------------------------------------------------------------------------------------------------
+def _rows_apply(T, u):
+    """A u, as four per-stage vectors (abox, dbox, rate, speed-sum)."""
+    a, d = u[:T], u[T:]
+    rate = np.zeros(T)
+    rate[:T - 1] = d[1:] - d[:-1]
+    return np.stack([a, d, rate, np.cumsum(a)])
+
+
+def _rows_apply_T(T, t):
+    """A' t for per-stage row values t[4, T] (rate row T-1 does not exist and must be 0)."""
+    out = np.zeros(2 * T)
+    out[:T] = t[0] + np.cumsum(t[3][::-1])[::-1]
+    out[T:] = t[1]
+    out[T:2 * T - 1] -= t[2][:T - 1]
+    out[T + 1:] += t[2][:T - 1]
+    return out
+
+
+def _assemble_K(T, P, w):
+    K = P.copy()
+    idx = np.arange(T)
+    K[idx, idx] += w[0]
+    K[T + idx, T + idx] += w[1]
+    for k in range(T - 1):
+        K[T + k, T + k] += w[2][k]
+        K[T + k + 1, T + k + 1] += w[2][k]
+        K[T + k, T + k + 1] -= w[2][k]
+        K[T + k + 1, T + k] -= w[2][k]
+    suffix = np.cumsum(w[3][::-1])[::-1]               # suffix[i] = sum_{k >= i} w_speed[k]
+    K[:T, :T] += suffix[np.maximum.outer(idx, idx)]
+    return K
+
+
+def ipm_solve(c: CondensedQP, max_iter: int = 40, mu_tol: float = 1e-13, s_min: float = 1e-2, lam0: float = 1.0):
+    """Returns (u, iterations, converged)."""
+    T = len(c.q) // 2
+    n = 2 * T
+    hi = np.stack([c.hi[:T], c.hi[T:2 * T], np.append(c.hi[2 * T:3 * T - 1], 1.0), c.hi[3 * T - 1:]])
+    lo = np.stack([c.lo[:T], c.lo[T:2 * T], np.append(c.lo[2 * T:3 * T - 1], -1.0), c.lo[3 * T - 1:]])
+    live = np.ones((4, T), bool)
+    live[2, T - 1] = False                                   # there is no rate row for the last stage
+    nrow = 2 * live.sum()
+    u = np.zeros(n)
+    z = _rows_apply(T, u)
+    sh = np.maximum(hi - z, s_min)
+    sl = np.maximum(z - lo, s_min)
+    lh = np.where(live, lam0, 0.0)
+    ll = np.where(live, lam0, 0.0)
+    gscale = 1.0 + np.abs(c.q).max()
+    ok = False
+    it = 0
+    for it in range(1, max_iter + 1):
+        z = _rows_apply(T, u)
+        rd = c.P @ u + c.q + _rows_apply_T(T, np.where(live, lh - ll, 0.0))
+        rph = np.where(live, z + sh - hi, 0.0)
+        rpl = np.where(live, -z + sl + lo, 0.0)
+        mu = float((lh * sh + ll * sl)[live].sum()) / nrow
+        if mu <= mu_tol and max(np.abs(rph).max(), np.abs(rpl).max()) <= 1e-9 and np.abs(rd).max() <= 1e-9 * gscale:
+            ok = True
+            it -= 1
+            break
+        w = np.where(live, lh / sh + ll / sl, 0.0)
+        K = _assemble_K(T, c.P, w)
+        try:
+            Lc = np.linalg.cholesky(K)
+        except np.linalg.LinAlgError:
+            break
+
+        def newton(rch, rcl):
+            th = np.where(live, (-rch + lh * rph) / sh, 0.0)
+            tl = np.where(live, (-rcl + ll * rpl) / sl, 0.0)
+            rhs = -rd - _rows_apply_T(T, th - tl)
+            du = np.linalg.solve(Lc.T, np.linalg.solve(Lc, rhs))
+            dz = _rows_apply(T, du)
+            dsh = -rph - dz
+            dsl = -rpl + dz
+            dlh = np.where(live, (-rch - lh * dsh) / sh, 0.0)
+            dll = np.where(live, (-rcl - ll * dsl) / sl, 0.0)
+            return du, dsh, dsl, dlh, dll
+
+        def max_step(v, dv):
+            m = live & (dv < 0)
+            return min(1.0, float((-v[m] / dv[m]).min())) if m.any() else 1.0
+
+        du, dsh, dsl, dlh, dll = newton(lh * sh, ll * sl)
+        a_aff = min(max_step(sh, dsh), max_step(sl, dsl), max_step(lh, dlh), max_step(ll, dll))
+        mu_aff = float(((lh + a_aff * dlh) * (sh + a_aff * dsh) + (ll + a_aff * dll) * (sl + a_aff * dsl))[live].sum()) / nrow
+        sigma = (mu_aff / mu) ** 3
+        du, dsh, dsl, dlh, dll = newton(lh * sh + dsh * dlh - sigma * mu, ll * sl + dsl * dll - sigma * mu)
+        alpha = min(1.0, 0.99 * min(max_step(sh, dsh), max_step(sl, dsl), max_step(lh, dlh), max_step(ll, dll)))
+        u = u + alpha * du
+        sh, sl = sh + alpha * dsh, sl + alpha * dsl
+        lh, ll = lh + alpha * dlh, ll + alpha * dll
+    return u, it, ok
