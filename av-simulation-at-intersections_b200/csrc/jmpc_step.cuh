@@ -528,33 +528,32 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
         const double sw = warp_rscan(w[3], lane);
         if (lane < T) { M.wA[lane] = w[0]; M.wD[lane] = w[1] + w[2] + wup; M.wR[lane] = w[2]; M.SW[lane] = sw; }
       }
+      // P -> shared (the scratch copy is L2 resident); P u is formed from the clean Hessian: folding the
+      // barrier weights in first and subtracting them again would cancel catastrophically once w ~ 1e12
+      for (int e = lane; e < npk; e += 32) M.K[e] = pscr[e];
       __syncwarp();
-      {
-        int i = 0, j = lane;
-        while (j > i) { j -= i + 1; ++i; }
-        for (int e = lane; e < npk; e += 32) {
-          double val = pscr[e];
-          if (i < T) { val += M.SW[i]; if (i == j) val += M.wA[i]; }
-          else if (j >= T) {
-            if (i == j) val += M.wD[i - T];
-            else if (i == j + 1) val -= M.wR[j - T];
-          }
-          M.K[e] = val;
-          j += 32;
-          while (j > i) { j -= i + 1; ++i; }
-        }
-      }
-      __syncwarp();
-      // dual residual: P u + q + A'(lh - ll) = K u + q + A'(lh - ll - w z)
-      double ku0, ku1;
-      symv_packed(M.K, M.u, n, lane, ku0, ku1);
+      double pu0, pu1;
+      symv_packed(M.K, M.u, n, lane, pu0, pu1);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) t4[r] = R.live[r] ? (R.lh[r] - R.ll[r] - w[r] * z[r]) : 0.0;
+      for (int r = 0; r < 4; ++r) t4[r] = R.live[r] ? (R.lh[r] - R.ll[r]) : 0.0;
       double ra, rd;
       rows_apply_T(t4, lane, ra, rd);
-      if (lane < n) M.grad[lane] = ku0 + M.q[lane];
-      if (lane + 32 < n) M.grad[lane + 32] = ku1 + M.q[lane + 32];
+      if (lane < n) M.grad[lane] = pu0 + M.q[lane];
+      if (lane + 32 < n) M.grad[lane + 32] = pu1 + M.q[lane + 32];
       __syncwarp();
+      // K = P + A' diag(w) A: only the accel block and the steer tridiagonal change
+      for (int e = lane; e < tri(T); e += 32) {          // accel x accel, packed rows 0..T-1
+        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while (tri(i + 1) <= e) ++i;
+        while (tri(i) > e) --i;
+        const int j = e - tri(i);
+        M.K[e] += M.SW[i] + ((i == j) ? M.wA[i] : 0.0);
+      }
+      if (lane < T) {
+        const int i = T + lane;
+        M.K[tri(i) + i] += M.wD[lane];
+        if (lane >= 1) M.K[tri(i) + i - 1] -= M.wR[lane - 1];
+      }
       double rdmax = 0.0;
       if (lane < T) {
         const double g0 = M.grad[lane] + ra, g1 = M.grad[T + lane] + rd;
