@@ -273,7 +273,7 @@ int32_t jmpc_set_car_geometry(jmpc_handle h, double front_offset, double rear_of
 int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                   const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa, double* od,
                   const double* params, double* ox, double* oy, double* ov, double* oyaw, double* xref,
-                  double* cost, int32_t* status, int32_t* iters, void* stream) {
+                  double* cost, int32_t* status, int32_t* iters, double* record, void* stream) {
   if (!h) return fail("jmpc_step: NULL handle");
   if (B < 0 || B > h->max_B) return fail("jmpc_step: B out of range");
   if (T < 2 || T > h->max_T) return fail("jmpc_step: T out of range");
@@ -295,7 +295,7 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
   a.state = state; a.course_id = course_id; a.course_len = course_len; a.warm = warm; a.params = params;
   memcpy(a.defaults, h->defaults, sizeof a.defaults);
   a.target_ind = target_ind; a.oa = oa; a.od = od; a.ox = ox; a.oy = oy; a.ov = ov; a.oyaw = oyaw; a.xref = xref;
-  a.cost = cost; a.status = status; a.iters = iters;
+  a.cost = cost; a.status = status; a.iters = iters; a.record = record;
   a.pscratch = h->d_pscratch; a.counter = h->d_counter;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
   jmpc::mpc_step_kernel<<<g.blocks, g.threads, g.smem, s>>>(a);
@@ -307,7 +307,7 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
 int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
                        double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
-                       double* xref, double* cost, int32_t* status, int32_t* iters) {
+                       double* xref, double* cost, int32_t* status, int32_t* iters, double* record) {
   if (!h) return fail("jmpc_step_host: NULL handle");
   if (B < 0 || B > h->max_B) return fail("jmpc_step_host: B out of range");
   if (T < 2 || T > h->max_T) return fail("jmpc_step_host: T out of range");
@@ -327,6 +327,7 @@ int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state,
   const size_t inout_end = off;
   const Seg s_ox = seg(b * T1 * 8), s_oy = seg(b * T1 * 8), s_ov = seg(b * T1 * 8), s_oyaw = seg(b * T1 * 8);
   const Seg s_xref = seg(b * 4 * T1 * 8), s_cost = seg(b * 8), s_status = seg(b * 4), s_iters = seg(b * 4);
+  const Seg s_rec = seg(record ? b * JMPC_RECORD_LEN * 8 : 0);
   const size_t total = off;
   if (ensure_stage(h, total)) return -1;
   char* hs = h->h_stage; char* ds = h->d_stage;
@@ -347,7 +348,7 @@ int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state,
                      params ? (const double*)(ds + s_params.off) : nullptr, (double*)(ds + s_ox.off),
                      (double*)(ds + s_oy.off), (double*)(ds + s_ov.off), (double*)(ds + s_oyaw.off),
                      (double*)(ds + s_xref.off), (double*)(ds + s_cost.off), (int*)(ds + s_status.off),
-                     (int*)(ds + s_iters.off), (void*)st);
+                     (int*)(ds + s_iters.off), record ? (double*)(ds + s_rec.off) : nullptr, (void*)st);
   if (rc) return rc;
   // results: everything from the in-out block to the end.  Instances that fail the index rule or are
   // infeasible keep their input values in the in-out block, so copying it back wholesale is safe.
@@ -362,6 +363,7 @@ int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state,
   memcpy(cost, hs + s_cost.off, s_cost.bytes);
   memcpy(status, hs + s_status.off, s_status.bytes);
   if (iters) memcpy(iters, hs + s_iters.off, s_iters.bytes);
+  if (record) memcpy(record, hs + s_rec.off, s_rec.bytes);
   return 0;
 }
 

@@ -41,6 +41,7 @@ struct StepArgs {
   // in-out / outputs
   int* target_ind; double* oa; double* od;
   double* ox; double* oy; double* ov; double* oyaw; double* xref; double* cost; int* status; int* iters;
+  double* record;           // [B][JMPC_RECORD_LEN] or nullptr
   // scratch
   double* pscratch;         // [resident warps][n(n+1)/2] condensed Hessian, L2 resident
   unsigned int* counter;    // dynamic work queue
@@ -310,7 +311,14 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
     // ---------------- 1. nearest index --------------------------------------------------------------
     const int near = nearest_index(cx, cy, n_course, target, x0, y0, lane);
     if (near < 0) {
-      if (lane == 0) { A.status[b] = JMPC_INDEX_RULE; if (A.iters) A.iters[b] = total_iters; }
+      if (lane == 0) {
+        A.status[b] = JMPC_INDEX_RULE; if (A.iters) A.iters[b] = total_iters;
+        if (A.record) {
+          double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
+          rec[0] = nan(""); rec[1] = nan(""); rec[2] = nan(""); rec[3] = JMPC_INDEX_RULE; rec[4] = A.target_ind[b];
+          rec[5] = total_iters; rec[6] = nan(""); rec[7] = nan("");
+        }
+      }
       return;
     }
     target = near;
@@ -478,8 +486,15 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
         double* xo = A.xref + (size_t)b * 4 * T1;
         xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = 0.0; xo[3 * T1 + lane] = psir;
       }
-      if (lane == 0) { A.status[b] = status; A.target_ind[b] = target; if (A.iters) A.iters[b] = total_iters;
-                       A.cost[b] = nan(""); }
+      if (lane == 0) {
+        A.status[b] = status; A.target_ind[b] = target; if (A.iters) A.iters[b] = total_iters;
+        A.cost[b] = nan("");
+        if (A.record) {
+          double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
+          rec[0] = nan(""); rec[1] = P(JMPC_P_MAX_DECEL); rec[2] = nan(""); rec[3] = status; rec[4] = target;
+          rec[5] = total_iters; rec[6] = nan(""); rec[7] = nan("");
+        }
+      }
       return;
     }
 
@@ -659,9 +674,15 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
         double* xo = A.xref + (size_t)b * 4 * T1;
         xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = 0.0; xo[3 * T1 + lane] = psir;
       }
+      const double v1 = __shfl_sync(kFull, v_t, 1), yaw1 = __shfl_sync(kFull, psi_t, 1);
       if (lane == 0) {
         A.cost[b] = cost; A.status[b] = status; A.target_ind[b] = target;
         if (A.iters) A.iters[b] = total_iters;
+        if (A.record) {
+          double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
+          rec[0] = d_sol; rec[1] = a_sol; rec[2] = cost; rec[3] = status; rec[4] = target; rec[5] = total_iters;
+          rec[6] = v1; rec[7] = yaw1;
+        }
       }
     } else {
       // feed the solution back as the next linearisation point (mpc.py:231-236)

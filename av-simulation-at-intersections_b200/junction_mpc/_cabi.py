@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JMPC_LIB", os.path.join(_HERE, "libjmpc.so"))
 
 JMPC_MAX_T = 31
+RECORD_LEN = 8
 STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_INDEX_RULE = 0, 1, 2, 3
 
 c_i32p = C.POINTER(C.c_int32)
@@ -31,8 +32,8 @@ SIGNATURES = {
     "jmpc_set_courses": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "jmpc_set_car_geometry": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
-    "jmpc_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 16 + [C.c_void_p]),
-    "jmpc_step_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 16),
+    "jmpc_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 17 + [C.c_void_p]),
+    "jmpc_step_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 17),
     "jmpc_collision": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jmpc_collision_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -51,6 +51,7 @@ class StepOutput:
     status: object      # [B] int32 (jmpc_status)
     iters: object       # [B] int32
     target_ind: object  # [B] int32
+    record: object = None  # [B, 8] packed {di, ai, cost, status, target_ind, iters, v_1, yaw_1}
 
 
 class BatchedMPC:
@@ -145,11 +146,12 @@ class BatchedMPC:
         cost = np.full(B, np.nan)
         status = np.zeros(B, np.int32)
         iters = np.zeros(B, np.int32)
+        record = np.zeros((B, _cabi.RECORD_LEN))
         _cabi.check(self._lib.jmpc_step_host(self._h, B, T, _ptr(state), _ptr(cid), _ptr(clen), _ptr(tgt), _ptr(wrm),
                                              _ptr(oa_b), _ptr(od_b), _ptr(prm), _ptr(ox), _ptr(oy), _ptr(ov),
-                                             _ptr(oyaw), _ptr(xref), _ptr(cost), _ptr(status), _ptr(iters)),
-                    "jmpc_step_host")
-        return StepOutput(oa_b, od_b, ox, oy, ov, oyaw, xref, cost, status, iters, tgt)
+                                             _ptr(oyaw), _ptr(xref), _ptr(cost), _ptr(status), _ptr(iters),
+                                             _ptr(record)), "jmpc_step_host")
+        return StepOutput(oa_b, od_b, ox, oy, ov, oyaw, xref, cost, status, iters, tgt, record)
 
     def collision_host(self, agent_idx, v, obstacles, frame_window: int, margin: int, course_id=None,
                        params=None, horizon_s: float = 7.0):
@@ -184,7 +186,8 @@ class BatchedMPC:
         f = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)  # noqa: E731
         i = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)    # noqa: E731
         return StepOutput(oa=None, od=None, ox=f(B, T + 1), oy=f(B, T + 1), ov=f(B, T + 1), oyaw=f(B, T + 1),
-                          xref=f(B, 4, T + 1), cost=f(B), status=i(B), iters=i(B), target_ind=None)
+                          xref=f(B, 4, T + 1), cost=f(B), status=i(B), iters=i(B), target_ind=None,
+                          record=f(B, _cabi.RECORD_LEN))
 
     def step(self, state, target_ind, oa, od, out: StepOutput, course_id=None, course_len=None, warm=None,
              params=None, T: Optional[int] = None, stream: Optional[int] = None) -> StepOutput:
@@ -200,7 +203,7 @@ class BatchedMPC:
             self._dp(target_ind, i32), self._dp(warm, i32), self._dp(oa, f64), self._dp(od, f64), self._dp(params, f64),
             self._dp(out.ox, f64), self._dp(out.oy, f64), self._dp(out.ov, f64), self._dp(out.oyaw, f64),
             self._dp(out.xref, f64), self._dp(out.cost, f64), self._dp(out.status, i32), self._dp(out.iters, i32),
-            C.c_void_p(stream)), "jmpc_step")
+            self._dp(out.record, f64), C.c_void_p(stream)), "jmpc_step")
         out.oa, out.od, out.target_ind = oa, od, target_ind
         return out
 

@@ -95,10 +95,12 @@ def make_obstacles(rng, B: int, n_obs: int) -> np.ndarray:
     return obs
 
 
-def make_workload(config: int, B: Optional[int] = None, cfg: Optional[MPCConfig] = None) -> Dict[str, object]:
-    """Configs 2-5 of BASELINE.json (config 1 is the recorded golden episode under tests/golden/)."""
+def make_workload(config: int, B: Optional[int] = None, cfg: Optional[MPCConfig] = None,
+                  seed_offset: int = 0) -> Dict[str, object]:
+    """Configs 2-5 of BASELINE.json (config 1 is the recorded golden episode under tests/golden/).
+    `seed_offset` gives every rank of a multi-GPU run its own batch (seed = config when 0)."""
     cfg = cfg or MPCConfig.default()
-    rng = np.random.default_rng(config)
+    rng = np.random.default_rng(config if seed_offset == 0 else config * 1000 + seed_offset)
     if config == 2:
         B = B or 4096
         T = 20

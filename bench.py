@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- batched MPC step solves/s on B200 (BASELINE.json metric) and the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (nearest index -> reference sampling -> rollout -> linearise/condense ->
+QP solve -> outputs) over one batch of synthetic instances: config 2 of BASELINE.json, 4096 ego instances x
+20-step horizon per GPU (weak scaling: every rank owns its own seeded batch; the only communication is one
+all-gather of the packed per-instance result record per step, as the north star describes).
+
+Timed region: CUDA events on the launching stream around each step, L2 flushed (256 MiB write) and the
+in-place warm-start buffers restored before every step outside the events; sum over K steps, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "av-simulation-at-intersections_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "batched MPC step solves/sec"
+UNIT = "solves/s"
+
+
+def flops_per_solve(T: int, iters: float) -> float:
+    """Algorithmic flop count of the implemented algorithm."""
+    n = 2 * T
+    f_prep = 64.0 * T
+    f_cond = 15.0 * (T * (T + 1) * (T + 2) / 3.0 + T * (T + 1) * (2 * T + 1) / 6.0) + 12.0 * T * (T + 1)
+    f_iter = n ** 3 / 3.0 + 7.0 * n * n + 240.0 * T
+    return f_prep + f_cond + iters * f_iter
+
+
+def bytes_per_solve(T: int) -> float:
+    return 8.0 * (15 * T + 23)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference(w, sample: int, processes: int, repeats: int = 1):
+    """The CPU controller (oracle port of main/lib/mpc.py, numpy float64) on `sample` instances of the workload,
+    one instance per call as the scenarios call it, spread over `processes` host processes."""
+    from helpers import oracle_batch
+    idx = list(range(sample))
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        res = oracle_batch(w, idx, processes=processes)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert all(r.status == 0 for r in res)
+    return sample / best, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  cvxpy+ECOS cannot be installed
+    offline and the reference is pure Python (nothing to compile into oracle/_ref), so this is the oracle port,
+    on all host cores, on the same config."""
+    if rank != 0:
+        return
+    from junction_mpc import synth
+    w = synth.make_workload(args.config, B=args.ref_sample)
+    cores = os.cpu_count() or 1
+    times = []
+    for k in range(args.warmup + args.steps):
+        rate, dt = cpu_reference(w, args.ref_sample, cores)
+        if k >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = args.ref_sample / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config {args.config}: {w['name']}, {args.ref_sample}-instance sample per step of the "
+                               f"4096 x T={w['T']} batch", "T": w["T"], "instances_per_step": args.ref_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.ref_sample} instances of config {args.config} per step, one solve per call, "
+                                   f"multiprocessing over {cores} processes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's own size)")
+    ap.add_argument("--ref-sample", type=int, default=256)
+    ap.add_argument("--cpu-sample", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    if rank == 0 or not os.path.exists(os.path.join(g.PKG, "junction_mpc", "libjmpc.so")):
+        g.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+
+    from junction_mpc import synth
+    from junction_mpc.batched import BatchedMPC
+    from junction_mpc import _cabi
+
+    # every rank owns its own batch (weak scaling); rank r draws from seed stream config*1000 + r
+    w = synth.make_workload(args.config, B=args.batch or None, seed_offset=rank)
+    B, T = w["B"], w["T"]
+    mpc = BatchedMPC(w["courses"], dl=w["dl"], T=T, max_batch=B, device=local)
+    f64, i32 = torch.float64, torch.int32
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+    state, clen = t(w["state"], f64), t(w["course_len"], i32)
+    tgt0, oa0, od0 = t(w["target_ind"], i32), t(w["oa"], f64), t(w["od"], f64)
+    tgt, oa, od = tgt0.clone(), oa0.clone(), od0.clone()
+    out = mpc.alloc_outputs(B)
+    gathered = torch.empty(world * B, _cabi.RECORD_LEN, dtype=f64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def one_step(e0=None, e1=None):
+        flush.zero_()
+        tgt.copy_(tgt0); oa.copy_(oa0); od.copy_(od0)
+        if e0 is not None:
+            e0.record()
+        mpc.step(state, tgt, oa, od, out, course_len=clen)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out.record)
+        if e1 is not None:
+            e1.record()
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = mpc.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for e0, e1 in evs:
+        one_step(e0, e1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.finish()
+    launches = mpc.launch_count - launches0
+    per_step = np.array([e0.elapsed_time(e1) for e0, e1 in evs])            # ms
+    total_ms = torch.tensor([per_step.sum()], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    status = out.status.cpu().numpy()
+    iters = out.iters.cpu().numpy()
+    assert (status == 0).all(), f"{(status != 0).sum()} instances not solved"
+
+    # end to end through the host API: pinned staging, H2D of the step's inputs and D2H of its results inside
+    e2e_steps = max(3, min(args.steps, 20))
+    h2d = w["state"].nbytes + w["oa"].nbytes + w["od"].nbytes + 4 * B * 2
+    T1 = T + 1
+    d2h = 8 * B * (2 * T + 4 * T1 + 4 * T1 + 1 + _cabi.RECORD_LEN) + 4 * B * 3
+    for _ in range(2):
+        mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"])
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ho = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"])
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(e2e_ms.item()) * 1e-3)
+    assert (ho.status == 0).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the (single) kernel of the step: CUDA-core FP64 FMA bound
+    fp64_peak, fp32_peak = mpc.measure_fma_peak()
+    kernel_ms = float(np.mean(per_step))
+    mean_iters = float(iters.mean())
+    fl = flops_per_solve(T, mean_iters) * B
+    achieved = fl / (kernel_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_ach = bytes_per_solve(T) * B / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"config {args.config}: {w['name']}, {B} synthetic ego instances x T={T} per GPU "
+                               f"(BASELINE.json configs[{args.config - 1}])", "instances_per_gpu": B, "T": T,
+                   "l2": "flushed with a 256 MiB write before every timed step",
+                   "solver": "condensed QP, Mehrotra predictor-corrector interior point, fp64",
+                   "mean_solver_iters": mean_iters, "max_solver_iters": int(iters.max())},
+        "p50_ms": float(np.percentile(per_step, 50)), "p99_ms": float(np.percentile(per_step, 99)),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": float(e2e_ms.item()), "steps": e2e_steps,
+                "api": "BatchedMPC.step_host -> jmpc_step_host (host numpy in, host numpy out)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                     "peak_source": "jmpc_measure_fma_peak: register-resident FP64 FMA loop on all SMs, measured in this run "
+                                    "(MEASURED_PEAKS.json holds no FP64 figure)",
+                     "flops_per_solve": flops_per_solve(T, mean_iters), "kernel": "jmpc::mpc_step_kernel",
+                     "kernel_ms": kernel_ms, "fp32_peak_tflops": fp32_peak,
+                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "bytes_per_solve": bytes_per_solve(T),
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md"}},
+    }
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        rate, dt = cpu_reference(w, min(args.cpu_sample, B), cores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"first {min(args.cpu_sample, B)} instances of the same batch, numpy float64 "
+                                          f"oracle (restated main/lib/mpc.py, certified QP solve), one solve per call, "
+                                          f"{cores} processes, {dt:.1f} s wall"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

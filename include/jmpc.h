@@ -34,6 +34,7 @@ extern "C" {
 #endif
 
 #define JMPC_ABI_VERSION 1
+#define JMPC_RECORD_LEN 8         /* doubles per instance in the packed result record, see jmpc_step */
 #define JMPC_MAX_T 31           /* horizon limit of the warp-per-instance kernels (reference GUI range 5..25) */
 
 /* Row order of a parameter vector.  Derivations as in main/lib/mpc.py:14-39 and main/lib/simulation.py:23-25:
@@ -112,17 +113,20 @@ int32_t jmpc_set_car_geometry(jmpc_handle h, double front_offset, double rear_of
  *   target_ind [B] in: search start, out: new nearest index            (mpc.py:94, :298)
  *   warm       [B] or NULL: 0 -> treat oa/od as zeros (mpc.py:225-227), 1 -> use them
  *   cost       [B]: objective value at the optimum, constants included (what `prob.value` would be)
- *   iters      [B] or NULL: solver iterations used */
+ *   iters      [B] or NULL: solver iterations used
+ *   record     [B][JMPC_RECORD_LEN] or NULL: packed per-instance result written by the kernel's epilogue --
+ *              {di = od[0], ai = oa[0] (MAX_DECEL when not solved, mpc.py:298-301), cost, status, target_ind,
+ *              iters, v_1, yaw_1} -- one contiguous buffer, the send buffer of the multi-GPU all-gather */
 int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                   const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa, double* od,
                   const double* params, double* ox, double* oy, double* ov, double* oyaw, double* xref,
-                  double* cost, int32_t* status, int32_t* iters, void* stream);
+                  double* cost, int32_t* status, int32_t* iters, double* record, void* stream);
 
 /* Same with HOST pointers: copies in, runs, copies out, synchronises. */
 int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
                        double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
-                       double* xref, double* cost, int32_t* status, int32_t* iters);
+                       double* xref, double* cost, int32_t* status, int32_t* iters, double* record);
 
 /* Collision flag + cut index for B instances (mpc_intersection.py:111-140, collision_avoidance.py:85-124,
  * 168-180, moving_obstacles_prediction.py:21-47, trajectories.py:58-86).  DEVICE pointers.
