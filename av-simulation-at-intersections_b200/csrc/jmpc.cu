@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -66,16 +67,21 @@ int step_geometry(jmpc_handle h, int B, int T, StepGeom* g) {
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(jmpc::mpc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(jmpc::mpc_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jmpc::mpc_step_kernel, wpb * 32, smem));
   if (per_sm < 1) return fail("step kernel does not fit on an SM for this horizon");
-  if (h->opt.warps_per_sm > 0) per_sm = std::max(1, std::min(per_sm, h->opt.warps_per_sm / wpb));
+  int cap = h->opt.warps_per_sm;
+  if (const char* e = getenv("JMPC_WARPS_PER_SM")) cap = atoi(e);
+  if (cap > 0) per_sm = std::max(1, std::min(per_sm, cap / wpb));
   int blocks = h->sm_count * per_sm;
   const int need = (B + wpb - 1) / wpb;
   if (blocks > need) blocks = need;
   g->blocks = blocks; g->threads = wpb * 32; g->smem = smem; g->warps = blocks * wpb;
+  if (getenv("JMPC_DEBUG")) fprintf(stderr, "[jmpc] step geometry: T=%d B=%d blocks=%d (%d per SM) smem/block=%zu\n", T, B, blocks, per_sm, smem);
   return 0;
 }
 

@@ -693,7 +693,7 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
 }
 
 // Persistent kernel: every resident warp pulls instances from a global counter.
-__global__ void __launch_bounds__(128) mpc_step_kernel(const StepArgs A) {
+__global__ void __launch_bounds__(128, 4) mpc_step_kernel(const StepArgs A) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;

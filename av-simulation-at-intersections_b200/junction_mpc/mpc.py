@@ -1,0 +1,235 @@
+"""Drop-in replacement of the reference's `lib.mpc` module (main/lib/mpc.py), backed by libjmpc.so.
+
+Everything a scenario runner touches keeps its name, signature and types:
+
+    from lib.mpc import MPC, MAX_ACCEL                                   mpc_intersection.py:20
+    mpc = MPC(cx=..., cy=..., cyaw=..., dl=..., dt=DT, car_dimensions=..., speed=30/3.6)     mpc.py:246-247
+    mpc.set_trajectory_fromarray(tmp_trajectory)                          mpc.py:279-282
+    delta, acceleration = mpc.step(state)                                 mpc.py:284-303
+    mpc.get_current_xref_deviation(); mpc.is_goal(state)                  mpc.py:305-330
+    mpc.ox, mpc.oy, mpc.xref, mpc.di                                      mpc_intersection.py:301-306
+
+A single ego is a batch of one: `step` runs the same CUDA kernel as `BatchedMPC` through `jmpc_step_host`.
+`install()` registers this module as `lib.mpc` (and the sensitivity flavour as `lib.mpc_sensitivity`) so the
+reference's scenario scripts run unmodified; see INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _cabi
+from .batched import BatchedMPC
+from .config import MPCConfig, SIM_MAX_SPEED
+
+# ---- module-level configuration, as main/lib/mpc.py:14-39 exposes it --------------------------------------
+_config_path = os.environ.get("JMPC_CONFIG")
+_cfg = MPCConfig.from_json(_config_path) if _config_path else MPCConfig.default()
+
+NX, NU, T = _cfg.nx, _cfg.nu, _cfg.T
+w_perp, w_para = _cfg.w_perp, _cfg.w_para
+R, Rd = np.diag(_cfg.R), np.diag(_cfg.Rd)
+Q_v_yaw = np.diag(_cfg.Q_v_yaw)
+Qf = np.diag(_cfg.Qf_raw) * T
+GOAL_DIS, STOP_SPEED, MAX_TIME = _cfg.goal_dis, _cfg.stop_speed, _cfg.max_time
+MAX_ITER, DU_TH = _cfg.max_iter, _cfg.du_th
+MAX_DSTEER = _cfg.max_dsteer
+MAX_ACCEL, MAX_DECEL = _cfg.max_accel, _cfg.max_decel
+
+
+class MPCSolutionNotFoundException(Exception):
+    pass
+
+
+def smooth_yaw(yaw):
+    """In-place yaw unwrapping (mpc.py:46-58); returns its argument."""
+    for k in range(len(yaw) - 1):
+        while yaw[k + 1] - yaw[k] >= math.pi / 2.0:
+            yaw[k + 1] -= math.pi * 2.0
+        while yaw[k + 1] - yaw[k] <= -math.pi / 2.0:
+            yaw[k + 1] += math.pi * 2.0
+    return yaw
+
+
+class MPC:
+    """Stateful single-ego controller with the reference's interface."""
+
+    _reload_config_each_step = False      # the sensitivity flavour re-reads its JSON in every solve
+    _config = _cfg
+
+    def __init__(self, cx: np.ndarray, cy: np.ndarray, cyaw: np.ndarray, dl: float, car_dimensions,
+                 speed: float = 30 / 3.6, dt: float = 0.2):
+        self.cx = cx
+        self.cy = cy
+        cyaw = smooth_yaw(cyaw)           # in place, on the caller's view of trajectory_full[:, 2] (mpc.py:260)
+        self.cyaw = cyaw
+        self.dl = dl
+        self.dt = dt
+        self.car_dimensions = car_dimensions
+        self.speed = speed
+        self.goal: Tuple[float, float] = cx[-1], cy[-1]
+        self.target_ind: int = 0
+        self.odelta: Optional[List[float]] = None
+        self.oa: Optional[List[float]] = None
+        self.ox = self.oy = self.oyaw = self.ov = self.xref = None
+        self.di: float = 0.0
+        self.ai: float = 0.0
+        self.status: int = _cabi.STATUS_OPTIMAL
+        self.iterations: int = 0
+        self.cost: float = float("nan")
+        self._full = np.stack([np.asarray(cx, float), np.asarray(cy, float), np.asarray(cyaw, float)], axis=1)
+        self._engine = self._make_engine(self._config)
+
+    # ---- engine plumbing ------------------------------------------------------------------------------------
+    def _make_engine(self, cfg: MPCConfig) -> BatchedMPC:
+        L = float(self.car_dimensions.distance_back_to_front_wheel)
+        self._cfg_used = cfg
+        return BatchedMPC([self._full], dl=float(self.dl), T=cfg.T, config=cfg, dt=float(self.dt), L=L,
+                          speed=float(self.speed), max_batch=1, max_T=_cabi.JMPC_MAX_T)
+
+    def _effective_length(self) -> int:
+        """`set_trajectory_fromarray(trajectory_full[:k])` always passes a prefix of the course given to the
+        constructor (mpc_intersection.py:138); it is expressed as an effective length on the uploaded table.
+        Anything else is uploaded afresh."""
+        n = len(self.cx)
+        full = self._full
+        if n <= len(full) and n >= 1 and self.cx[0] == full[0, 0] and self.cx[n - 1] == full[n - 1, 0] \
+                and self.cy[n - 1] == full[n - 1, 1] and self.cyaw[n - 1] == full[n - 1, 2] \
+                and (n < 3 or self.cx[n // 2] == full[n // 2, 0]):
+            return n
+        self._full = np.stack([np.asarray(self.cx, float), np.asarray(self.cy, float), np.asarray(self.cyaw, float)],
+                              axis=1)
+        self._engine.close()
+        self._engine = self._make_engine(self._cfg_used)
+        return n
+
+    # ---- reference interface --------------------------------------------------------------------------------
+    def set_trajectory_fromarray(self, trajectory: np.ndarray):
+        self.cx = trajectory[:, 0]
+        self.cy = trajectory[:, 1]
+        self.cyaw = trajectory[:, 2]
+
+    def step(self, state) -> Tuple[float, float]:
+        if self._reload_config_each_step:
+            cfg = type(self)._load_config()
+            if cfg != self._cfg_used:
+                self._engine.close()
+                self._engine = self._make_engine(cfg)
+        n = self._effective_length()
+        Th = self._cfg_used.T
+        warm = self.oa is not None and self.odelta is not None
+        x0 = np.array([[state.x, state.y, state.v, state.yaw]], dtype=np.float64)
+        out = self._engine.step_host(
+            x0, np.array([self.target_ind], np.int32),
+            oa=np.asarray(self.oa, float).reshape(1, Th) if warm else np.zeros((1, Th)),
+            od=np.asarray(self.odelta, float).reshape(1, Th) if warm else np.zeros((1, Th)),
+            course_len=np.array([n], np.int32), warm=np.array([1 if warm else 0], np.int32))
+        self.status = int(out.status[0])
+        self.iterations = int(out.iters[0])
+        if self.status == _cabi.STATUS_INDEX_RULE:
+            raise Exception("something wrong")                     # trajectories.py:120
+        self.target_ind = int(out.target_ind[0])
+        self.xref = out.xref[0]
+        if self.status == _cabi.STATUS_INFEASIBLE:
+            print("Error: Cannot solve mpc...", file=sys.stderr)   # mpc.py:207-209
+            self.oa = self.odelta = self.ox = self.oy = self.oyaw = self.ov = None
+            self.ai = MAX_DECEL if not self._reload_config_each_step else self._cfg_used.max_decel
+            return self.di, self.ai
+        self.oa, self.odelta = out.oa[0], out.od[0]
+        self.ox, self.oy, self.ov, self.oyaw = out.ox[0], out.oy[0], out.ov[0], out.oyaw[0]
+        self.cost = float(out.cost[0])
+        self.di, self.ai = float(self.odelta[0]), float(self.oa[0])
+        return self.di, self.ai
+
+    def get_current_xref_deviation(self):
+        ref_point = np.array([self.cx[self.target_ind], self.cy[self.target_ind]])
+        true_point = np.array([self.ox[0], self.oy[0]])
+        ref_yaw_perp = self.cyaw[self.target_ind] + np.pi / 2
+        diff = ref_point - true_point
+        return np.linalg.norm(np.array([np.cos(ref_yaw_perp) * diff[0], np.sin(ref_yaw_perp) * diff[1]]))
+
+    def is_goal(self, state) -> bool:
+        d = math.hypot(state.x - self.goal[0], state.y - self.goal[1])
+        isgoal = d <= self._cfg_used.goal_dis
+        if abs(self.target_ind - len(self.cx)) >= 5:
+            isgoal = False
+        isstop = abs(state.v) <= self._cfg_used.stop_speed
+        return bool(isgoal and isstop)
+
+
+# ---- the sensitivity flavour (main/lib/mpc_sensitivity.py) ---------------------------------------------------
+class _SensitivityMPC(MPC):
+    """`lib.mpc_sensitivity.MPC`: no `speed` argument (Simulation.MAX_SPEED is the cap, mpc_sensitivity.py:207)
+    and the JSON is re-read inside every solve (mpc_sensitivity.py:153-166), which is how the sweep script changes
+    weights between runs."""
+    _reload_config_each_step = True
+    _config_file: Optional[str] = None
+
+    def __init__(self, cx, cy, cyaw, dl, car_dimensions, dt: float = 0.2):
+        type(self)._config = type(self)._load_config()
+        super().__init__(cx, cy, cyaw, dl, car_dimensions, speed=SIM_MAX_SPEED, dt=dt)
+
+    @classmethod
+    def _load_config(cls) -> MPCConfig:
+        path = cls._config_file or os.environ.get("JMPC_CONFIG_SENSITIVITY")
+        return MPCConfig.from_json(path) if path else MPCConfig.default()
+
+
+def _module_from(cls, cfg: MPCConfig, name: str) -> types.ModuleType:
+    m = types.ModuleType(name)
+    m.__doc__ = f"junction_mpc drop-in for the reference module {name}"
+    m.MPC = cls
+    m.MPCSolutionNotFoundException = MPCSolutionNotFoundException
+    m.smooth_yaw = smooth_yaw
+    m.NX, m.NU, m.T = cfg.nx, cfg.nu, cfg.T
+    m.w_perp, m.w_para = cfg.w_perp, cfg.w_para
+    m.R, m.Rd, m.Q_v_yaw = np.diag(cfg.R), np.diag(cfg.Rd), np.diag(cfg.Q_v_yaw)
+    m.Qf = np.diag(cfg.Qf_raw) * cfg.T
+    m.GOAL_DIS, m.STOP_SPEED, m.MAX_TIME = cfg.goal_dis, cfg.stop_speed, cfg.max_time
+    m.MAX_ITER, m.DU_TH = cfg.max_iter, cfg.du_th
+    m.MAX_DSTEER, m.MAX_ACCEL, m.MAX_DECEL = cfg.max_dsteer, cfg.max_accel, cfg.max_decel
+    return m
+
+
+def install(reference_main: Optional[str] = None) -> None:
+    """Make `from lib.mpc import MPC, MAX_ACCEL` and `from lib.mpc_sensitivity import MPC, MAX_ACCEL` resolve to
+    this implementation.  `reference_main` is the reference's `main/` directory: its `config/mpc_config.json` and
+    `config/mpc_config_sensitivity.json` are read unchanged, and it is put on sys.path so the rest of `lib`
+    (simulation, collision_avoidance, ...) is still the reference's own code."""
+    global _cfg
+    cfg, sens_cfg_path = _cfg, None
+    if reference_main:
+        if reference_main not in sys.path:
+            sys.path.insert(0, reference_main)
+        p = os.path.join(reference_main, "config", "mpc_config.json")
+        if os.path.exists(p):
+            cfg = MPCConfig.from_json(p)
+        p = os.path.join(reference_main, "config", "mpc_config_sensitivity.json")
+        if os.path.exists(p):
+            sens_cfg_path = p
+
+    class _MPC(MPC):
+        _config = cfg
+    _MPC.__name__ = _MPC.__qualname__ = "MPC"
+
+    class _SMPC(_SensitivityMPC):
+        _config_file = sens_cfg_path
+    _SMPC.__name__ = _SMPC.__qualname__ = "MPC"
+
+    sys.modules["lib.mpc"] = _module_from(_MPC, cfg, "lib.mpc")
+    sens_cfg = MPCConfig.from_json(sens_cfg_path) if sens_cfg_path else cfg
+    sys.modules["lib.mpc_sensitivity"] = _module_from(_SMPC, sens_cfg, "lib.mpc_sensitivity")
+    try:                                   # `import lib.mpc` also needs the attribute on the package
+        import lib                         # the reference's package, when reference_main is on sys.path
+        lib.mpc = sys.modules["lib.mpc"]
+        lib.mpc_sensitivity = sys.modules["lib.mpc_sensitivity"]
+    except ImportError:
+        pkg = types.ModuleType("lib")
+        pkg.__path__ = []
+        pkg.mpc, pkg.mpc_sensitivity = sys.modules["lib.mpc"], sys.modules["lib.mpc_sensitivity"]
+        sys.modules["lib"] = pkg
