@@ -292,7 +292,7 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
   StepGeom g;
   if (step_geometry(h, B, T, &g)) return -1;
   const int n = 2 * T;
-  if (ensure_scratch(h, (size_t)g.warps * (n * (n + 1) / 2))) return -1;
+  if (ensure_scratch(h, (size_t)g.warps * jmpc::tiles_doubles(n))) return -1;
   jmpc::StepArgs a;
   a.B = B; a.T = T; a.lin_iters = h->opt.linearisation_iters; a.max_iters = h->opt.max_solver_iters;
   a.mu_tol = h->opt.mu_tol;
@@ -463,6 +463,32 @@ int32_t jmpc_plant_step(jmpc_handle h, int32_t B, double* state, const double* a
 }
 
 int64_t jmpc_launch_count(jmpc_handle h) { return h ? h->launches : 0; }
+
+int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const double* b, const double* x, double* sol,
+                          double* prod) {
+  if (!h || !A || !b || !x || !sol || !prod) return fail("jmpc_debug_linalg: NULL argument");
+  if (n < 1 || n > 2 * JMPC_MAX_T) return fail("jmpc_debug_linalg: n out of range");
+  CK(cudaSetDevice(h->device));
+  const size_t nn = (size_t)n * n;
+  if (ensure_stage(h, (nn + 4 * (size_t)n + 2) * sizeof(double))) return -1;
+  double* d = (double*)h->d_stage;
+  double *dA = d, *db = dA + nn, *dx = db + n, *dsol = dx + n, *dprod = dsol + n;
+  int* dok = (int*)(dprod + n);
+  CK(cudaMemcpy(dA, A, nn * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+  const int nb = jmpc::nblk(n);
+  const size_t smem = (jmpc::tiles_doubles(n) + 16 * nb + 8 * nb) * sizeof(double);
+  jmpc::linalg_selftest_kernel<<<1, 32, smem, h->own_stream>>>(n, dA, db, dx, dsol, dprod, dok);
+  CK(cudaGetLastError());
+  h->launches++;
+  CK(cudaStreamSynchronize(h->own_stream));
+  int ok = 0;
+  CK(cudaMemcpy(sol, dsol, n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(prod, dprod, n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost));
+  return ok ? 0 : 1;
+}
 
 int32_t jmpc_measure_fma_peak(jmpc_handle h, double* fp64_tflops, double* fp32_tflops) {
   if (!h || !fp64_tflops || !fp32_tflops) return fail("jmpc_measure_fma_peak: NULL argument");

@@ -1,0 +1,227 @@
+// jmpc_linalg.cuh -- warp-cooperative dense linear algebra on 4x4 tiles in shared memory (fp64).
+//
+// A symmetric n x n matrix (n = 2T <= 62) is stored as its lower block triangle of 4x4 tiles: tile (I, J),
+// I >= J, sits at slot I(I+1)/2 + J, each slot kTS = 18 doubles (16 used, row major).  The 144-byte slot stride
+// keeps every tile 16-byte aligned for 128-bit shared loads and spreads tiles that different lanes touch at the
+// same in-tile offset over different banks (36 words apart; 128-bit accesses are served per quarter warp).
+// Diagonal tiles of a *matrix* (not of a factor) are stored full (both triangles).  n is padded to a multiple of
+// 4 with identity rows.
+//
+// Compared with a column-at-a-time factorisation on a packed triangle this does 64 FMAs per 32 shared-memory
+// instructions in the trailing update instead of 1 per 2, and synchronises the warp 3 times per 4 columns.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace jmpc {
+
+constexpr int kTS = 18;                               // doubles per tile slot
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__host__ __device__ inline int nblk(int n) { return (n + 3) >> 2; }
+__host__ __device__ inline int tiles_doubles(int n) { const int nb = nblk(n); return (nb * (nb + 1) / 2) * kTS; }
+__host__ __device__ __forceinline__ int tile_off(int I, int J) { return (((I * (I + 1)) >> 1) + J) * kTS; }
+// element (i, j) with j <= i, or any (i, j) inside a diagonal tile
+__host__ __device__ __forceinline__ int elem_off(int i, int j) { return tile_off(i >> 2, j >> 2) + ((i & 3) << 2) + (j & 3); }
+
+__device__ __forceinline__ void ld4(const double* p, double& a, double& b, double& c, double& d) {
+  const double2 x = *reinterpret_cast<const double2*>(p), y = *reinterpret_cast<const double2*>(p + 2);
+  a = x.x; b = x.y; c = y.x; d = y.y;
+}
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+}
+
+// In-place Cholesky K = L L' on tiles.  Dinv receives the inverses of the diagonal blocks of L (nb x 16 doubles,
+// lower triangular), which turn the panel and the triangular solves into multiplications.
+// Returns false when a pivot is not positive (all lanes agree).
+__device__ inline bool chol_tiles(double* __restrict__ K, double* __restrict__ Dinv, int nb, int lane) {
+  for (int J = 0; J < nb; ++J) {
+    // ---- diagonal block: every lane factors it redundantly in registers (no broadcast needed)
+    const double* D = K + tile_off(J, J);
+    double a00, a10, a11, a20, a21, a22, a30, a31, a32, a33;
+    {
+      double u01, u02, u03, u12, u13, u23;             // upper triangle of the block: loaded, not used
+      ld4(D, a00, u01, u02, u03); ld4(D + 4, a10, a11, u12, u13);
+      ld4(D + 8, a20, a21, a22, u23); ld4(D + 12, a30, a31, a32, a33);
+      (void)u01; (void)u02; (void)u03; (void)u12; (void)u13; (void)u23;
+    }
+    if (!(a00 > 0.0)) return false;
+    const double r0 = rsqrt(a00);
+    const double l00 = a00 * r0, l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+    a11 = fma(-l10, l10, a11);
+    if (!(a11 > 0.0)) return false;
+    const double r1 = rsqrt(a11);
+    const double l11 = a11 * r1, l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
+    a22 = fma(-l21, l21, fma(-l20, l20, a22));
+    if (!(a22 > 0.0)) return false;
+    const double r2 = rsqrt(a22);
+    const double l22 = a22 * r2, l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
+    a33 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
+    if (!(a33 > 0.0)) return false;
+    const double r3 = rsqrt(a33);
+    const double l33 = a33 * r3;
+    // M = L^{-1} (lower triangular)
+    const double m00 = r0, m11 = r1, m22 = r2, m33 = r3;
+    const double m10 = -(l10 * m00) * r1;
+    const double m21 = -(l21 * m11) * r2;
+    const double m32 = -(l32 * m22) * r3;
+    const double m20 = -fma(l21, m10, l20 * m00) * r2;
+    const double m31 = -fma(l32, m21, l31 * m11) * r3;
+    const double m30 = -fma(l32, m20, fma(l31, m10, l30 * m00)) * r3;
+    __syncwarp();                                    // every lane has read the block before it is overwritten
+    // ---- panel below the block: X = A L^{-T}, one matrix row per lane
+    const int prow = (nb - J - 1) << 2;
+    for (int r = lane; r < prow; r += 32) {
+      double* row = K + tile_off(J + 1 + (r >> 2), J) + ((r & 3) << 2);
+      double a0, a1, a2, a3;
+      ld4(row, a0, a1, a2, a3);
+      st4(row, a0 * m00, fma(a1, m11, a0 * m10), fma(a2, m22, fma(a1, m21, a0 * m20)),
+          fma(a3, m33, fma(a2, m32, fma(a1, m31, a0 * m30))));
+    }
+    if (lane == 0) {
+      double* Dw = K + tile_off(J, J);
+      st4(Dw, l00, 0.0, 0.0, 0.0); st4(Dw + 4, l10, l11, 0.0, 0.0);
+      st4(Dw + 8, l20, l21, l22, 0.0); st4(Dw + 12, l30, l31, l32, l33);
+    } else if (lane == 1) {
+      double* Mw = Dinv + (J << 4);
+      st4(Mw, m00, 0.0, 0.0, 0.0); st4(Mw + 4, m10, m11, 0.0, 0.0);
+      st4(Mw + 8, m20, m21, m22, 0.0); st4(Mw + 12, m30, m31, m32, m33);
+    }
+    __syncwarp();
+    // ---- trailing update: C(I, Kc) -= L(I, J) L(Kc, J)', one tile per lane
+    const int m = nb - J - 1, ntiles = (m * (m + 1)) >> 1;
+    for (int t = lane; t < ntiles; t += 32) {
+      int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while (((a + 1) * (a + 2) >> 1) <= t) ++a;
+      while (((a * (a + 1)) >> 1) > t) --a;
+      const int b = t - ((a * (a + 1)) >> 1);
+      const int I = J + 1 + a, Kc = J + 1 + b;
+      const double* LI = K + tile_off(I, J);
+      const double* LK = K + tile_off(Kc, J);
+      double* C = K + tile_off(I, Kc);
+      double k00, k01, k02, k03, k10, k11, k12, k13, k20, k21, k22, k23, k30, k31, k32, k33;
+      ld4(LK, k00, k01, k02, k03); ld4(LK + 4, k10, k11, k12, k13);
+      ld4(LK + 8, k20, k21, k22, k23); ld4(LK + 12, k30, k31, k32, k33);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        double x0, x1, x2, x3, c0, c1, c2, c3;
+        ld4(LI + 4 * r, x0, x1, x2, x3);
+        ld4(C + 4 * r, c0, c1, c2, c3);
+        c0 = fma(-x3, k03, fma(-x2, k02, fma(-x1, k01, fma(-x0, k00, c0))));
+        c1 = fma(-x3, k13, fma(-x2, k12, fma(-x1, k11, fma(-x0, k10, c1))));
+        c2 = fma(-x3, k23, fma(-x2, k22, fma(-x1, k21, fma(-x0, k20, c2))));
+        c3 = fma(-x3, k33, fma(-x2, k32, fma(-x1, k31, fma(-x0, k30, c3))));
+        st4(C + 4 * r, c0, c1, c2, c3);
+      }
+    }
+    __syncwarp();
+  }
+  return true;
+}
+
+// Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).
+__device__ inline void solve_tiles(const double* __restrict__ K, const double* __restrict__ Dinv,
+                                   double* __restrict__ b, int nb, int lane) {
+  const int n4 = nb << 2;
+  for (int J = 0; J < nb; ++J) {                      // forward: L y = b
+    const double* Mw = Dinv + (J << 4);
+    double b0, b1, b2, b3;
+    ld4(b + (J << 2), b0, b1, b2, b3);
+    const double m00 = Mw[0], m10 = Mw[4], m11 = Mw[5], m20 = Mw[8], m21 = Mw[9], m22 = Mw[10];
+    double m30, m31, m32, m33;
+    ld4(Mw + 12, m30, m31, m32, m33);
+    const double y0 = m00 * b0, y1 = fma(m11, b1, m10 * b0), y2 = fma(m22, b2, fma(m21, b1, m20 * b0));
+    const double y3 = fma(m33, b3, fma(m32, b2, fma(m31, b1, m30 * b0)));
+    __syncwarp();
+    for (int i = ((J + 1) << 2) + lane; i < n4; i += 32) {
+      double l0, l1, l2, l3;
+      ld4(K + tile_off(i >> 2, J) + ((i & 3) << 2), l0, l1, l2, l3);
+      b[i] = fma(-l3, y3, fma(-l2, y2, fma(-l1, y1, fma(-l0, y0, b[i]))));
+    }
+    if (lane == 0) st4(b + (J << 2), y0, y1, y2, y3);
+    __syncwarp();
+  }
+  for (int J = nb - 1; J >= 0; --J) {                 // backward: L' x = y
+    const double* Mw = Dinv + (J << 4);
+    double y0, y1, y2, y3;
+    ld4(b + (J << 2), y0, y1, y2, y3);
+    const double m00 = Mw[0], m10 = Mw[4], m11 = Mw[5], m20 = Mw[8], m21 = Mw[9], m22 = Mw[10];
+    double m30, m31, m32, m33;
+    ld4(Mw + 12, m30, m31, m32, m33);
+    const double x3 = m33 * y3, x2 = fma(m32, y3, m22 * y2), x1 = fma(m31, y3, fma(m21, y2, m11 * y1));
+    const double x0 = fma(m30, y3, fma(m20, y2, fma(m10, y1, m00 * y0)));
+    __syncwarp();
+    for (int i = lane; i < (J << 2); i += 32) {
+      const double* col = K + tile_off(J, i >> 2) + (i & 3);
+      b[i] = fma(-col[12], x3, fma(-col[8], x2, fma(-col[4], x1, fma(-col[0], x0, b[i]))));
+    }
+    if (lane == 0) st4(b + (J << 2), x0, x1, x2, x3);
+    __syncwarp();
+  }
+}
+
+// y = P x for a symmetric P on tiles (diagonal tiles stored full); lane owns rows lane and lane + 32.
+__device__ inline void symv_tiles(const double* __restrict__ P, const double* __restrict__ x, int nb, int lane,
+                                  double& y0, double& y1) {
+  const int n4 = nb << 2;
+  y0 = 0.0; y1 = 0.0;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int i = lane + 32 * pass;
+    if (i < n4) {
+      const int I = i >> 2, r = i & 3;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int J = 0; J <= I; ++J) {
+        double p0, p1, p2, p3, x0, x1, x2, x3;
+        ld4(P + tile_off(I, J) + (r << 2), p0, p1, p2, p3);
+        ld4(x + (J << 2), x0, x1, x2, x3);
+        acc0 = fma(p1, x1, fma(p0, x0, acc0));
+        acc1 = fma(p3, x3, fma(p2, x2, acc1));
+      }
+      for (int J = I + 1; J < nb; ++J) {
+        const double* col = P + tile_off(J, I) + r;
+        double x0, x1, x2, x3;
+        ld4(x + (J << 2), x0, x1, x2, x3);
+        acc0 = fma(col[4], x1, fma(col[0], x0, acc0));
+        acc1 = fma(col[12], x3, fma(col[8], x2, acc1));
+      }
+      if (pass == 0) y0 = acc0 + acc1; else y1 = acc0 + acc1;
+    }
+  }
+}
+
+// Self-test kernel: one warp packs a dense symmetric matrix into tiles, multiplies, factors and solves.
+__global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, const double* __restrict__ b,
+                                       const double* __restrict__ x, double* __restrict__ sol,
+                                       double* __restrict__ prod, int* __restrict__ ok) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, nb = nblk(n), n4 = nb << 2;
+  double* K = sm;
+  double* Dinv = K + tiles_doubles(n);
+  double* rhs = Dinv + 16 * nb;
+  double* xv = rhs + n4;
+  for (int e = lane; e < tiles_doubles(n); e += 32) K[e] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < n4 * n4; e += 32) {
+    const int i = e / n4, j = e % n4;
+    if (j > i && (i >> 2) != (j >> 2)) continue;
+    double v = (i < n && j < n) ? A[i * n + j] : ((i == j) ? 1.0 : 0.0);
+    K[elem_off(i, j)] = v;
+  }
+  for (int i = lane; i < n4; i += 32) { rhs[i] = (i < n) ? b[i] : 0.0; xv[i] = (i < n) ? x[i] : 0.0; }
+  __syncwarp();
+  double y0, y1;
+  symv_tiles(K, xv, nb, lane, y0, y1);
+  if (lane < n) prod[lane] = y0;
+  if (lane + 32 < n) prod[lane + 32] = y1;
+  __syncwarp();
+  const bool good = chol_tiles(K, Dinv, nb, lane);
+  if (good) solve_tiles(K, Dinv, rhs, nb, lane);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) sol[i] = rhs[i];
+  if (lane == 0) *ok = good ? 1 : 0;
+}
+
+}  // namespace jmpc

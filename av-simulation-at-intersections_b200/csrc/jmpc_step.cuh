@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "../../include/jmpc.h"
+#include "jmpc_linalg.cuh"
 
 namespace jmpc {
 
@@ -43,20 +44,20 @@ struct StepArgs {
   double* ox; double* oy; double* ov; double* oyaw; double* xref; double* cost; int* status; int* iters;
   double* record;           // [B][JMPC_RECORD_LEN] or nullptr
   // scratch
-  double* pscratch;         // [resident warps][n(n+1)/2] condensed Hessian, L2 resident
+  double* pscratch;         // [resident warps][tiles_doubles(n)] condensed Hessian on tiles, L2 resident
   unsigned int* counter;    // dynamic work queue
 };
 
-// shared-memory doubles one warp needs for horizon T
+// shared-memory doubles one warp needs for horizon T (every sub-array starts 16-byte aligned)
+__host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline int warp_smem_doubles(int T) {
-  const int n = 2 * T;
-  return n * (n + 1) / 2        // K / L packed lower, row major
-         + 5 * n                // invd, u, q, rhs, grad
-         + 4 * (T + 1)          // prefix sums ca, cb, cc, ck
-         + 5 * (T + 1)          // stage weights W11, W12, W22, qv, qpsi
-         + 3 * (T + 1)          // WeX, WeY, epsi
-         + 4 * T                // per-iteration row weights wA, wD, wR, SW
-         + 2;                   // pad
+  const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
+  return tiles_doubles(n)       // K / L on 4x4 tiles
+         + 16 * nblk(n)         // inverses of the factor's diagonal blocks
+         + 4 * n4               // u, q, rhs, grad
+         + 12 * T1e             // prefix sums ca, cb, cc, ck; stage weights W11, W12, W22, qv, qpsi; WeX, WeY, epsi
+         + 4 * Te               // per-iteration row weights wA, wD, wR, SW
+         + even_up(JMPC_NPARAM);// the instance's parameter vector
 }
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -151,111 +152,24 @@ __device__ inline int nearest_index(const double* __restrict__ cx, const double*
 
 // ---- per-warp shared-memory views --------------------------------------------------------------------
 struct WarpMem {
-  double *K, *invd, *u, *q, *rhs, *grad;
+  double *K, *Dinv, *u, *q, *rhs, *grad;
   double *ca, *cb, *cc, *ck;
   double *W11, *W12, *W22, *qv, *qpsi;
   double *WeX, *WeY, *epsi;
   double *wA, *wD, *wR, *SW;
+  double *prm;
   __device__ WarpMem(double* base, int T) {
-    const int n = 2 * T, T1 = T + 1;
+    const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
     double* p = base;
-    K = p; p += n * (n + 1) / 2;
-    invd = p; p += n; u = p; p += n; q = p; p += n; rhs = p; p += n; grad = p; p += n;
-    ca = p; p += T1; cb = p; p += T1; cc = p; p += T1; ck = p; p += T1;
-    W11 = p; p += T1; W12 = p; p += T1; W22 = p; p += T1; qv = p; p += T1; qpsi = p; p += T1;
-    WeX = p; p += T1; WeY = p; p += T1; epsi = p; p += T1;
-    wA = p; p += T; wD = p; p += T; wR = p; p += T; SW = p; p += T;
+    K = p; p += tiles_doubles(n);
+    Dinv = p; p += 16 * nblk(n);
+    u = p; p += n4; q = p; p += n4; rhs = p; p += n4; grad = p; p += n4;
+    ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
+    W11 = p; p += T1e; W12 = p; p += T1e; W22 = p; p += T1e; qv = p; p += T1e; qpsi = p; p += T1e;
+    WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e;
+    wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; SW = p; p += Te;
+    prm = p;
   }
-};
-
-// In-place Cholesky of the packed lower matrix K (n x n): column by column, a lane owns a row and forms
-// the dot product of its row with row j.  Returns false when a pivot is not positive.
-__device__ inline bool cholesky_packed(double* __restrict__ K, double* __restrict__ invd, int n, int lane) {
-  bool ok = true;
-  for (int j = 0; j < n; ++j) {
-    const double* rowj = K + tri(j);
-    double s0 = 0.0, s1 = 0.0;
-    const int i0 = j + lane, i1 = j + lane + 32;
-    if (i0 < n) {
-      const double* rowi = K + tri(i0);
-      double a0 = rowi[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int k = 0;
-      for (; k + 3 < j; k += 4) {
-        a0 = fma(-rowi[k], rowj[k], a0);
-        a1 = fma(-rowi[k + 1], rowj[k + 1], a1);
-        a2 = fma(-rowi[k + 2], rowj[k + 2], a2);
-        a3 = fma(-rowi[k + 3], rowj[k + 3], a3);
-      }
-      for (; k < j; ++k) a0 = fma(-rowi[k], rowj[k], a0);
-      s0 = (a0 + a1) + (a2 + a3);
-    }
-    if (i1 < n) {
-      const double* rowi = K + tri(i1);
-      double a0 = rowi[j], a1 = 0.0;
-      int k = 0;
-      for (; k + 1 < j; k += 2) {
-        a0 = fma(-rowi[k], rowj[k], a0);
-        a1 = fma(-rowi[k + 1], rowj[k + 1], a1);
-      }
-      for (; k < j; ++k) a0 = fma(-rowi[k], rowj[k], a0);
-      s1 = a0 + a1;
-    }
-    const double d = __shfl_sync(kFull, s0, 0);
-    if (!(d > 0.0)) { ok = false; break; }
-    const double inv = 1.0 / sqrt(d);
-    __syncwarp();
-    if (i0 < n) K[tri(i0) + j] = (lane == 0) ? d * inv : s0 * inv;
-    if (i1 < n) K[tri(i1) + j] = s1 * inv;
-    if (lane == 0) invd[j] = inv;
-    __syncwarp();
-  }
-  return ok;
-}
-
-// Solve L L' x = b in place (b in shared memory).
-__device__ inline void chol_solve(const double* __restrict__ K, const double* __restrict__ invd,
-                                  double* __restrict__ b, int n, int lane) {
-  // forward: L y = b
-  for (int j = 0; j < n; ++j) {
-    const double yj = b[j] * invd[j];
-    __syncwarp();
-    for (int i = j + 1 + lane; i < n; i += 32) b[i] = fma(-K[tri(i) + j], yj, b[i]);
-    if (lane == 0) b[j] = yj;
-    __syncwarp();
-  }
-  // backward: L' x = y
-  for (int j = n - 1; j >= 0; --j) {
-    const double xj = b[j] * invd[j];
-    __syncwarp();
-    const double* rowj = K + tri(j);
-    for (int i = lane; i < j; i += 32) b[i] = fma(-rowj[i], xj, b[i]);
-    if (lane == 0) b[j] = xj;
-    __syncwarp();
-  }
-}
-
-// y = K x for the packed symmetric K; a lane owns rows lane and lane + 32.  Result returned in registers.
-__device__ inline void symv_packed(const double* __restrict__ K, const double* __restrict__ x, int n, int lane,
-                                   double& y0, double& y1) {
-  y0 = 0.0; y1 = 0.0;
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    const int i = lane + 32 * pass;
-    if (i < n) {
-      const double* rowi = K + tri(i);
-      double a0 = 0.0, a1 = 0.0;
-      int j = 0;
-      for (; j + 1 <= i; j += 2) { a0 = fma(rowi[j], x[j], a0); a1 = fma(rowi[j + 1], x[j + 1], a1); }
-      for (; j <= i; ++j) a0 = fma(rowi[j], x[j], a0);
-      for (j = i + 1; j < n; ++j) a1 = fma(K[tri(j) + i], x[j], a1);
-      if (pass == 0) y0 = a0 + a1; else y1 = a0 + a1;
-    }
-  }
-}
-
-struct StageRows {   // the four two-sided rows of stage k = lane: accel box, steer box, steer rate k->k+1, speed t=k+1
-  double hi[4], lo[4], sh[4], sl[4], lh[4], ll[4];
-  bool live[4];
 };
 
 // z = A u for the stage rows (u in shared memory)
@@ -273,16 +187,14 @@ __device__ __forceinline__ void rows_apply_T(const double t[4], int lane, double
   rd = t[1] - t[2] + up;
 }
 
-__device__ __forceinline__ double step_to_boundary(double v, double dv) {
-  return (dv < 0.0) ? (-v / dv) : INFINITY;
-}
-
 // The fused step for one instance, executed by one warp.
 __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane) {
-  const int T = A.T, n = 2 * T, T1 = T + 1;
+  const int T = A.T, n = 2 * T, T1 = T + 1, nb = nblk(n), n4 = nb << 2;
   WarpMem M(smem_base, T);
-  const double* prm = A.params ? (A.params + (size_t)b * JMPC_NPARAM) : nullptr;
-  auto P = [&](int k) -> double { return prm ? prm[k] : A.defaults[k]; };
+  // the instance's parameter vector lives in shared memory (uniform reads, no registers held across phases)
+  if (lane < JMPC_NPARAM) M.prm[lane] = A.params ? A.params[(size_t)b * JMPC_NPARAM + lane] : A.defaults[lane];
+  __syncwarp();
+  auto P = [&](int k) -> double { return M.prm[k]; };
 
   const int cid = A.course_id ? A.course_id[b] : 0;
   const double* cx = A.cx + (size_t)cid * A.course_stride;
@@ -413,7 +325,14 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
     const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
     const double Rea = P(JMPC_P_REND_A), Red = P(JMPC_P_REND_D);
     const double dt2 = dt * dt;
-    // Hessian, packed lower, variable order [a_0..a_{T-1}, delta_0..delta_{T-1}]
+    // Hessian on 4x4 tiles (jmpc_linalg.cuh), variable order [a_0..a_{T-1}, delta_0..delta_{T-1}]; the last
+    // block row is cleared first so that the identity padding (n -> multiple of 4) is in place
+    {
+      const int last0 = tile_off(nb - 1, 0), last1 = tiles_doubles(n);
+      for (int e = last0 + lane; e < last1; e += 32) pscr[e] = 0.0;
+      __syncwarp();
+      if (lane < n4 - n) pscr[elem_off(n + lane, n + lane)] = 1.0;
+    }
     {
       int i = 0, j = lane;
       while (j > i) { j -= i + 1; ++i; }
@@ -456,7 +375,8 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
             acc -= 2.0 * rd_w;
           }
         }
-        pscr[e] = acc;
+        pscr[elem_off(i, j)] = acc;
+        if (i != j && (i >> 2) == (j >> 2)) pscr[elem_off(j, i)] = acc;      // diagonal tiles are stored full
         j += 32;
         while (j > i) { j -= i + 1; ++i; }
       }
@@ -476,6 +396,7 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
       M.q[k] = 2.0 * qa; M.q[T + k] = 2.0 * qd;
       M.u[k] = 0.0; M.u[T + k] = 0.0;
     }
+    if (lane < n4 - n) { M.q[n + lane] = 0.0; M.u[n + lane] = 0.0; M.rhs[n + lane] = 0.0; M.grad[n + lane] = 0.0; }
     __syncwarp();
 
     // feasibility predicate: the t = 0 speed rows act on the fixed v0
@@ -499,75 +420,82 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
     }
 
     // ---------------- 5. interior-point solve -------------------------------------------------------
-    StageRows R;
-    {
-      const double lim = P(JMPC_P_MAX_DSTEER) * dt;
-      R.hi[0] = P(JMPC_P_MAX_ACCEL); R.lo[0] = P(JMPC_P_MAX_DECEL);
-      R.hi[1] = max_steer;           R.lo[1] = -max_steer;
-      R.hi[2] = lim;                 R.lo[2] = -lim;
-      R.hi[3] = (speed - v0) / dt;   R.lo[3] = (min_speed - v0) / dt;
-      R.live[0] = R.live[1] = R.live[3] = lane < T;
-      R.live[2] = lane < T - 1;
+    // Stage k = lane owns four two-sided rows: r = 0 accel box, 1 steer box, 2 steer rate k -> k+1, 3 speed
+    // (running sum of a up to k).  Only slacks and multipliers stay in registers across the factorisation;
+    // bounds are rebuilt from the parameter block when needed.
+    double sh[4], sl[4], lh[4], ll[4];
+    const bool live013 = lane < T, live2 = lane < T - 1;
+    auto is_live = [&](int r) -> bool { return r == 2 ? live2 : live013; };
+    auto bound_hi = [&](int r) -> double {
+      return r == 0 ? P(JMPC_P_MAX_ACCEL) : r == 1 ? P(JMPC_P_MAX_STEER) : r == 2 ? P(JMPC_P_MAX_DSTEER) * dt
+                                                                               : (speed - v0) / dt;
+    };
+    auto bound_lo = [&](int r) -> double {
+      return r == 0 ? P(JMPC_P_MAX_DECEL) : r == 1 ? -P(JMPC_P_MAX_STEER) : r == 2 ? -(P(JMPC_P_MAX_DSTEER) * dt)
+                                                                                : (min_speed - v0) / dt;
+    };
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        // u = 0 -> z = 0
-        R.sh[r] = fmax(R.hi[r], 1e-2); R.sl[r] = fmax(-R.lo[r], 1e-2);
-        R.lh[r] = R.live[r] ? 1.0 : 0.0; R.ll[r] = R.lh[r];
-      }
+    for (int r = 0; r < 4; ++r) {
+      sh[r] = fmax(bound_hi(r), 1e-2); sl[r] = fmax(-bound_lo(r), 1e-2);      // u = 0 -> A u = 0
+      lh[r] = is_live(r) ? 1.0 : 0.0; ll[r] = lh[r];
     }
     const double inv_rows = 1.0 / (double)(2 * (4 * T - 1));
     double gscale = 0.0;
     if (lane < T) gscale = fmax(fabs(M.q[lane]), fabs(M.q[T + lane]));
     gscale = 1.0 + warp_max(gscale);
-    const int npk = n * (n + 1) / 2;
+    const int ntd = tiles_doubles(n);
     bool converged = false;
     int it = 0;
     for (it = 0; it < A.max_iters; ++it) {
-      double z[4], rph[4], rpl[4], w[4], t4[4];
+      double z[4], rph[4], rpl[4], ish[4], isl[4], t4[4];
       rows_apply(M.u, T, lane, z);
       double mu = 0.0, rpmax = 0.0;
+      double w2, w3;
+      {
+        double w[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        rph[r] = R.live[r] ? (z[r] + R.sh[r] - R.hi[r]) : 0.0;
-        rpl[r] = R.live[r] ? (-z[r] + R.sl[r] + R.lo[r]) : 0.0;
-        w[r] = R.live[r] ? (R.lh[r] / R.sh[r] + R.ll[r] / R.sl[r]) : 0.0;
-        mu += R.lh[r] * R.sh[r] + R.ll[r] * R.sl[r];
-        rpmax = fmax(rpmax, fmax(fabs(rph[r]), fabs(rpl[r])));
+        for (int r = 0; r < 4; ++r) {
+          const bool lv = is_live(r);
+          ish[r] = 1.0 / sh[r]; isl[r] = 1.0 / sl[r];
+          rph[r] = lv ? (z[r] + sh[r] - bound_hi(r)) : 0.0;
+          rpl[r] = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
+          w[r] = lv ? fma(lh[r], ish[r], ll[r] * isl[r]) : 0.0;
+          mu += lh[r] * sh[r] + ll[r] * sl[r];
+          rpmax = fmax(rpmax, fmax(fabs(rph[r]), fabs(rpl[r])));
+        }
+        w2 = w[2]; w3 = w[3];
+        double wup = __shfl_up_sync(kFull, w2, 1);
+        if (lane == 0) wup = 0.0;
+        const double sw = warp_rscan(w3, lane);
+        if (lane < T) { M.wA[lane] = w[0]; M.wD[lane] = w[1] + w2 + wup; M.wR[lane] = w2; M.SW[lane] = sw; }
       }
       mu = warp_sum(mu) * inv_rows;
       rpmax = warp_max(rpmax);
-      // row weights -> shared, K = P + A' diag(w) A
-      {
-        double wup = __shfl_up_sync(kFull, w[2], 1);
-        if (lane == 0) wup = 0.0;
-        const double sw = warp_rscan(w[3], lane);
-        if (lane < T) { M.wA[lane] = w[0]; M.wD[lane] = w[1] + w[2] + wup; M.wR[lane] = w[2]; M.SW[lane] = sw; }
-      }
       // P -> shared (the scratch copy is L2 resident); P u is formed from the clean Hessian: folding the
       // barrier weights in first and subtracting them again would cancel catastrophically once w ~ 1e12
-      for (int e = lane; e < npk; e += 32) M.K[e] = pscr[e];
+      for (int e = lane; e < ntd; e += 32) M.K[e] = pscr[e];
       __syncwarp();
       double pu0, pu1;
-      symv_packed(M.K, M.u, n, lane, pu0, pu1);
+      symv_tiles(M.K, M.u, nb, lane, pu0, pu1);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) t4[r] = R.live[r] ? (R.lh[r] - R.ll[r]) : 0.0;
+      for (int r = 0; r < 4; ++r) t4[r] = is_live(r) ? (lh[r] - ll[r]) : 0.0;
       double ra, rd;
       rows_apply_T(t4, lane, ra, rd);
       if (lane < n) M.grad[lane] = pu0 + M.q[lane];
       if (lane + 32 < n) M.grad[lane + 32] = pu1 + M.q[lane + 32];
       __syncwarp();
       // K = P + A' diag(w) A: only the accel block and the steer tridiagonal change
-      for (int e = lane; e < tri(T); e += 32) {          // accel x accel, packed rows 0..T-1
+      for (int e = lane; e < tri(T); e += 32) {          // accel x accel, lower triangle rows 0..T-1
         int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
         while (tri(i + 1) <= e) ++i;
         while (tri(i) > e) --i;
         const int j = e - tri(i);
-        M.K[e] += M.SW[i] + ((i == j) ? M.wA[i] : 0.0);
+        M.K[elem_off(i, j)] += M.SW[i] + ((i == j) ? M.wA[i] : 0.0);
       }
       if (lane < T) {
         const int i = T + lane;
-        M.K[tri(i) + i] += M.wD[lane];
-        if (lane >= 1) M.K[tri(i) + i - 1] -= M.wR[lane - 1];
+        M.K[elem_off(i, i)] += M.wD[lane];
+        if (lane >= 1) M.K[elem_off(i, i - 1)] -= M.wR[lane - 1];
       }
       double rdmax = 0.0;
       if (lane < T) {
@@ -579,7 +507,7 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
       __syncwarp();
       if (mu <= A.mu_tol && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) { converged = true; break; }
 
-      if (!cholesky_packed(M.K, M.invd, n, lane)) break;
+      if (!chol_tiles(M.K, M.Dinv, nb, lane)) break;
 
       double dsh[4], dsl[4], dlh[4], dll[4];
       double sigma_mu = 0.0;
@@ -589,40 +517,42 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
         double th[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          double rch = R.lh[r] * R.sh[r], rcl = R.ll[r] * R.sl[r];
+          double rch = lh[r] * sh[r], rcl = ll[r] * sl[r];
           if (phase == 1) { rch += dsh[r] * dlh[r] - sigma_mu; rcl += dsl[r] * dll[r] - sigma_mu; }
-          const double a_h = (-rch + R.lh[r] * rph[r]) / R.sh[r];
-          const double a_l = (-rcl + R.ll[r] * rpl[r]) / R.sl[r];
-          th[r] = R.live[r] ? (a_h - a_l) : 0.0;
-          // stash rc in dlh/dll for the direction recovery below
-          dlh[r] = rch; dll[r] = rcl;
+          const double a_h = fma(lh[r], rph[r], -rch) * ish[r];
+          const double a_l = fma(ll[r], rpl[r], -rcl) * isl[r];
+          th[r] = is_live(r) ? (a_h - a_l) : 0.0;
+          dlh[r] = rch; dll[r] = rcl;                 // stash rc for the direction recovery below
         }
         rows_apply_T(th, lane, ra, rd);
         if (lane < T) { M.rhs[lane] = -M.grad[lane] - ra; M.rhs[T + lane] = -M.grad[T + lane] - rd; }
         __syncwarp();
-        chol_solve(M.K, M.invd, M.rhs, n, lane);
+        solve_tiles(M.K, M.Dinv, M.rhs, nb, lane);
         double dz[4];
         rows_apply(M.rhs, T, lane, dz);
-        double amax = INFINITY;
+        // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l)
+        double worst = 0.0;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
+          const bool lv = is_live(r);
           const double rch = dlh[r], rcl = dll[r];
-          dsh[r] = R.live[r] ? (-rph[r] - dz[r]) : 0.0;
-          dsl[r] = R.live[r] ? (-rpl[r] + dz[r]) : 0.0;
-          dlh[r] = R.live[r] ? ((-rch - R.lh[r] * dsh[r]) / R.sh[r]) : 0.0;
-          dll[r] = R.live[r] ? ((-rcl - R.ll[r] * dsl[r]) / R.sl[r]) : 0.0;
-          if (R.live[r]) {
-            amax = fmin(amax, fmin(step_to_boundary(R.sh[r], dsh[r]), step_to_boundary(R.sl[r], dsl[r])));
-            amax = fmin(amax, fmin(step_to_boundary(R.lh[r], dlh[r]), step_to_boundary(R.ll[r], dll[r])));
+          dsh[r] = lv ? (-rph[r] - dz[r]) : 0.0;
+          dsl[r] = lv ? (-rpl[r] + dz[r]) : 0.0;
+          dlh[r] = lv ? (-(fma(lh[r], dsh[r], rch)) * ish[r]) : 0.0;
+          dll[r] = lv ? (-(fma(ll[r], dsl[r], rcl)) * isl[r]) : 0.0;
+          if (lv) {
+            worst = fmax(worst, fmax(-dsh[r] * ish[r], -dsl[r] * isl[r]));
+            worst = fmax(worst, fmax(-dlh[r] / lh[r], -dll[r] / ll[r]));
           }
         }
-        amax = warp_min(amax);
+        worst = warp_max(worst);
+        const double amax = (worst > 0.0) ? 1.0 / worst : INFINITY;
         if (phase == 0) {
           const double aa = fmin(1.0, amax);
           double mu_aff = 0.0;
 #pragma unroll
           for (int r = 0; r < 4; ++r)
-            mu_aff += (R.lh[r] + aa * dlh[r]) * (R.sh[r] + aa * dsh[r]) + (R.ll[r] + aa * dll[r]) * (R.sl[r] + aa * dsl[r]);
+            mu_aff += fma(aa, dlh[r], lh[r]) * fma(aa, dsh[r], sh[r]) + fma(aa, dll[r], ll[r]) * fma(aa, dsl[r], sl[r]);
           mu_aff = warp_sum(mu_aff) * inv_rows;
           const double ratio = mu_aff / mu;
           sigma_mu = ratio * ratio * ratio * mu;
@@ -631,8 +561,8 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
           if (lane < T) { M.u[lane] = fma(alpha, M.rhs[lane], M.u[lane]); M.u[T + lane] = fma(alpha, M.rhs[T + lane], M.u[T + lane]); }
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            R.sh[r] = fma(alpha, dsh[r], R.sh[r]); R.sl[r] = fma(alpha, dsl[r], R.sl[r]);
-            R.lh[r] = fma(alpha, dlh[r], R.lh[r]); R.ll[r] = fma(alpha, dll[r], R.ll[r]);
+            sh[r] = fma(alpha, dsh[r], sh[r]); sl[r] = fma(alpha, dsl[r], sl[r]);
+            lh[r] = fma(alpha, dlh[r], lh[r]); ll[r] = fma(alpha, dll[r], ll[r]);
           }
         }
         __syncwarp();
@@ -694,13 +624,13 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
 
 // Persistent kernel: every resident warp pulls instances from a global counter.
 __global__ void __launch_bounds__(128, 4) mpc_step_kernel(const StepArgs A) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   double* base = smem + (size_t)wib * warp_smem_doubles(A.T);
   const int gw = blockIdx.x * warps_per_block + wib;
   const int n = 2 * A.T;
-  double* pscr = A.pscratch + (size_t)gw * (n * (n + 1) / 2);
+  double* pscr = A.pscratch + (size_t)gw * tiles_doubles(n);
   for (;;) {
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(A.counter, 1u);

@@ -122,6 +122,17 @@ class BatchedMPC:
         _cabi.check(self._lib.jmpc_measure_fma_peak(self._h, C.byref(a), C.byref(b)), "jmpc_measure_fma_peak")
         return a.value, b.value
 
+    def debug_linalg(self, A, b, x):
+        """Building-block self-test: returns (A^{-1} b, A x, ok) computed by the tiled warp routines."""
+        A = _f64(A)
+        n = A.shape[0]
+        b, x = _f64(b, (n,)), _f64(x, (n,))
+        sol, prod = np.zeros(n), np.zeros(n)
+        rc = self._lib.jmpc_debug_linalg(self._h, n, _ptr(A), _ptr(b), _ptr(x), _ptr(sol), _ptr(prod))
+        if rc < 0:
+            _cabi.check(rc, "jmpc_debug_linalg")
+        return sol, prod, rc == 0
+
     # ---- host path --------------------------------------------------------------------------------------
     def step_host(self, state, target_ind, oa=None, od=None, course_id=None, course_len=None, warm=None,
                   params=None, T: Optional[int] = None) -> StepOutput:

@@ -155,6 +155,12 @@ int64_t jmpc_launch_count(jmpc_handle h);
  * the denominator of the solver kernel's roofline, which is CUDA-core bound. */
 int32_t jmpc_measure_fma_peak(jmpc_handle h, double* fp64_tflops, double* fp32_tflops);
 
+/* Self-test of the solver's building blocks (4x4-tiled symmetric matvec, Cholesky, triangular solves) on one
+ * warp: A is a dense symmetric positive definite n x n matrix (row major, n <= 2*JMPC_MAX_T), HOST pointers.
+ * prod = A x, sol = A^{-1} b.  Returns 0 on success, 1 when the factorisation met a non-positive pivot. */
+int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const double* b, const double* x, double* sol,
+                          double* prod);
+
 #ifdef __cplusplus
 }
 #endif
