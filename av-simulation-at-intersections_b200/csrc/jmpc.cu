@@ -61,18 +61,28 @@ namespace {
 // launch geometry of the step kernel for horizon T
 struct StepGeom { int blocks, threads; size_t smem; int warps; };
 
+using StepKernel = void (*)(const jmpc::StepArgs);
+
+// horizons with a compile-time specialisation; anything else runs the generic kernel
+StepKernel step_kernel_for(int T) {
+  if (getenv("JMPC_GENERIC")) return jmpc::mpc_step_kernel<0>;
+  switch (T) {
+    case 8: return jmpc::mpc_step_kernel<8>;
+    case 13: return jmpc::mpc_step_kernel<13>;
+    case 20: return jmpc::mpc_step_kernel<20>;
+    case 25: return jmpc::mpc_step_kernel<25>;
+    default: return jmpc::mpc_step_kernel<0>;
+  }
+}
+
 int step_geometry(jmpc_handle h, int B, int T, StepGeom* g) {
   const int wpb = 4;
   const size_t smem = (size_t)wpb * jmpc::warp_smem_doubles(T) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(jmpc::mpc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(jmpc::mpc_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                            cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
-  }
+  StepKernel k = step_kernel_for(T);
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jmpc::mpc_step_kernel, wpb * 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, wpb * 32, smem));
   if (per_sm < 1) return fail("step kernel does not fit on an SM for this horizon");
   int cap = h->opt.warps_per_sm;
   if (const char* e = getenv("JMPC_WARPS_PER_SM")) cap = atoi(e);
@@ -304,7 +314,7 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
   a.cost = cost; a.status = status; a.iters = iters; a.record = record;
   a.pscratch = h->d_pscratch; a.counter = h->d_counter;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
-  jmpc::mpc_step_kernel<<<g.blocks, g.threads, g.smem, s>>>(a);
+  step_kernel_for(T)<<<g.blocks, g.threads, g.smem, s>>>(a);
   CK(cudaGetLastError());
   h->launches++;
   return 0;

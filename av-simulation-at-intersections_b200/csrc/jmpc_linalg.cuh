@@ -7,6 +7,10 @@
 // Diagonal tiles of a *matrix* (not of a factor) are stored full (both triangles).  n is padded to a multiple of
 // 4 with identity rows.
 //
+// None of the shared-memory pointers below is __restrict__: lanes exchange data through them around
+// __syncwarp(), and a noalias parameter lets the compiler move its loads/stores across that call (it did, as soon
+// as the block count became a compile-time constant and the loops were unrolled).
+//
 // Compared with a column-at-a-time factorisation on a packed triangle this does 64 FMAs per 32 shared-memory
 // instructions in the trailing update instead of 1 per 2, and synchronises the warp 3 times per 4 columns.
 #pragma once
@@ -36,7 +40,7 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
 // In-place Cholesky K = L L' on tiles.  Dinv receives the inverses of the diagonal blocks of L (nb x 16 doubles,
 // lower triangular), which turn the panel and the triangular solves into multiplications.
 // Returns false when a pivot is not positive (all lanes agree).
-__device__ inline bool chol_tiles(double* __restrict__ K, double* __restrict__ Dinv, int nb, int lane) {
+__device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane) {
   for (int J = 0; J < nb; ++J) {
     // ---- diagonal block: every lane factors it redundantly in registers (no broadcast needed)
     const double* D = K + tile_off(J, J);
@@ -122,8 +126,7 @@ __device__ inline bool chol_tiles(double* __restrict__ K, double* __restrict__ D
 }
 
 // Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).
-__device__ inline void solve_tiles(const double* __restrict__ K, const double* __restrict__ Dinv,
-                                   double* __restrict__ b, int nb, int lane) {
+__device__ inline void solve_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
   const int n4 = nb << 2;
   for (int J = 0; J < nb; ++J) {                      // forward: L y = b
     const double* Mw = Dinv + (J << 4);
@@ -163,7 +166,7 @@ __device__ inline void solve_tiles(const double* __restrict__ K, const double* _
 }
 
 // y = P x for a symmetric P on tiles (diagonal tiles stored full); lane owns rows lane and lane + 32.
-__device__ inline void symv_tiles(const double* __restrict__ P, const double* __restrict__ x, int nb, int lane,
+__device__ inline void symv_tiles(const double* P, const double* x, int nb, int lane,
                                   double& y0, double& y1) {
   const int n4 = nb << 2;
   y0 = 0.0; y1 = 0.0;

@@ -48,6 +48,10 @@ struct StepArgs {
   unsigned int* counter;    // dynamic work queue
 };
 
+constexpr int kSlotHi3 = JMPC_NPARAM, kSlotLo3 = JMPC_NPARAM + 1, kSlotLim = JMPC_NPARAM + 2;   // derived bounds
+constexpr int kParamSlots = 32;
+static_assert(JMPC_NPARAM + 3 <= kParamSlots, "parameter block too small");
+
 // shared-memory doubles one warp needs for horizon T (every sub-array starts 16-byte aligned)
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline int warp_smem_doubles(int T) {
@@ -55,9 +59,9 @@ __host__ __device__ inline int warp_smem_doubles(int T) {
   return tiles_doubles(n)       // K / L on 4x4 tiles
          + 16 * nblk(n)         // inverses of the factor's diagonal blocks
          + 4 * n4               // u, q, rhs, grad
-         + 12 * T1e             // prefix sums ca, cb, cc, ck; stage weights W11, W12, W22, qv, qpsi; WeX, WeY, epsi
+         + 14 * T1e             // prefix sums ca, cb, cc, ck; stage weights W11, W12, W22, qv, qpsi; WeX, WeY, epsi; vb, th
          + 4 * Te               // per-iteration row weights wA, wD, wR, SW
-         + even_up(JMPC_NPARAM);// the instance's parameter vector
+         + kParamSlots;         // the instance's parameter vector + derived row bounds
 }
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -155,7 +159,7 @@ struct WarpMem {
   double *K, *Dinv, *u, *q, *rhs, *grad;
   double *ca, *cb, *cc, *ck;
   double *W11, *W12, *W22, *qv, *qpsi;
-  double *WeX, *WeY, *epsi;
+  double *WeX, *WeY, *epsi, *vb, *th;
   double *wA, *wD, *wR, *SW;
   double *prm;
   __device__ WarpMem(double* base, int T) {
@@ -166,14 +170,14 @@ struct WarpMem {
     u = p; p += n4; q = p; p += n4; rhs = p; p += n4; grad = p; p += n4;
     ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
     W11 = p; p += T1e; W12 = p; p += T1e; W22 = p; p += T1e; qv = p; p += T1e; qpsi = p; p += T1e;
-    WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e;
+    WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e; vb = p; p += T1e; th = p; p += T1e;
     wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; SW = p; p += Te;
     prm = p;
   }
 };
 
 // z = A u for the stage rows (u in shared memory)
-__device__ __forceinline__ void rows_apply(const double* __restrict__ u, int T, int lane, double z[4]) {
+__device__ __forceinline__ void rows_apply(const double* u, int T, int lane, double z[4]) {
   const double a = (lane < T) ? u[lane] : 0.0;
   const double d = (lane < T) ? u[T + lane] : 0.0;
   const double dn = __shfl_down_sync(kFull, d, 1);
@@ -187,39 +191,29 @@ __device__ __forceinline__ void rows_apply_T(const double t[4], int lane, double
   rd = t[1] - t[2] + up;
 }
 
-// The fused step for one instance, executed by one warp.
-__device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane) {
-  const int T = A.T, n = 2 * T, T1 = T + 1, nb = nblk(n), n4 = nb << 2;
+// ---- phase A: index, reference sampling, rollout, linearisation, condensing --------------------------------
+// Leaves everything the later phases need in shared memory / the L2 scratch; returns a jmpc_status
+// (JMPC_OPTIMAL = go on and solve).
+template <int TT>
+__device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_base, double* pscr, int lane, int lin,
+                                      int total_iters, double oa_k, double od_k, double ov_k, int& target,
+                                      int& idx_out, unsigned& end_mask_out) {
+  const int T = (TT > 0) ? TT : A.T;
+  const int n = 2 * T, T1 = T + 1, nb = nblk(n), n4 = nb << 2;
   WarpMem M(smem_base, T);
-  // the instance's parameter vector lives in shared memory (uniform reads, no registers held across phases)
-  if (lane < JMPC_NPARAM) M.prm[lane] = A.params ? A.params[(size_t)b * JMPC_NPARAM + lane] : A.defaults[lane];
-  __syncwarp();
   auto P = [&](int k) -> double { return M.prm[k]; };
-
   const int cid = A.course_id ? A.course_id[b] : 0;
   const double* cx = A.cx + (size_t)cid * A.course_stride;
   const double* cy = A.cy + (size_t)cid * A.course_stride;
   const double* cyaw = A.cyaw + (size_t)cid * A.course_stride;
   int n_course = A.course_n[cid];
   if (A.course_len) n_course = min(n_course, max(A.course_len[b], 1));
-
   const double x0 = A.state[(size_t)b * 4 + 0], y0 = A.state[(size_t)b * 4 + 1];
   const double v0 = A.state[(size_t)b * 4 + 2], yaw0 = A.state[(size_t)b * 4 + 3];
   const double dt = P(JMPC_P_DT), dl = P(JMPC_P_DL), Lw = P(JMPC_P_L), speed = P(JMPC_P_SPEED);
   const double min_speed = P(JMPC_P_MIN_SPEED);
-
-  // warm start = linearisation point (mpc.py:225-227: None -> zeros)
-  const bool use_warm = A.warm ? (A.warm[b] != 0) : true;
-  double oa_k = 0.0, od_k = 0.0;
-  if (use_warm && lane < T) { oa_k = A.oa[(size_t)b * T + lane]; od_k = A.od[(size_t)b * T + lane]; }
-
-  int target = A.target_ind[b];
-  target = min(max(target, 0), n_course);          // numpy slicing clamps an out-of-range start
-  double ov_k = 0.0;                               // |ov| feedback for lin_iters > 1 (lane k <-> horizon point k)
-  int status = JMPC_OPTIMAL;
-  int total_iters = 0;
-
-  for (int lin = 0; lin < A.lin_iters; ++lin) {
+  if (lin == 0) target = min(max(target, 0), n_course);      // numpy slicing clamps an out-of-range start
+  {
     // ---------------- 1. nearest index --------------------------------------------------------------
     const int near = nearest_index(cx, cy, n_course, target, x0, y0, lane);
     if (near < 0) {
@@ -231,7 +225,7 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
           rec[5] = total_iters; rec[6] = nan(""); rec[7] = nan("");
         }
       }
-      return;
+      return JMPC_INDEX_RULE;
     }
     target = near;
 
@@ -320,6 +314,11 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
       M.WeX[lane] = w11 * ex + w12 * ey; M.WeY[lane] = w12 * ex + w22 * ey; M.epsi[lane] = eps;
     }
     if (lane < T) M.wA[lane] = gk;      // borrow wA for g_k during condensing
+    if (lane <= T) { M.vb[lane] = vb; M.th[lane] = th; }       // operating point, reused by the epilogue
+    if (lane == 0) {                     // derived row bounds, read back by the solver
+      M.prm[kSlotHi3] = (speed - v0) / dt; M.prm[kSlotLo3] = (min_speed - v0) / dt;
+      M.prm[kSlotLim] = P(JMPC_P_MAX_DSTEER) * dt;
+    }
     __syncwarp();
 
     const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
@@ -381,10 +380,7 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
         while (j > i) { j -= i + 1; ++i; }
       }
     }
-    // linear term and the constant
-    double c0 = 0.0;
-    if (lane >= 1 && lane <= T) c0 = ex * M.WeX[lane] + ey * M.WeY[lane] + wv * ev * ev + wpsi * eps * eps;
-    c0 = warp_sum(c0);
+    // linear term
     if (lane < T) {
       const int k = lane;
       const double ai = M.ca[k + 1], ci = M.cc[k + 1], bi = M.cb[k + 1], kki = M.ck[k + 1];
@@ -401,7 +397,7 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
 
     // feasibility predicate: the t = 0 speed rows act on the fixed v0
     if (!(min_speed <= v0 && v0 <= speed)) {
-      status = JMPC_INFEASIBLE;
+      const int status = JMPC_INFEASIBLE;
       // xref / target are still reported, as the reference assigns them before the solve result
       if (lane <= T) {
         double* xo = A.xref + (size_t)b * 4 * T1;
@@ -416,9 +412,24 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
           rec[5] = total_iters; rec[6] = nan(""); rec[7] = nan("");
         }
       }
-      return;
+      return JMPC_INFEASIBLE;
     }
+    idx_out = idx; end_mask_out = end_mask;
+    return JMPC_OPTIMAL;
 
+
+  }
+}
+
+// ---- phase B: Mehrotra predictor-corrector on the condensed QP -----------------------------------------------
+// Returns the iteration count; `converged` says whether the KKT tolerances were met.
+template <int TT>
+__device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, const double* pscr, int lane,
+                                       bool& converged_out) {
+  const int T = (TT > 0) ? TT : A.T;
+  const int n = 2 * T, nb = nblk(n);
+  WarpMem M(smem_base, T);
+  auto P = [&](int k) -> double { return M.prm[k]; };
     // ---------------- 5. interior-point solve -------------------------------------------------------
     // Stage k = lane owns four two-sided rows: r = 0 accel box, 1 steer box, 2 steer rate k -> k+1, 3 speed
     // (running sum of a up to k).  Only slacks and multipliers stay in registers across the factorisation;
@@ -427,12 +438,10 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
     const bool live013 = lane < T, live2 = lane < T - 1;
     auto is_live = [&](int r) -> bool { return r == 2 ? live2 : live013; };
     auto bound_hi = [&](int r) -> double {
-      return r == 0 ? P(JMPC_P_MAX_ACCEL) : r == 1 ? P(JMPC_P_MAX_STEER) : r == 2 ? P(JMPC_P_MAX_DSTEER) * dt
-                                                                               : (speed - v0) / dt;
+      return r == 0 ? P(JMPC_P_MAX_ACCEL) : r == 1 ? P(JMPC_P_MAX_STEER) : r == 2 ? P(kSlotLim) : P(kSlotHi3);
     };
     auto bound_lo = [&](int r) -> double {
-      return r == 0 ? P(JMPC_P_MAX_DECEL) : r == 1 ? -P(JMPC_P_MAX_STEER) : r == 2 ? -(P(JMPC_P_MAX_DSTEER) * dt)
-                                                                                : (min_speed - v0) / dt;
+      return r == 0 ? P(JMPC_P_MAX_DECEL) : r == 1 ? -P(JMPC_P_MAX_STEER) : r == 2 ? -P(kSlotLim) : P(kSlotLo3);
     };
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -568,9 +577,38 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
         __syncwarp();
       }
     }
-    total_iters += it;
-    status = converged ? JMPC_OPTIMAL : JMPC_MAX_ITER;
+    converged_out = converged;
+    return it;
+}
 
+// ---- phase C: states of the linearised model for the solution, objective, outputs ---------------------------
+template <int TT>
+__device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_base, int lane, bool last, int status,
+                                         int target, int idx, unsigned end_mask, int total_iters, double& oa_k,
+                                         double& od_k, double& ov_k) {
+  const int T = (TT > 0) ? TT : A.T;
+  const int T1 = T + 1;
+  WarpMem M(smem_base, T);
+  auto P = [&](int k) -> double { return M.prm[k]; };
+  const double x0 = A.state[(size_t)b * 4 + 0], y0 = A.state[(size_t)b * 4 + 1];
+  const double v0 = A.state[(size_t)b * 4 + 2], yaw0 = A.state[(size_t)b * 4 + 3];
+  const double dt = P(JMPC_P_DT), Lw = P(JMPC_P_L);
+  // per-lane data of phase A, re-read instead of being held in registers across the solve
+  const int cid = A.course_id ? A.course_id[b] : 0;
+  double xr = 0.0, yr = 0.0, psir = 0.0, vb = 0.0, th = 0.0, w11 = 0.0, w12 = 0.0, w22 = 0.0, wv = 0.0, wpsi = 0.0;
+  if (lane <= T) {
+    const size_t off = (size_t)cid * A.course_stride + idx;
+    xr = A.cx[off]; yr = A.cy[off]; psir = A.cyaw[off];
+    vb = M.vb[lane]; th = M.th[lane];
+    w11 = M.W11[lane]; w12 = M.W12[lane]; w22 = M.W22[lane]; wv = M.qv[lane]; wpsi = M.qpsi[lane];
+  }
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  double al = 0.0, be = 0.0, ga = 0.0, ka = 0.0, gk = 0.0;
+  if (lane < T) { al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw; }
+  const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
+  const double Rea = P(JMPC_P_REND_A), Red = P(JMPC_P_REND_D);
+  {
     // ---------------- 6. states of the linearised model for the solution ---------------------------
     const double a_sol = (lane < T) ? M.u[lane] : 0.0, d_sol = (lane < T) ? M.u[T + lane] : 0.0;
     const double v_t = v0 + dt * (warp_scan(a_sol, lane) - a_sol);                  // lane t: v_t
@@ -581,7 +619,6 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
     const double X_t = x0 + (warp_scan(tx, lane) - tx);
     const double Y_t = y0 + (warp_scan(ty, lane) - ty);
 
-    const bool last = (lin == A.lin_iters - 1);
     if (last) {
       // objective value, evaluated term by term as mpc.py:159-187 writes it
       double cterm = 0.0;
@@ -596,7 +633,6 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
       const double a_next = __shfl_down_sync(kFull, a_sol, 1), d_next = __shfl_down_sync(kFull, d_sol, 1);
       if (lane < T - 1) cterm += Rda * (a_next - a_sol) * (a_next - a_sol) + Rdd * (d_next - d_sol) * (d_next - d_sol);
       const double cost = warp_sum(cterm);
-      (void)c0;
       if (lane < T) { A.oa[(size_t)b * T + lane] = a_sol; A.od[(size_t)b * T + lane] = d_sol; }
       if (lane <= T) {
         A.ox[(size_t)b * T1 + lane] = X_t; A.oy[(size_t)b * T1 + lane] = Y_t;
@@ -618,25 +654,55 @@ __device__ inline void mpc_step_instance(const StepArgs& A, int b, double* smem_
       // feed the solution back as the next linearisation point (mpc.py:231-236)
       oa_k = a_sol; od_k = d_sol; ov_k = v_t;
     }
+  }
+}
+
+// The fused step for one instance, executed by one warp.  TT > 0 fixes the horizon at compile time (every
+// shared-memory offset and tile count becomes an immediate); TT == 0 is the generic runtime-T version.  The three
+// phases are separate functions so that the solver's register allocation is not burdened by the values the
+// preparation and the epilogue need; they communicate through the warp's shared memory.
+template <int TT>
+__device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane) {
+  const int T = (TT > 0) ? TT : A.T;
+  WarpMem M(smem_base, T);
+  // the instance's parameter vector lives in shared memory (uniform reads, no registers held across phases)
+  if (lane < JMPC_NPARAM) M.prm[lane] = A.params ? A.params[(size_t)b * JMPC_NPARAM + lane] : A.defaults[lane];
+  __syncwarp();
+  // warm start = linearisation point (mpc.py:225-227: None -> zeros)
+  const bool use_warm = A.warm ? (A.warm[b] != 0) : true;
+  double oa_k = 0.0, od_k = 0.0, ov_k = 0.0;       // ov: |ov| feedback for lin_iters > 1 (lane k <-> horizon point k)
+  if (use_warm && lane < T) { oa_k = A.oa[(size_t)b * T + lane]; od_k = A.od[(size_t)b * T + lane]; }
+  int target = A.target_ind[b];
+  int total_iters = 0;
+  for (int lin = 0; lin < A.lin_iters; ++lin) {
+    int idx = 0; unsigned end_mask = 0;
+    const int st = step_prep<TT>(A, b, smem_base, pscr, lane, lin, total_iters, oa_k, od_k, ov_k, target, idx, end_mask);
+    if (st != JMPC_OPTIMAL) return;
+    bool converged = false;
+    total_iters += step_solve<TT>(A, smem_base, pscr, lane, converged);
+    step_output<TT>(A, b, smem_base, lane, lin == A.lin_iters - 1, converged ? JMPC_OPTIMAL : JMPC_MAX_ITER, target, idx,
+                    end_mask, total_iters, oa_k, od_k, ov_k);
     __syncwarp();
   }
 }
 
 // Persistent kernel: every resident warp pulls instances from a global counter.
+template <int TT>
 __global__ void __launch_bounds__(128, 4) mpc_step_kernel(const StepArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  double* base = smem + (size_t)wib * warp_smem_doubles(A.T);
+  const int T = (TT > 0) ? TT : A.T;
+  double* base = smem + (size_t)wib * warp_smem_doubles(T);
   const int gw = blockIdx.x * warps_per_block + wib;
-  const int n = 2 * A.T;
+  const int n = 2 * T;
   double* pscr = A.pscratch + (size_t)gw * tiles_doubles(n);
   for (;;) {
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(A.counter, 1u);
     b = __shfl_sync(kFull, b, 0);
     if (b >= (unsigned)A.B) break;
-    mpc_step_instance(A, (int)b, base, pscr, lane);
+    mpc_step_instance<TT>(A, (int)b, base, pscr, lane);
     __syncwarp();
   }
 }

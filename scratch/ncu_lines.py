@@ -11,7 +11,7 @@ for r in rows:
         kcount+=1
         if kcount>1: break
         continue
-    if r[0]=="File Name": sec=r[1].split('/')[-1]; continue
+    if r[0] in ("File Name","File Path"): sec=r[1].split('/')[-1]; continue
     if r[0]=="Line No": hdr=r; continue
     if r[0] in ("Kernel Name","File Path") or not r[0].isdigit() and r[0]!="": continue
     if hdr is None: continue
