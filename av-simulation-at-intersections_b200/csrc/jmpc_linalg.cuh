@@ -94,22 +94,24 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane) {
       st4(Mw + 8, m20, m21, m22, 0.0); st4(Mw + 12, m30, m31, m32, m33);
     }
     __syncwarp();
-    // ---- trailing update: C(I, Kc) -= L(I, J) L(Kc, J)', one tile per lane
-    const int m = nb - J - 1, ntiles = (m * (m + 1)) >> 1;
-    for (int t = lane; t < ntiles; t += 32) {
+    // ---- trailing update: C(I, Kc) -= L(I, J) L(Kc, J)'; a task is half a tile (two rows), so the 45 / 36 / 28 ...
+    // tiles of the first block columns fill the 32 lanes better than whole tiles would
+    const int m = nb - J - 1, ntasks = m * (m + 1);
+    for (int q = lane; q < ntasks; q += 32) {
+      const int t = q >> 1, h = (q & 1) << 1;
       int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
       while (((a + 1) * (a + 2) >> 1) <= t) ++a;
       while (((a * (a + 1)) >> 1) > t) --a;
       const int b = t - ((a * (a + 1)) >> 1);
       const int I = J + 1 + a, Kc = J + 1 + b;
-      const double* LI = K + tile_off(I, J);
+      const double* LI = K + tile_off(I, J) + 4 * h;
       const double* LK = K + tile_off(Kc, J);
-      double* C = K + tile_off(I, Kc);
+      double* C = K + tile_off(I, Kc) + 4 * h;
       double k00, k01, k02, k03, k10, k11, k12, k13, k20, k21, k22, k23, k30, k31, k32, k33;
       ld4(LK, k00, k01, k02, k03); ld4(LK + 4, k10, k11, k12, k13);
       ld4(LK + 8, k20, k21, k22, k23); ld4(LK + 12, k30, k31, k32, k33);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < 2; ++r) {
         double x0, x1, x2, x3, c0, c1, c2, c3;
         ld4(LI + 4 * r, x0, x1, x2, x3);
         ld4(C + 4 * r, c0, c1, c2, c3);

@@ -176,6 +176,14 @@ struct WarpMem {
   }
 };
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); both addresses 16-byte aligned
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // z = A u for the stage rows (u in shared memory)
 __device__ __forceinline__ void rows_apply(const double* u, int T, int lane, double z[4]) {
   const double a = (lane < T) ? u[lane] : 0.0;
@@ -456,6 +464,9 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
     bool converged = false;
     int it = 0;
     for (it = 0; it < A.max_iters; ++it) {
+      // P -> shared, asynchronously (the scratch copy is L2 resident): the copy runs under the row work below
+      for (int e = lane * 2; e < ntd; e += 64) cp_async16(M.K + e, pscr + e);
+      cp_async_commit();
       double z[4], rph[4], rpl[4], ish[4], isl[4], t4[4];
       rows_apply(M.u, T, lane, z);
       double mu = 0.0, rpmax = 0.0;
@@ -480,9 +491,9 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       }
       mu = warp_sum(mu) * inv_rows;
       rpmax = warp_max(rpmax);
-      // P -> shared (the scratch copy is L2 resident); P u is formed from the clean Hessian: folding the
-      // barrier weights in first and subtracting them again would cancel catastrophically once w ~ 1e12
-      for (int e = lane; e < ntd; e += 32) M.K[e] = pscr[e];
+      // P u is formed from the clean Hessian: folding the barrier weights in first and subtracting them again
+      // would cancel catastrophically once w ~ 1e12
+      cp_async_wait_all();
       __syncwarp();
       double pu0, pu1;
       symv_tiles(M.K, M.u, nb, lane, pu0, pu1);
