@@ -39,8 +39,10 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
 
 // In-place Cholesky K = L L' on tiles.  Dinv receives the inverses of the diagonal blocks of L (nb x 16 doubles,
 // lower triangular), which turn the panel and the triangular solves into multiplications.
-// Returns false when a pivot is not positive (all lanes agree).
+// Returns false when some pivot was not positive and had to be replaced (all lanes agree); the factor is usable
+// either way.
 __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane) {
+  bool all_clean = true;
   for (int J = 0; J < nb; ++J) {
     // ---- diagonal block: every lane factors it redundantly in registers (no broadcast needed)
     const double* D = K + tile_off(J, J);
@@ -51,20 +53,21 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane) {
       ld4(D + 8, a20, a21, a22, u23); ld4(D + 12, a30, a31, a32, a33);
       (void)u01; (void)u02; (void)u03; (void)u12; (void)u13; (void)u23;
     }
-    if (!(a00 > 0.0)) return false;
-    const double r0 = rsqrt(a00);
+    // A pivot that is not positive (roundoff once the barrier weights reach ~1e13) is treated as infinite, the
+    // usual interior-point remedy: its reciprocal root is set to 0, which zeroes the column of L and that
+    // component of every solve; the outer iteration corrects the step.  `clean` reports whether it happened.
+    bool clean = true;
+    const double r0 = (a00 > 0.0) ? rsqrt(a00) : (clean = false, 0.0);
     const double l00 = a00 * r0, l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
     a11 = fma(-l10, l10, a11);
-    if (!(a11 > 0.0)) return false;
-    const double r1 = rsqrt(a11);
+    const double r1 = (a11 > 0.0) ? rsqrt(a11) : (clean = false, 0.0);
     const double l11 = a11 * r1, l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
     a22 = fma(-l21, l21, fma(-l20, l20, a22));
-    if (!(a22 > 0.0)) return false;
-    const double r2 = rsqrt(a22);
+    const double r2 = (a22 > 0.0) ? rsqrt(a22) : (clean = false, 0.0);
     const double l22 = a22 * r2, l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
     a33 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
-    if (!(a33 > 0.0)) return false;
-    const double r3 = rsqrt(a33);
+    const double r3 = (a33 > 0.0) ? rsqrt(a33) : (clean = false, 0.0);
+    all_clean = all_clean && clean;
     const double l33 = a33 * r3;
     // M = L^{-1} (lower triangular)
     const double m00 = r0, m11 = r1, m22 = r2, m33 = r3;
@@ -124,7 +127,7 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane) {
     }
     __syncwarp();
   }
-  return true;
+  return all_clean;
 }
 
 // Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).
@@ -223,7 +226,7 @@ __global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, cons
   if (lane + 32 < n) prod[lane + 32] = y1;
   __syncwarp();
   const bool good = chol_tiles(K, Dinv, nb, lane);
-  if (good) solve_tiles(K, Dinv, rhs, nb, lane);
+  solve_tiles(K, Dinv, rhs, nb, lane);
   __syncwarp();
   for (int i = lane; i < n; i += 32) sol[i] = rhs[i];
   if (lane == 0) *ok = good ? 1 : 0;
