@@ -320,6 +320,27 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
   return 0;
 }
 
+int32_t jmpc_host_alloc(jmpc_handle h, size_t bytes, void** out) {
+  if (!h || !out) return fail("jmpc_host_alloc: NULL argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMallocHost(out, bytes ? bytes : 1));
+  return 0;
+}
+
+int32_t jmpc_host_free(jmpc_handle h, void* p) {
+  if (!h) return fail("jmpc_host_free: NULL handle");
+  if (p) CK(cudaFreeHost(p));
+  return 0;
+}
+
+namespace {
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
 int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
                        double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
@@ -332,54 +353,69 @@ int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state,
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   const size_t T1 = T + 1, b = (size_t)B;
-  // one contiguous staging block: [inputs | in-out | outputs], 8-byte fields first
-  struct Seg { size_t off, bytes; };
+  // Device side: one contiguous block [inputs | in-out | outputs].  Host side: arrays that live in page-locked
+  // memory (jmpc_host_alloc, cudaHostAlloc, torch pin_memory) are copied straight to / from the device; pageable
+  // ones go through the handle's pinned staging block (one memcpy each way).
+  struct Seg { size_t off, bytes; void* host; bool pinned; bool out; };
   size_t off = 0;
-  auto seg = [&](size_t bytes) { Seg s{off, bytes}; off += (bytes + 15) & ~size_t(15); return s; };
-  const Seg s_state = seg(b * 4 * 8), s_params = seg(params ? b * JMPC_NPARAM * 8 : 0);
-  const Seg s_cid = seg(course_id ? b * 4 : 0), s_clen = seg(course_len ? b * 4 : 0), s_warm = seg(warm ? b * 4 : 0);
-  const size_t in_end = off;
-  const Seg s_oa = seg(b * T * 8), s_od = seg(b * T * 8), s_tgt = seg(b * 4);
-  const size_t inout_end = off;
-  const Seg s_ox = seg(b * T1 * 8), s_oy = seg(b * T1 * 8), s_ov = seg(b * T1 * 8), s_oyaw = seg(b * T1 * 8);
-  const Seg s_xref = seg(b * 4 * T1 * 8), s_cost = seg(b * 8), s_status = seg(b * 4), s_iters = seg(b * 4);
-  const Seg s_rec = seg(record ? b * JMPC_RECORD_LEN * 8 : 0);
+  Seg segs[17];
+  int ns = 0;
+  auto seg = [&](size_t bytes, const void* host, bool out) -> Seg& {
+    Seg& s = segs[ns++];
+    s.off = off; s.bytes = host ? bytes : 0; s.host = const_cast<void*>(host); s.out = out;
+    s.pinned = host ? is_pinned(host) : false;
+    off += (s.bytes + 15) & ~size_t(15);
+    return s;
+  };
+  const Seg& s_state = seg(b * 4 * 8, state, false);
+  const Seg& s_params = seg(b * JMPC_NPARAM * 8, params, false);
+  const Seg& s_cid = seg(b * 4, course_id, false);
+  const Seg& s_clen = seg(b * 4, course_len, false);
+  const Seg& s_warm = seg(b * 4, warm, false);
+  const int first_inout = ns;
+  const Seg& s_oa = seg(b * T * 8, oa, true);
+  const Seg& s_od = seg(b * T * 8, od, true);
+  const Seg& s_tgt = seg(b * 4, target_ind, true);
+  const int first_out = ns;
+  const Seg& s_ox = seg(b * T1 * 8, ox, true);
+  const Seg& s_oy = seg(b * T1 * 8, oy, true);
+  const Seg& s_ov = seg(b * T1 * 8, ov, true);
+  const Seg& s_oyaw = seg(b * T1 * 8, oyaw, true);
+  const Seg& s_xref = seg(b * 4 * T1 * 8, xref, true);
+  const Seg& s_cost = seg(b * 8, cost, true);
+  const Seg& s_status = seg(b * 4, status, true);
+  const Seg& s_iters = seg(b * 4, iters, true);
+  const Seg& s_rec = seg(b * JMPC_RECORD_LEN * 8, record, true);
   const size_t total = off;
   if (ensure_stage(h, total)) return -1;
   char* hs = h->h_stage; char* ds = h->d_stage;
-  memcpy(hs + s_state.off, state, s_state.bytes);
-  if (params) memcpy(hs + s_params.off, params, s_params.bytes);
-  if (course_id) memcpy(hs + s_cid.off, course_id, s_cid.bytes);
-  if (course_len) memcpy(hs + s_clen.off, course_len, s_clen.bytes);
-  if (warm) memcpy(hs + s_warm.off, warm, s_warm.bytes);
-  memcpy(hs + s_oa.off, oa, s_oa.bytes);
-  memcpy(hs + s_od.off, od, s_od.bytes);
-  memcpy(hs + s_tgt.off, target_ind, s_tgt.bytes);
-  (void)in_end;
   cudaStream_t st = h->own_stream;
-  CK(cudaMemcpyAsync(ds, hs, inout_end, cudaMemcpyHostToDevice, st));
-  int rc = jmpc_step(h, B, T, (const double*)(ds + s_state.off), course_id ? (const int*)(ds + s_cid.off) : nullptr,
-                     course_len ? (const int*)(ds + s_clen.off) : nullptr, (int*)(ds + s_tgt.off),
-                     warm ? (const int*)(ds + s_warm.off) : nullptr, (double*)(ds + s_oa.off), (double*)(ds + s_od.off),
-                     params ? (const double*)(ds + s_params.off) : nullptr, (double*)(ds + s_ox.off),
-                     (double*)(ds + s_oy.off), (double*)(ds + s_ov.off), (double*)(ds + s_oyaw.off),
-                     (double*)(ds + s_xref.off), (double*)(ds + s_cost.off), (int*)(ds + s_status.off),
-                     (int*)(ds + s_iters.off), record ? (double*)(ds + s_rec.off) : nullptr, (void*)st);
+  // host -> device: inputs and in-out arrays
+  for (int k = 0; k < first_out; ++k) {
+    const Seg& s = segs[k];
+    if (!s.bytes) continue;
+    const void* src = s.host;
+    if (!s.pinned) { memcpy(hs + s.off, s.host, s.bytes); src = hs + s.off; }
+    CK(cudaMemcpyAsync(ds + s.off, src, s.bytes, cudaMemcpyHostToDevice, st));
+  }
+  auto dp = [&](const Seg& s) -> char* { return s.bytes ? ds + s.off : nullptr; };
+  int rc = jmpc_step(h, B, T, (const double*)dp(s_state), (const int*)dp(s_cid), (const int*)dp(s_clen), (int*)dp(s_tgt),
+                     (const int*)dp(s_warm), (double*)dp(s_oa), (double*)dp(s_od), (const double*)dp(s_params),
+                     (double*)dp(s_ox), (double*)dp(s_oy), (double*)dp(s_ov), (double*)dp(s_oyaw), (double*)dp(s_xref),
+                     (double*)dp(s_cost), (int*)dp(s_status), (int*)dp(s_iters), (double*)dp(s_rec), (void*)st);
   if (rc) return rc;
-  // results: everything from the in-out block to the end.  Instances that fail the index rule or are
-  // infeasible keep their input values in the in-out block, so copying it back wholesale is safe.
-  CK(cudaMemcpyAsync(hs + s_oa.off, ds + s_oa.off, total - s_oa.off, cudaMemcpyDeviceToHost, st));
+  // device -> host.  Instances that fail the index rule or are infeasible keep their input values in the in-out
+  // arrays, so copying those back wholesale is safe.
+  for (int k = first_inout; k < ns; ++k) {
+    const Seg& s = segs[k];
+    if (!s.bytes) continue;
+    CK(cudaMemcpyAsync(s.pinned ? s.host : (void*)(hs + s.off), ds + s.off, s.bytes, cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaStreamSynchronize(st));
-  memcpy(oa, hs + s_oa.off, s_oa.bytes);
-  memcpy(od, hs + s_od.off, s_od.bytes);
-  memcpy(target_ind, hs + s_tgt.off, s_tgt.bytes);
-  memcpy(ox, hs + s_ox.off, s_ox.bytes); memcpy(oy, hs + s_oy.off, s_oy.bytes);
-  memcpy(ov, hs + s_ov.off, s_ov.bytes); memcpy(oyaw, hs + s_oyaw.off, s_oyaw.bytes);
-  memcpy(xref, hs + s_xref.off, s_xref.bytes);
-  memcpy(cost, hs + s_cost.off, s_cost.bytes);
-  memcpy(status, hs + s_status.off, s_status.bytes);
-  if (iters) memcpy(iters, hs + s_iters.off, s_iters.bytes);
-  if (record) memcpy(record, hs + s_rec.off, s_rec.bytes);
+  for (int k = first_inout; k < ns; ++k) {
+    const Seg& s = segs[k];
+    if (s.bytes && !s.pinned) memcpy(s.host, hs + s.off, s.bytes);
+  }
   return 0;
 }
 

@@ -78,6 +78,8 @@ class BatchedMPC:
                                           len(courses), _ptr(self.default_params), C.byref(opt), C.byref(h)),
                     "jmpc_create")
         self._h = h
+        self._pinned = []
+        self._host_out = {}
         self.set_courses(courses)
 
     # ---- configuration ----------------------------------------------------------------------------------
@@ -104,6 +106,10 @@ class BatchedMPC:
 
     def close(self):
         if getattr(self, "_h", None):
+            self._host_out = {}
+            for p in getattr(self, "_pinned", []):
+                self._lib.jmpc_host_free(self._h, p)
+            self._pinned = []
             self._lib.jmpc_destroy(self._h)
             self._h = None
 
@@ -133,10 +139,35 @@ class BatchedMPC:
             _cabi.check(rc, "jmpc_debug_linalg")
         return sol, prod, rc == 0
 
+    # ---- page-locked host arrays --------------------------------------------------------------------------
+    def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
+        """numpy array in page-locked memory owned by this engine (freed by close())."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _cabi.check(self._lib.jmpc_host_alloc(self._h, n, C.byref(p)), "jmpc_host_alloc")
+        self._pinned.append(p)
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def host_outputs(self, B: int, T: Optional[int] = None) -> StepOutput:
+        """Reusable page-locked result arrays for `step_host(..., out=...)`: no allocation, page faults or staging
+        copy per step.  Contents are overwritten by the next call that is given the same object."""
+        T = int(T or self.T)
+        key = (B, T)
+        if key not in self._host_out:
+            f, i = self.pinned_empty, lambda s: self.pinned_empty(s, np.int32)
+            self._host_out[key] = StepOutput(oa=f((B, T)), od=f((B, T)), ox=f((B, T + 1)), oy=f((B, T + 1)),
+                                             ov=f((B, T + 1)), oyaw=f((B, T + 1)), xref=f((B, 4, T + 1)), cost=f((B,)),
+                                             status=i((B,)), iters=i((B,)), target_ind=i((B,)),
+                                             record=f((B, _cabi.RECORD_LEN)))
+        return self._host_out[key]
+
     # ---- host path --------------------------------------------------------------------------------------
     def step_host(self, state, target_ind, oa=None, od=None, course_id=None, course_len=None, warm=None,
-                  params=None, T: Optional[int] = None) -> StepOutput:
+                  params=None, T: Optional[int] = None, out: Optional[StepOutput] = None) -> StepOutput:
         T = int(T or self.T)
+        if out is not None:
+            return self._step_host_into(out, T, state, target_ind, oa, od, course_id, course_len, warm, params)
         state = _f64(state)
         B = state.shape[0]
         if state.shape != (B, 4):
@@ -163,6 +194,29 @@ class BatchedMPC:
                                              _ptr(oyaw), _ptr(xref), _ptr(cost), _ptr(status), _ptr(iters),
                                              _ptr(record)), "jmpc_step_host")
         return StepOutput(oa_b, od_b, ox, oy, ov, oyaw, xref, cost, status, iters, tgt, record)
+
+    def _step_host_into(self, out, T, state, target_ind, oa, od, course_id, course_len, warm, params) -> StepOutput:
+        state = _f64(state)
+        B = state.shape[0]
+        if out.oa.shape != (B, T):
+            raise ValueError("`out` was made for another batch size / horizon")
+        if oa is None or od is None:
+            out.oa[...] = 0.0
+            out.od[...] = 0.0
+            warm = np.zeros(B, np.int32)
+        else:
+            np.copyto(out.oa, oa)
+            np.copyto(out.od, od)
+        np.copyto(out.target_ind, target_ind)
+        cid = None if course_id is None else _i32(course_id, (B,))
+        clen = None if course_len is None else _i32(course_len, (B,))
+        wrm = None if warm is None else _i32(warm, (B,))
+        prm = None if params is None else _f64(params, (B, NPARAM))
+        _cabi.check(self._lib.jmpc_step_host(self._h, B, T, _ptr(state), _ptr(cid), _ptr(clen), _ptr(out.target_ind),
+                                             _ptr(wrm), _ptr(out.oa), _ptr(out.od), _ptr(prm), _ptr(out.ox), _ptr(out.oy),
+                                             _ptr(out.ov), _ptr(out.oyaw), _ptr(out.xref), _ptr(out.cost),
+                                             _ptr(out.status), _ptr(out.iters), _ptr(out.record)), "jmpc_step_host")
+        return out
 
     def collision_host(self, agent_idx, v, obstacles, frame_window: int, margin: int, course_id=None,
                        params=None, horizon_s: float = 7.0):

@@ -27,6 +27,7 @@
 #ifndef JMPC_H_
 #define JMPC_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -127,6 +128,11 @@ int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
                        double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
                        double* xref, double* cost, int32_t* status, int32_t* iters, double* record);
+
+/* Page-locked host memory for the *_host entry points: arrays placed in it are transferred without the staging
+ * memcpy (any page-locked memory is recognised, e.g. cudaHostAlloc or torch pin_memory). */
+int32_t jmpc_host_alloc(jmpc_handle h, size_t bytes, void** out);
+int32_t jmpc_host_free(jmpc_handle h, void* p);
 
 /* Collision flag + cut index for B instances (mpc_intersection.py:111-140, collision_avoidance.py:85-124,
  * 168-180, moving_obstacles_prediction.py:21-47, trajectories.py:58-86).  DEVICE pointers.

@@ -180,3 +180,18 @@ def test_full_config2_properties(jm):
     inp = (ra * out.oa ** 2 + rd * out.od ** 2).sum(1)
     rate = (p.Rd[0] * np.diff(out.oa, axis=1) ** 2 + p.Rd[1] * np.diff(out.od, axis=1) ** 2).sum(1)
     np.testing.assert_allclose(out.cost, stage + inp + rate, rtol=1e-9)
+
+
+def test_pinned_host_outputs_equal_plain_host_path(jm):
+    synth, BatchedMPC = jm
+    w = synth.make_workload(2, B=257)
+    mpc, plain = _run(BatchedMPC, w)
+    out = mpc.host_outputs(257)
+    for _ in range(2):      # reuse of the same page-locked arrays
+        got = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"], out=out)
+    assert got is out
+    for key in ["oa", "od", "ox", "oy", "ov", "oyaw", "xref", "cost", "status", "iters", "target_ind", "record"]:
+        assert np.array_equal(getattr(got, key), getattr(plain, key)), key
+    # the packed record is what the multi-GPU all-gather ships
+    assert np.array_equal(got.record[:, 0], got.od[:, 0]) and np.array_equal(got.record[:, 1], got.oa[:, 0])
+    assert np.array_equal(got.record[:, 3], got.status) and np.array_equal(got.record[:, 4], got.target_ind)
