@@ -199,7 +199,12 @@ def ipm_solve(c: CondensedQP, max_iter: int = 40, mu_tol: float = 1e-13, s_min: 
         mu_aff = float(((lh + a_aff * dlh) * (sh + a_aff * dsh) + (ll + a_aff * dll) * (sl + a_aff * dsl))[live].sum()) / nrow
         sigma = (mu_aff / mu) ** 3
         du, dsh, dsl, dlh, dll = newton(lh * sh + dsh * dlh - sigma * mu, ll * sl + dsl * dll - sigma * mu)
-        alpha = min(1.0, 0.99 * min(max_step(sh, dsh), max_step(sl, dsl), max_step(lh, dlh), max_step(ll, dll)))
+        def raw_step(v, dv):
+            m = live & (dv < 0)
+            return float((-v[m] / dv[m]).min()) if m.any() else np.inf
+
+        frac = min(0.9999, max(0.99, 1.0 - 0.1 * (1.0 - a_aff) ** 2))   # fraction to the boundary, as in the kernel
+        alpha = min(1.0, frac * min(raw_step(sh, dsh), raw_step(sl, dsl), raw_step(lh, dlh), raw_step(ll, dll)))
         u = u + alpha * du
         sh, sl = sh + alpha * dsh, sl + alpha * dsl
         lh, ll = lh + alpha * dlh, ll + alpha * dll
