@@ -251,6 +251,16 @@ def main():
             dist.destroy_process_group()
         return
 
+    # latency of one controller call for a single ego (what a scenario runner sees per timestep)
+    one = BatchedMPC(w["courses"], dl=w["dl"], T=T, max_batch=1, device=local)
+    lat = []
+    for k in range(60):
+        t0 = time.perf_counter()
+        one.step_host(w["state"][:1], w["target_ind"][:1], w["oa"][:1], w["od"][:1], course_len=w["course_len"][:1])
+        if k >= 10:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    one.close()
+
     # roofline of the (single) kernel of the step: CUDA-core FP64 FMA bound
     fp64_peak, fp32_peak = mpc.measure_fma_peak()
     kernel_ms = float(np.mean(per_step))
@@ -261,6 +271,14 @@ def main():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1d_traffic.json")) as f:
+            tr = json.load(f)
+        if B == 4096 and T == 20:
+            traffic = tr["dram_bytes_per_launch"]          # from the committed ncu --set full capture, per launch
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -275,13 +293,16 @@ def main():
                    "solver": "condensed QP, Mehrotra predictor-corrector interior point, fp64",
                    "mean_solver_iters": mean_iters, "max_solver_iters": int(iters.max())},
         "p50_ms": float(np.percentile(per_step, 50)), "p99_ms": float(np.percentile(per_step, 99)),
+        "single_instance_step_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                    "api": "step_host, B=1, host in / host out"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": float(e2e_ms.item()), "steps": e2e_steps,
                 "api": "BatchedMPC.step_host(out=host_outputs) -> jmpc_step_host: numpy inputs in pageable memory staged through pinned memory, results DMA-ed into page-locked numpy arrays"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
+                     "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1d_traffic.json)",
                      "peak_source": "jmpc_measure_fma_peak: register-resident FP64 FMA loop on all SMs, measured in this run "
                                     "(MEASURED_PEAKS.json holds no FP64 figure)",
                      "flops_per_solve": flops_per_solve(T, mean_iters), "kernel": "jmpc::mpc_step_kernel",
