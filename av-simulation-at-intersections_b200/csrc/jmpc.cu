@@ -11,6 +11,7 @@
 #include "../../include/jmpc.h"
 #include "jmpc_collision.cuh"
 #include "jmpc_step.cuh"
+#include "jmpc_episode.cuh"
 
 namespace {
 
@@ -76,7 +77,8 @@ StepKernel step_kernel_for(int T) {
 }
 
 int step_geometry(jmpc_handle h, int B, int T, StepGeom* g) {
-  const int wpb = 4;
+  int wpb = 4;
+  if (const char* e = getenv("JMPC_WPB")) wpb = std::max(1, std::min(4, atoi(e)));
   const size_t smem = (size_t)wpb * jmpc::warp_smem_doubles(T) * sizeof(double);
   StepKernel k = step_kernel_for(T);
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -503,6 +505,68 @@ int32_t jmpc_plant_step(jmpc_handle h, int32_t B, double* state, const double* a
   jmpc::ParamBlock d;
   memcpy(d.v, h->defaults, sizeof h->defaults);
   plant_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, state, a, delta, params, d);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+namespace {
+void fill_episode_args(jmpc_handle h, jmpc::EpisodeArgs& a, int B, const int* course_id, const double* params) {
+  memset(&a, 0, sizeof a);
+  a.B = B; a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
+  a.course_stride = h->course_stride; a.course_id = course_id; a.params = params;
+  memcpy(a.defaults.v, h->defaults, sizeof h->defaults);
+}
+}  // namespace
+
+int32_t jmpc_episode_pre(jmpc_handle h, int32_t B, const double* state, const int32_t* course_id,
+                         const int32_t* course_len, const int32_t* target_ind, const int32_t* steps,
+                         int32_t* agent_idx, int32_t* done, double goal_dis, double stop_speed, void* stream) {
+  if (!h) return fail("jmpc_episode_pre: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_episode_pre: B out of range");
+  if (!state || !course_len || !target_ind || !steps || !agent_idx || !done) return fail("jmpc_episode_pre: NULL array");
+  if (h->n_courses < 1) return fail("jmpc_episode_pre: no courses uploaded (jmpc_set_courses)");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  jmpc::EpisodeArgs a;
+  fill_episode_args(h, a, B, course_id, nullptr);
+  a.state = const_cast<double*>(state); a.course_len = const_cast<int*>(course_len);
+  a.target_ind = const_cast<int*>(target_ind); a.steps = const_cast<int*>(steps);
+  a.agent_idx = agent_idx; a.done = done; a.goal_dis = goal_dis; a.stop_speed = stop_speed;
+  jmpc::episode_pre_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int32_t jmpc_episode_post(jmpc_handle h, int32_t B, double* state, const int32_t* course_id, const double* record,
+                          const double* params, int32_t* target_ind, int32_t* steps, int32_t* done, double* di,
+                          int32_t* warm, double* history, double t_now, void* stream) {
+  if (!h) return fail("jmpc_episode_post: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_episode_post: B out of range");
+  if (!state || !record || !target_ind || !steps || !done || !di) return fail("jmpc_episode_post: NULL array");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  jmpc::EpisodeArgs a;
+  fill_episode_args(h, a, B, course_id, params);
+  a.state = state; a.record = record; a.target_ind = target_ind; a.steps = steps; a.done = done; a.di = di;
+  a.warm = warm; a.history = history; a.t_now = t_now;
+  jmpc::episode_post_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int32_t jmpc_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, double* obstacles, const int32_t* done,
+                           double dt, void* stream) {
+  if (!h) return fail("jmpc_obstacle_step: NULL handle");
+  if (B < 0 || B > h->max_B || n_obs < 0) return fail("jmpc_obstacle_step: size out of range");
+  if (B == 0 || n_obs == 0) return 0;
+  if (!obstacles) return fail("jmpc_obstacle_step: NULL array");
+  CK(cudaSetDevice(h->device));
+  const int count = B * n_obs;
+  jmpc::obstacle_step_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(count, obstacles, done, n_obs, dt,
+                                                                                   h->defaults[JMPC_P_L]);
   CK(cudaGetLastError());
   h->launches++;
   return 0;

@@ -1,0 +1,142 @@
+// jmpc_episode.cuh -- the pieces of the scenario loop around the MPC step, for B closed-loop episodes on the device.
+//
+// Reference loop: main/scenarios/mpc_intersection.py:99-163 (identical in mpc_roundabout.py / _multi_lane.py):
+//   is_goal(state) -> break                                  mpc.py:314-330            [episode_pre_kernel]
+//   traj_agent_idx = nearest forward index on the full course, unless the truncated course has collapsed onto
+//                    the ego's point                         mpc_intersection.py:107-109 [episode_pre_kernel]
+//   collision check -> truncated course length               :111-143                  [collision_kernel]
+//   delta, a = mpc.step(state)                               :146                      [mpc_step_kernel]
+//   xref deviation; plant step; history                      :163, mpc.py:305-312, simulation.py:35-61 [episode_post_kernel]
+// Obstacles move with constant inputs here (the reference's scripted obstacles are outside the hot path):
+//   obstacle_step_kernel uses the same update as their predictor, moving_obstacles_prediction.py:21-29.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/jmpc.h"
+#include "jmpc_collision.cuh"
+
+namespace jmpc {
+
+__device__ inline int nearest_index(const double* __restrict__ cx, const double* __restrict__ cy, int n_course,
+                                    int start, double x, double y, int lane);   // jmpc_step.cuh
+
+struct EpisodeArgs {
+  int B, T;
+  const double* cx; const double* cy; const double* cyaw; const int* course_n; int course_stride;
+  const int* course_id;
+  const double* params; ParamBlock defaults;
+  double goal_dis, stop_speed;
+  double* state;            // [B][4] x, y, v, yaw   (in-out)
+  int* agent_idx;           // [B]   traj_agent_idx  (in-out)
+  int* course_len;          // [B]   length of the course the MPC was last given (len(mpc.cx))
+  int* target_ind;          // [B]   mpc.target_ind
+  int* done;                // [B]   1 once is_goal fired (or the index rule failed: done = 2)
+  int* steps;               // [B]   loop iterations executed
+  double* di;               // [B]   last commanded steer (kept when a solve fails, mpc.py:298-301)
+  int* warm;                // [B]   1 when the next step may use oa/od as its linearisation point (mpc.py:225-227)
+  const double* record;     // [B][JMPC_RECORD_LEN] from the step kernel
+  double* history;          // [B][8] slice for this step: x, y, yaw, v, t, delta, a, xref_deviation; or nullptr
+  double t_now;
+};
+
+// One warp per episode: goal test, then the ego's index on the full course.
+__global__ void __launch_bounds__(128) episode_pre_kernel(const EpisodeArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= A.B) return;
+  if (A.done[b]) return;
+  const int cid = A.course_id ? A.course_id[b] : 0;
+  const double* cx = A.cx + (size_t)cid * A.course_stride;
+  const double* cy = A.cy + (size_t)cid * A.course_stride;
+  const double* cyaw = A.cyaw + (size_t)cid * A.course_stride;
+  const int N = A.course_n[cid];
+  const double x = A.state[4 * b], y = A.state[4 * b + 1], v = A.state[4 * b + 2];
+  // is_goal: distance to the end of the FULL course, target index against the CURRENT course length (mpc.py:322)
+  const int len = A.course_len[b];
+  const double d = hypot(x - cx[N - 1], y - cy[N - 1]);
+  bool goal = d <= A.goal_dis;
+  if (abs(A.target_ind[b] - len) >= 5) goal = false;
+  if (goal && fabs(v) <= A.stop_speed) {
+    if (lane == 0) A.done[b] = 1;
+    return;
+  }
+  // mpc_intersection.py:107: skip the update when the truncated course ends exactly at the ego's course point
+  int a0 = A.agent_idx[b];
+  bool update = true;
+  if (A.steps[b] > 0) {
+    const int last = min(len, N) - 1;
+    const int at = min(a0, last);                 // tmp_trajectory[traj_agent_idx] (a0 < len always holds: cut >= a0 + 1)
+    update = (cx[at] != cx[last]) || (cy[at] != cy[last]) || (cyaw[at] != cyaw[last]);
+  }
+  if (update) {
+    const int near = nearest_index(cx, cy, N, a0, x, y, lane);
+    if (near < 0) { if (lane == 0) A.done[b] = 2; return; }     // reference raises (trajectories.py:120)
+    a0 = near;
+  }
+  if (lane == 0) A.agent_idx[b] = a0;
+}
+
+// One thread per episode: controls from the step's record, xref deviation, plant step, history, counters.
+__global__ void episode_post_kernel(const EpisodeArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  if (A.done[b]) return;
+  const double* prm = A.params ? A.params + (size_t)b * JMPC_NPARAM : A.defaults.v;
+  const double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
+  const int status = (int)rec[3];
+  if (status == JMPC_INDEX_RULE) { A.done[b] = 2; return; }
+  const int cid = A.course_id ? A.course_id[b] : 0;
+  const size_t coff = (size_t)cid * A.course_stride;
+  double x = A.state[4 * b], y = A.state[4 * b + 1], v = A.state[4 * b + 2], yaw = A.state[4 * b + 3];
+  const int target = (int)rec[4];
+  A.target_ind[b] = target;
+  double delta = A.di[b], acc = prm[JMPC_P_MAX_DECEL];
+  double dev = nan("");
+  if (status == JMPC_OPTIMAL || status == JMPC_MAX_ITER) {
+    delta = rec[0]; acc = rec[1];
+    // get_current_xref_deviation (mpc.py:305-312); ox[0], oy[0] are the current position
+    const double ang = A.cyaw[coff + target] + M_PI / 2;
+    const double ex = A.cx[coff + target] - x, ey = A.cy[coff + target] - y;
+    const double px = cos(ang) * ex, py = sin(ang) * ey;
+    dev = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+  }
+  A.di[b] = delta;
+  if (A.warm) A.warm[b] = (status == JMPC_OPTIMAL || status == JMPC_MAX_ITER) ? 1 : 0;
+  // Simulation.step (simulation.py:35-47)
+  const double dt = prm[JMPC_P_DT], L = prm[JMPC_P_L], ms = prm[JMPC_P_MAX_STEER];
+  const double dcl = fmax(fmin(delta, ms), -ms);
+  const double xd = __dmul_rn(v, cos(yaw)), yd = __dmul_rn(v, sin(yaw)), td = __dmul_rn(v / L, tan(dcl));
+  x = __dadd_rn(x, __dmul_rn(xd, dt));
+  y = __dadd_rn(y, __dmul_rn(yd, dt));
+  yaw = __dadd_rn(yaw, __dmul_rn(td, dt));
+  v = __dadd_rn(v, __dmul_rn(acc, dt));
+  v = fmax(fmin(v, prm[JMPC_P_SIM_MAX_SPEED]), prm[JMPC_P_MIN_SPEED]);
+  A.state[4 * b] = x; A.state[4 * b + 1] = y; A.state[4 * b + 2] = v; A.state[4 * b + 3] = yaw;
+  A.steps[b] += 1;
+  if (A.history) {
+    double* hrow = A.history + (size_t)b * 8;        // History.store (simulation.py:76-84), raw delta as stored there
+    hrow[0] = x; hrow[1] = y; hrow[2] = yaw; hrow[3] = v; hrow[4] = A.t_now + dt; hrow[5] = delta; hrow[6] = acc;
+    hrow[7] = dev;
+  }
+}
+
+// Constant-input obstacle motion, one thread per obstacle: obstacles [B][n_obs][6] = x, y, v, yaw, a, steer.
+__global__ void obstacle_step_kernel(int count, double* __restrict__ obs, const int* __restrict__ done, int n_obs,
+                                     double dt, double L) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  if (done && done[k / n_obs]) return;
+  double* o = obs + (size_t)k * 6;
+  double x = o[0], y = o[1], v = o[2], yaw = o[3];
+  double s, c;
+  sincos(yaw, &s, &c);
+  x = __dadd_rn(x, __dmul_rn(__dmul_rn(v, c), dt));
+  y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, s), dt));
+  v = __dadd_rn(v, __dmul_rn(o[4], dt));
+  yaw = __dadd_rn(yaw, __dmul_rn(__dmul_rn(v / L, tan(o[5])), dt));
+  o[0] = x; o[1] = y; o[2] = v; o[3] = yaw;
+}
+
+}  // namespace jmpc

@@ -1,0 +1,108 @@
+"""BatchedEpisodes: B closed-loop episodes of the reference's scenario loop, device resident.
+
+One iteration = the body of `for i in itertools.count()` in main/scenarios/mpc_intersection.py:99-163:
+goal test -> ego index on the full course -> collision flag / cut -> MPC step -> plant step + history.
+Everything runs in libjmpc.so kernels on torch-owned device tensors; the host only sequences launches and looks
+at the `done` flags every few iterations.  Obstacles are either a per-step script (e.g. a recording of the
+reference's scripted obstacles) or constant-input vehicles advanced on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi
+from .batched import BatchedMPC
+
+
+class BatchedEpisodes:
+    def __init__(self, engine: BatchedMPC, state0, course_id=None, obstacles=None, obstacle_script=None,
+                 frame_window: int = 10, margin: int = 72, params=None, max_steps: int = 256,
+                 record_history: bool = True, horizon_s: float = 7.0):
+        import torch
+        self.torch = torch
+        self.e = engine
+        self.dev = torch.device("cuda", engine.device)
+        f64, i32 = torch.float64, torch.int32
+        t = lambda a, dt: None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=self.dev)  # noqa: E731
+        self.state = t(state0, f64)
+        self.B = B = self.state.shape[0]
+        self.T = engine.T
+        self.course_id = t(course_id, i32)
+        self.params = t(params, f64)
+        self.obstacles = t(obstacles, f64)                       # [B, n_obs, 6], advanced on the device
+        self.script = t(obstacle_script, f64)                    # [S, B, n_obs, 6], read per step
+        if self.obstacles is not None and self.script is not None:
+            raise ValueError("give either constant-input obstacles or a script")
+        self.frame_window, self.margin, self.horizon_s = int(frame_window), int(margin), float(horizon_s)
+        self.max_steps = int(max_steps)
+        full = torch.as_tensor(engine.course_len, dtype=i32, device=self.dev)
+        self.full_len = full[self.course_id.long()] if self.course_id is not None else full[0].expand(B).contiguous()
+        self.course_len = self.full_len.clone()
+        z = lambda: torch.zeros(B, dtype=i32, device=self.dev)   # noqa: E731
+        self.agent_idx, self.target_ind, self.done, self.steps, self.warm, self.flag = z(), z(), z(), z(), z(), z()
+        self.di = torch.zeros(B, dtype=f64, device=self.dev)
+        self.v = torch.zeros(B, dtype=f64, device=self.dev)
+        self.oa = torch.zeros(B, self.T, dtype=f64, device=self.dev)
+        self.od = torch.zeros(B, self.T, dtype=f64, device=self.dev)
+        self.out = engine.alloc_outputs(B)
+        self.history = torch.full((self.max_steps, B, 8), float("nan"), dtype=f64, device=self.dev) if record_history else None
+        self.flags = torch.zeros(self.max_steps, B, dtype=i32, device=self.dev) if record_history else None
+        self.iteration = 0
+
+    def _p(self, ten):
+        return None if ten is None else C.c_void_p(ten.data_ptr())
+
+    def iterate(self):
+        """One loop iteration for every episode that is not done."""
+        e, lib, torch = self.e, self.e._lib, self.torch
+        stream = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
+        i = self.iteration
+        cfg = e.config
+        _cabi.check(lib.jmpc_episode_pre(e._h, self.B, self._p(self.state), self._p(self.course_id), self._p(self.course_len),
+                                         self._p(self.target_ind), self._p(self.steps), self._p(self.agent_idx),
+                                         self._p(self.done), float(cfg.goal_dis), float(cfg.stop_speed), stream),
+                    "jmpc_episode_pre")
+        obs = self.obstacles if self.script is None else self.script[min(i, self.script.shape[0] - 1)]
+        if obs is not None and obs.shape[1] > 0:
+            self.v.copy_(self.state[:, 2])
+            e.collision(self.agent_idx, self.v, obs, self.frame_window, self.margin, self.flag, self.course_len,
+                        course_id=self.course_id, params=self.params, horizon_s=self.horizon_s)
+            if self.flags is not None and i < self.max_steps:
+                self.flags[i].copy_(self.flag)
+        e.step(self.state, self.target_ind, self.oa, self.od, self.out, course_id=self.course_id,
+               course_len=self.course_len, warm=self.warm, params=self.params)
+        hist = self.history[i] if (self.history is not None and i < self.max_steps) else None
+        _cabi.check(lib.jmpc_episode_post(e._h, self.B, self._p(self.state), self._p(self.course_id), self._p(self.out.record),
+                                          self._p(self.params), self._p(self.target_ind), self._p(self.steps),
+                                          self._p(self.done), self._p(self.di), self._p(self.warm), self._p(hist),
+                                          float(i * e.dt), stream), "jmpc_episode_post")
+        if self.obstacles is not None and self.obstacles.shape[1] > 0:
+            _cabi.check(lib.jmpc_obstacle_step(e._h, self.B, int(self.obstacles.shape[1]), self._p(self.obstacles),
+                                               self._p(self.done), float(e.dt), stream), "jmpc_obstacle_step")
+        self.iteration += 1
+
+    def run(self, max_steps: Optional[int] = None, check_every: int = 8):
+        """Iterate until every episode reached its goal (or max_steps).  Returns a dict of numpy results."""
+        max_steps = int(max_steps or self.max_steps)
+        while self.iteration < max_steps:
+            self.iterate()
+            if self.iteration % check_every == 0 and bool((self.done != 0).all().item()):
+                break
+        # the reference tests the goal at the top of the next iteration
+        lib, e = self.e._lib, self.e
+        stream = C.c_void_p(self.torch.cuda.current_stream(e.device).cuda_stream)
+        _cabi.check(lib.jmpc_episode_pre(e._h, self.B, self._p(self.state), self._p(self.course_id), self._p(self.course_len),
+                                         self._p(self.target_ind), self._p(self.steps), self._p(self.agent_idx),
+                                         self._p(self.done), float(e.config.goal_dis), float(e.config.stop_speed), stream),
+                    "jmpc_episode_pre")
+        self.torch.cuda.synchronize(e.device)
+        res = dict(steps=self.steps.cpu().numpy(), done=self.done.cpu().numpy(), state=self.state.cpu().numpy(),
+                   iterations=self.iteration)
+        if self.history is not None:
+            n = min(self.iteration, self.max_steps)
+            res["history"] = self.history[:n].cpu().numpy()          # [steps, B, 8]: x, y, yaw, v, t, delta, a, xref_dev
+            res["flags"] = self.flags[:n].cpu().numpy()
+        return res

@@ -154,6 +154,27 @@ int32_t jmpc_collision_host(jmpc_handle h, int32_t B, const int32_t* course_id, 
 int32_t jmpc_plant_step(jmpc_handle h, int32_t B, double* state, const double* a, const double* delta,
                         const double* params, void* stream);
 
+/* Closed-loop episodes on the device (the scenario loop around the step, main/scenarios/mpc_intersection.py:99-163).
+ * DEVICE pointers; all arrays [B] unless noted; episodes with done != 0 are left untouched by all three.
+ *   jmpc_episode_pre : done |= is_goal(state) (mpc.py:314-330; done = 2 when the index rule raises), then
+ *                      agent_idx = nearest forward index on the full course unless the truncated course has
+ *                      collapsed onto the ego's point (mpc_intersection.py:107-109).  course_len = length of the
+ *                      course the MPC was last given, steps = iterations executed so far.
+ *   jmpc_episode_post: takes the step's record [B][JMPC_RECORD_LEN], applies (a, delta) to the plant
+ *                      (simulation.py:35-47; a = MAX_DECEL and the previous delta when the solve failed,
+ *                      mpc.py:298-301), stores target_ind, sets warm (0 after a failed solve: the next step starts
+ *                      from zeros, mpc.py:225-227), increments steps and, if history != NULL, writes one
+ *                      History row [B][8] = x, y, yaw, v, t, delta, a, xref_deviation (simulation.py:76-84).
+ *   jmpc_obstacle_step: constant-input motion of obstacles [B][n_obs][6] (moving_obstacles_prediction.py:21-29). */
+int32_t jmpc_episode_pre(jmpc_handle h, int32_t B, const double* state, const int32_t* course_id,
+                         const int32_t* course_len, const int32_t* target_ind, const int32_t* steps,
+                         int32_t* agent_idx, int32_t* done, double goal_dis, double stop_speed, void* stream);
+int32_t jmpc_episode_post(jmpc_handle h, int32_t B, double* state, const int32_t* course_id, const double* record,
+                          const double* params, int32_t* target_ind, int32_t* steps, int32_t* done, double* di,
+                          int32_t* warm, double* history, double t_now, void* stream);
+int32_t jmpc_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, double* obstacles, const int32_t* done,
+                           double dt, void* stream);
+
 /* Number of kernel launches issued through this handle since creation (for bench.py's gpu_launches). */
 int64_t jmpc_launch_count(jmpc_handle h);
 

@@ -1,0 +1,115 @@
+"""Device-resident closed-loop episodes against the recorded reference episodes and
+against the same loop run on the CPU with the oracle's functions."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import collision_oracle as C
+from oracle import mpc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def jm():
+    import __graft_entry__ as g
+    g.build()
+    from junction_mpc import synth
+    from junction_mpc.batched import BatchedMPC
+    from junction_mpc.episodes import BatchedEpisodes
+    return synth, BatchedMPC, BatchedEpisodes
+
+
+@pytest.mark.parametrize("name", ["intersection", "roundabout"])
+def test_replay_of_reference_episode(jm, golden_dir, name):
+    """Config 1 on the device: obstacles scripted from the recording, everything else computed by the kernels."""
+    synth, BatchedMPC, BatchedEpisodes = jm
+    e = np.load(os.path.join(golden_dir, f"episode_{name}.npz"))
+    course = e["course_smoothed"]
+    n = len(e["state"])
+    engine = BatchedMPC([course], dl=float(e["dl"]), T=13, max_batch=8)
+    state0 = np.repeat(e["state"][:1], 3, axis=0)                      # three identical egos
+    script = np.repeat(e["obs"][:, None], 3, axis=1)                   # [steps, B, n_obs, 6]
+    ep = BatchedEpisodes(engine, state0, obstacle_script=script, frame_window=int(e["frame_window"]),
+                         margin=int(e["margin"]), max_steps=160)
+    res = ep.run(check_every=4)
+    assert (res["done"] == 1).all()
+    assert (res["steps"] == n).all()                                    # 91 / 116 iterations, as the reference
+    h = res["history"][:n, 0]
+    # history row i holds the state AFTER step i
+    states_after = np.vstack([e["state"][1:], e["final_state"][None]])
+    np.testing.assert_allclose(h[:, [0, 1, 3, 2]], states_after, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(h[:, 5], e["di"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(h[:, 6], e["ai"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(h[:, 7], e["dev"], rtol=0, atol=1e-5)
+    assert np.array_equal(res["flags"][:n, 0], e["flag"])
+    np.testing.assert_allclose(res["state"][0], e["final_state"], rtol=0, atol=1e-5)
+    assert np.array_equal(res["history"][:n, 1], res["history"][:n, 0])  # identical egos stay identical
+
+
+def _cpu_episode(course, p, state0, obstacles, fw, margin, max_steps):
+    """The scenario loop with constant-input obstacles, on the CPU with the oracle's functions."""
+    geo = C.CarGeometry()
+    st = tuple(state0)
+    obs = [list(o) for o in obstacles]
+    agent, tmp_len, target, oa, od, di = 0, None, 0, None, None, 0.0
+    n_full = len(course)
+    log = []
+    for i in range(max_steps):
+        d = np.hypot(st[0] - course[-1, 0], st[1] - course[-1, 1])
+        cur_len = n_full if tmp_len is None else tmp_len
+        if d <= p.goal_dis and abs(target - cur_len) < 5 and abs(st[2]) <= p.stop_speed:
+            break
+        if tmp_len is None or np.any(course[min(agent, tmp_len - 1)] != course[tmp_len - 1]):
+            agent = O.nearest_index_forward(st[0], st[1], course[:, 0], course[:, 1], agent)
+        flag, cut = C.collision_cut(geo, course, agent, st[2], obs, dt=p.dt, frame_window=fw, max_accel=p.max_accel,
+                                    max_speed=p.sim_max_speed, margin=margin)
+        tmp_len = cut
+        r = O.mpc_step(p, st, oa, od, course[:cut, 0], course[:cut, 1], course[:cut, 2], target)
+        target = r.target_ind
+        if r.oa is not None:
+            oa, od, di, ai = r.oa, r.od, float(r.od[0]), float(r.oa[0])
+        else:
+            oa = od = None
+            ai = p.max_decel
+        st = O.plant_step(p, st, ai, di)
+        log.append(st + (int(flag),))
+        for o in obs:        # constant-input motion, as their predictor does it
+            o[0] += o[2] * np.cos(o[3]) * p.dt
+            o[1] += o[2] * np.sin(o[3]) * p.dt
+            o[2] += o[4] * p.dt
+            o[3] += (o[2] / p.L) * np.tan(o[5]) * p.dt
+    return np.array(log)
+
+
+def test_synthetic_episodes_match_cpu_loop(jm):
+    synth, BatchedMPC, BatchedEpisodes = jm
+    from helpers import params_from_vector
+    course = synth.load_course("intersection")
+    dl = float(np.linalg.norm(course[0, :2] - course[1, :2]))
+    engine = BatchedMPC([course], dl=dl, T=13, max_batch=16)
+    p = params_from_vector(engine.default_params, 13)
+    rng = np.random.default_rng(7)
+    B, steps = 6, 40
+    state0 = np.repeat(np.array([[course[0, 0], course[0, 1], 0.0, course[0, 2]]]), B, axis=0)
+    state0[:, 2] = rng.uniform(0, 3, B)
+    obstacles = np.zeros((B, 2, 6))
+    for b in range(B):
+        for o in range(2):
+            k = int(rng.integers(150, 400))
+            ang = rng.uniform(-np.pi, np.pi)
+            obstacles[b, o] = (course[k, 0] - 25 * np.cos(ang), course[k, 1] - 25 * np.sin(ang), rng.uniform(3, 8), ang,
+                               0.0, rng.uniform(-0.05, 0.05))
+    geo = C.CarGeometry()
+    margin = C.cutoff_margin(geo, dl)
+    ep = BatchedEpisodes(engine, state0, obstacles=obstacles.copy(), frame_window=10, margin=margin, max_steps=steps)
+    res = ep.run(max_steps=steps)
+    flagged = 0
+    for b in range(B):
+        ref = _cpu_episode(course, p, state0[b], obstacles[b], 10, margin, steps)
+        got = res["history"][:len(ref), b]
+        np.testing.assert_allclose(got[:, [0, 1, 3, 2]], ref[:, :4], rtol=0, atol=1e-5)
+        assert np.array_equal(res["flags"][:len(ref), b], ref[:, 4].astype(np.int32))
+        flagged += int(ref[:, 4].sum())
+    assert flagged > 0          # the obstacles do interfere in this scene
