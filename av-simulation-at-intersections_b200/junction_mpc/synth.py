@@ -48,40 +48,51 @@ def load_course(name: str) -> np.ndarray:
     return c
 
 
-def _index_rule_ok(x, y, cx, cy, start, n):
-    d = np.hypot(cx[start:n] - x, cy[start:n] - y)
-    if len(d) < 3:
-        return True
-    o = np.argsort(d, kind="stable")[:3]
-    return abs(int(o[1]) - int(o[2])) == 2 or abs(int(o[0]) - int(o[1])) == 1
+def _index_rule_ok(x, y, start, n, cx, cy, chunk: int = 8192) -> np.ndarray:
+    """Vectorised 3-nearest rule of trajectories.py:100-126 on the window [start, n) of the course: True where the
+    reference would return an index, False where it would raise."""
+    ok = np.ones(len(x), bool)
+    j = np.arange(len(cx))[None, :]
+    for lo in range(0, len(x), chunk):
+        sl = slice(lo, lo + chunk)
+        d = np.hypot(cx[None, :] - x[sl, None], cy[None, :] - y[sl, None])
+        d[(j < start[sl, None]) | (j >= n[sl, None])] = np.inf
+        idx = np.argpartition(d, 2, axis=1)[:, :3]
+        dd = np.take_along_axis(d, idx, axis=1)
+        order = np.lexsort((idx, dd), axis=1)                      # by distance, ties by index
+        idx = np.take_along_axis(idx, order, axis=1)
+        good = (np.abs(idx[:, 1] - idx[:, 2]) == 2) | (np.abs(idx[:, 0] - idx[:, 1]) == 1)
+        ok[sl] = good | ((n[sl] - start[sl]) < 3)
+    return ok
 
 
 def make_states(rng, course: np.ndarray, B: int, T: int, cut_fraction: float = 0.3) -> Dict[str, np.ndarray]:
     N = len(course)
-    state = np.zeros((B, 4))
-    target = np.zeros(B, np.int32)
-    clen = np.zeros(B, np.int32)
-    agent = np.zeros(B, np.int32)
-    k = 0
-    while k < B:
-        s = int(rng.integers(0, N - 60))
-        x = course[s, 0] + rng.uniform(-0.5, 0.5)
-        y = course[s, 1] + rng.uniform(-0.5, 0.5)
-        yaw = course[s, 2] + rng.uniform(-0.1, 0.1)
-        v = rng.uniform(0.0, 30.0 / 3.6)
-        n = N if rng.random() >= cut_fraction else int(rng.integers(s + 2, min(N, s + 300) + 1))
-        t0 = max(s - 3, 0)
-        if not _index_rule_ok(x, y, course[:, 0], course[:, 1], t0, n):
-            continue
-        state[k] = (x, y, v, yaw)
-        target[k], clen[k], agent[k] = t0, n, s
-        k += 1
+    parts = []
+    have = 0
+    while have < B:
+        m = int((B - have) * 1.1) + 16
+        s = rng.integers(0, N - 60, m)
+        x = course[s, 0] + rng.uniform(-0.5, 0.5, m)
+        y = course[s, 1] + rng.uniform(-0.5, 0.5, m)
+        yaw = course[s, 2] + rng.uniform(-0.1, 0.1, m)
+        v = rng.uniform(0.0, 30.0 / 3.6, m)
+        n_cut = rng.integers(s + 2, np.minimum(N, s + 300) + 1)
+        n = np.where(rng.random(m) < cut_fraction, n_cut, N)
+        t0 = np.maximum(s - 3, 0)
+        keep = _index_rule_ok(x, y, t0, n, course[:, 0], course[:, 1])
+        parts.append((np.stack([x, y, v, yaw], 1)[keep], t0[keep], n[keep], s[keep]))
+        have += int(keep.sum())
+    state = np.concatenate([p[0] for p in parts])[:B]
+    target = np.concatenate([p[1] for p in parts])[:B].astype(np.int32)
+    clen = np.concatenate([p[2] for p in parts])[:B].astype(np.int32)
+    agent = np.concatenate([p[3] for p in parts])[:B].astype(np.int32)
     cold = rng.random(B) < 0.25
     oa = rng.uniform(-1.0, 2.0, (B, T))
     od = np.clip(np.cumsum(rng.uniform(-0.05, 0.05, (B, T)), axis=1) + rng.uniform(-0.2, 0.2, (B, 1)), -0.7, 0.7)
     oa[cold] = 0.0
     od[cold] = 0.0
-    return dict(state=state, target_ind=target, course_len=clen, agent_idx=agent, oa=oa, od=od,
+    return dict(state=np.ascontiguousarray(state), target_ind=target, course_len=clen, agent_idx=agent, oa=oa, od=od,
                 course_id=np.zeros(B, np.int32))
 
 

@@ -176,6 +176,12 @@ def _solve_qp(P, q, A, b, G, h, c0, tol, max_iter) -> QPResult:
         if (np.abs(r_d).max(initial=0.0) <= 1e-11 * scale_d and np.abs(r_e).max(initial=0.0) <= 1e-11 * scale_p
                 and np.abs(r_p).max(initial=0.0) <= 1e-11 * scale_p and mu <= 1e-13):
             break
+        # Complementarity far below its target with the primal rows satisfied: the interior-point phase has done
+        # its job (identify the active set).  What is left in r_d is multiplier noise on rows whose slack is at
+        # roundoff; iterating on only amplifies it (w = lam / s overflows the factorisation).  The active-set
+        # refinement below produces the certified point.
+        if mu <= 1e-15 and np.abs(r_e).max(initial=0.0) <= 1e-9 * scale_p and np.abs(r_p).max(initial=0.0) <= 1e-9 * scale_p:
+            break
         fac = aug_factor(lam / s)
 
         def newton(r_c):

@@ -144,42 +144,84 @@ def test_device_path_equals_host_path(jm):
         assert np.array_equal(getattr(out, key).cpu().numpy(), getattr(host, key)), key
 
 
-def test_full_config2_properties(jm):
-    """The whole 4096 x T=20 batch: size-independent checks (feasibility, dynamics, cost re-evaluation)."""
-    synth, BatchedMPC = jm
-    w = synth.make_workload(2)
-    mpc, out = _run(BatchedMPC, w)
-    assert (out.status == 0).all()
-    pv = default_vector(w)
-    p = params_from_vector(pv, w["T"])
-    T, dt = p.T, p.dt
+def _check_properties(w, out, default_vector_fn):
+    """Size-independent checks on a whole batch: every instance solved, all constraint rows satisfied, the
+    linearised speed dynamics and initial state reproduced, and the reported cost equal to the objective of
+    mpc.py:159-187 re-evaluated (vectorised numpy) on the returned trajectories."""
+    from junction_mpc.config import PARAM_INDEX as PI
+    B, T = w["B"], w["T"]
+    assert (out.status == 0).all(), np.unique(out.status, return_counts=True)
+    prm = w["params"] if w["params"] is not None else np.repeat(default_vector_fn(w)[None, :], B, axis=0)
+    col = lambda k: prm[:, PI[k]][:, None]                 # noqa: E731
+    dt = col("dt")
     tol = 1e-7
-    assert (out.oa <= p.max_accel + tol).all() and (out.oa >= p.max_decel - tol).all()
-    assert (np.abs(out.od) <= p.max_steer + tol).all()
-    assert (np.abs(np.diff(out.od, axis=1)) <= p.max_dsteer * dt + tol).all()
-    assert (out.ov <= p.speed + tol).all() and (out.ov >= p.min_speed - tol).all()
-    # speed row of the linearised dynamics and the initial state
+    assert (out.oa <= col("max_accel") + tol).all() and (out.oa >= col("max_decel") - tol).all()
+    assert (np.abs(out.od) <= col("max_steer") + tol).all()
+    assert (np.abs(np.diff(out.od, axis=1)) <= col("max_dsteer") * dt + tol).all()
+    assert (out.ov <= col("speed") + tol).all() and (out.ov >= col("min_speed") - tol).all()
     np.testing.assert_allclose(out.ov[:, 1:], out.ov[:, :1] + dt * np.cumsum(out.oa, axis=1), atol=1e-9)
     np.testing.assert_allclose(np.stack([out.ox[:, 0], out.oy[:, 0], out.ov[:, 0], out.oyaw[:, 0]], 1), w["state"],
                                atol=1e-12)
-    # re-evaluate the objective of mpc.py:159-187 on the returned trajectories
-    reach = out.xref[:, 0, :] == 0   # placeholder, replaced below
-    idx_last = np.minimum(w["course_len"], len(w["courses"][0])) - 1
-    end_xy = w["courses"][0][idx_last, :2]
+    course = w["courses"][0]
+    idx_last = np.minimum(w["course_len"], len(course)) - 1
+    end_xy = course[idx_last, :2]
     reach = (out.xref[:, 0, :] == end_xy[:, :1]) & (out.xref[:, 1, :] == end_xy[:, 1:])
     psi = out.xref[:, 3, :]
     ex, ey = out.xref[:, 0] - out.ox, out.xref[:, 1] - out.oy
     c1, s1 = np.cos(psi + 0.5 * np.pi), np.sin(psi + 0.5 * np.pi)
     c2, s2 = np.cos(psi), np.sin(psi)
-    track = p.w_perp * (c1 * ex + s1 * ey) ** 2 + p.w_para * (c2 * ex + s2 * ey) ** 2 \
-        + p.Q_v_yaw[0] * out.ov ** 2 + p.Q_v_yaw[1] * (psi - out.oyaw) ** 2
-    final = p.Qf[0] * ex ** 2 + p.Qf[1] * ey ** 2 + p.Qf[2] * out.ov ** 2 + p.Qf[3] * (psi - out.oyaw) ** 2
+    track = col("w_perp") * (c1 * ex + s1 * ey) ** 2 + col("w_para") * (c2 * ex + s2 * ey) ** 2 \
+        + col("Q_v") * out.ov ** 2 + col("Q_yaw") * (psi - out.oyaw) ** 2
+    final = col("Qf_x") * ex ** 2 + col("Qf_y") * ey ** 2 + col("Qf_v") * out.ov ** 2 + col("Qf_yaw") * (psi - out.oyaw) ** 2
     stage = np.where(reach, final, track)[:, 1:].sum(1)
-    ra = np.where(reach[:, :T], p.R_end[0], p.R[0])
-    rd = np.where(reach[:, :T], p.R_end[1], p.R[1])
+    ra = np.where(reach[:, :T], col("Rend_a"), col("R_a"))
+    rd = np.where(reach[:, :T], col("Rend_d"), col("R_d"))
     inp = (ra * out.oa ** 2 + rd * out.od ** 2).sum(1)
-    rate = (p.Rd[0] * np.diff(out.oa, axis=1) ** 2 + p.Rd[1] * np.diff(out.od, axis=1) ** 2).sum(1)
+    rate = (col("Rd_a") * np.diff(out.oa, axis=1) ** 2 + col("Rd_d") * np.diff(out.od, axis=1) ** 2).sum(1)
     np.testing.assert_allclose(out.cost, stage + inp + rate, rtol=1e-9)
+
+
+def test_full_config2_properties(jm):
+    """The whole 4096 x T=20 batch of BASELINE.json configs[1]."""
+    synth, BatchedMPC = jm
+    w = synth.make_workload(2)
+    mpc, out = _run(BatchedMPC, w)
+    _check_properties(w, out, default_vector)
+
+
+@pytest.mark.parametrize("config", [3, 4])
+def test_full_size_roundabout_and_multilane_properties(jm, config):
+    """BASELINE.json configs[2] (65 536 instances) and configs[3] (262 144 instances) at full size, with the
+    truncated course lengths coming from the collision-flag kernel as in the scenario loop."""
+    synth, BatchedMPC = jm
+    from oracle import collision_oracle as C
+    w = synth.make_workload(config)
+    mpc = BatchedMPC(w["courses"], dl=w["dl"], T=w["T"], max_batch=w["B"])
+    margin = C.cutoff_margin(C.CarGeometry(), w["dl"])
+    flag, clen = mpc.collision_host(w["agent_idx"], w["state"][:, 2], w["obstacles"], frame_window=w["frame_window"],
+                                    margin=margin)
+    assert 0.05 < flag.mean() < 0.95
+    assert (clen[flag == 0] == len(w["courses"][0])).all() and (clen[flag == 1] > w["agent_idx"][flag == 1]).all()
+    # the step searches the course from the ego index, as mpc.target_ind does in the closed loop
+    w["course_len"] = clen
+    w["target_ind"] = np.minimum(w["target_ind"], clen - 1).astype(np.int32)
+    out = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=clen)
+    ok = out.status != 3          # a cut right behind the search start can leave the index rule undefined
+    assert ok.mean() > 0.999
+    sub = dict(w, B=int(ok.sum()), state=w["state"][ok], course_len=clen[ok], params=None)
+    import types
+    sel = types.SimpleNamespace(**{k: getattr(out, k)[ok] for k in ["oa", "od", "ox", "oy", "ov", "oyaw", "xref", "cost", "status"]})
+    _check_properties(sub, sel, default_vector)
+
+
+@pytest.mark.parametrize("T", [8, 25])
+def test_full_size_sweep_properties(jm, T):
+    """BASELINE.json configs[4]: one horizon slice (262 144 instances) of the 1M-instance parameter sweep."""
+    synth, BatchedMPC = jm
+    w = synth.make_sweep(T, states_per_point=32)
+    mpc, out = _run(BatchedMPC, w)
+    _check_properties(w, out, default_vector)
+    assert out.iters.max() <= 40
 
 
 def test_pinned_host_outputs_equal_plain_host_path(jm):
