@@ -91,19 +91,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference(w, sample: int, processes: int, repeats: int = 1):
+def cpu_reference(w, sample: int, pool):
     """The CPU controller (oracle port of main/lib/mpc.py, numpy float64) on `sample` instances of the workload,
-    one instance per call as the scenarios call it, spread over `processes` host processes."""
+    one instance per call as the scenarios call it, spread over the worker processes of `pool` (started by the
+    caller, outside the timed region)."""
     from helpers import oracle_batch
-    idx = list(range(sample))
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        res = oracle_batch(w, idx, processes=processes)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+    t0 = time.perf_counter()
+    res = oracle_batch(w, list(range(sample)), pool=pool)
+    dt = time.perf_counter() - t0
     assert all(r.status == 0 for r in res)
-    return sample / best, best
+    return sample / dt, dt
 
 
 def run_reference(args, rank, world):
@@ -113,13 +110,15 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from junction_mpc import synth
+    from helpers import make_pool
     w = synth.make_workload(args.config, B=args.ref_sample)
     cores = os.cpu_count() or 1
     times = []
-    for k in range(args.warmup + args.steps):
-        rate, dt = cpu_reference(w, args.ref_sample, cores)
-        if k >= args.warmup:
-            times.append(dt)
+    with make_pool(cores) as pool:
+        for k in range(args.warmup + args.steps):
+            rate, dt = cpu_reference(w, args.ref_sample, pool)
+            if k >= args.warmup:
+                times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = args.ref_sample / (ms * 1e-3)
     line = {
@@ -312,8 +311,11 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md"}},
     }
     if world == 1 and not args.no_cpu:
+        from helpers import make_pool
         cores = os.cpu_count() or 1
-        rate, dt = cpu_reference(w, min(args.cpu_sample, B), cores)
+        with make_pool(cores) as pool:
+            cpu_reference(w, min(64, B), pool)                     # warm the workers (imports, BLAS)
+            rate, dt = cpu_reference(w, min(args.cpu_sample, B), pool)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"first {min(args.cpu_sample, B)} instances of the same batch, numpy float64 "
                                           f"oracle (restated main/lib/mpc.py, certified QP solve), one solve per call, "

@@ -43,7 +43,12 @@ def _one(args):
     return r
 
 
-def oracle_batch(w, idx, processes=None, max_iter=1, warm=None):
+def make_pool(processes=None):
+    """A worker pool for oracle_batch(..., pool=...); lets a benchmark keep process start-up out of its timed region."""
+    return get_context("fork").Pool(processes or min(8, os.cpu_count() or 1))
+
+
+def oracle_batch(w, idx, processes=None, max_iter=1, warm=None, pool=None):
     """Oracle results for workload instances `idx` (list of StepResult)."""
     base = default_vector(w)
     jobs = []
@@ -53,6 +58,9 @@ def oracle_batch(w, idx, processes=None, max_iter=1, warm=None):
         wk = True if warm is None else bool(warm[k])
         jobs.append((pv, w["T"], w["state"][k], w["oa"][k], w["od"][k], wk, w["courses"][cid], int(w["course_len"][k]),
                      int(w["target_ind"][k]), max_iter))
+    if pool is not None:
+        n = pool._processes
+        return pool.map(_one, jobs, chunksize=max(1, len(jobs) // (4 * n)))
     processes = processes or min(8, os.cpu_count() or 1)
     if processes == 1 or len(jobs) < 8:
         return [_one(j) for j in jobs]
