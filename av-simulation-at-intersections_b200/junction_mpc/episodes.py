@@ -78,7 +78,7 @@ class BatchedEpisodes:
         _cabi.check(lib.jmpc_episode_post(e._h, self.B, self._p(self.state), self._p(self.course_id), self._p(self.out.record),
                                           self._p(self.params), self._p(self.target_ind), self._p(self.steps),
                                           self._p(self.done), self._p(self.di), self._p(self.warm), self._p(hist),
-                                          float(i * e.dt), stream), "jmpc_episode_post")
+                                          float((i + 1) * e.dt), stream), "jmpc_episode_post")
         if self.obstacles is not None and self.obstacles.shape[1] > 0:
             _cabi.check(lib.jmpc_obstacle_step(e._h, self.B, int(self.obstacles.shape[1]), self._p(self.obstacles),
                                                self._p(self.done), float(e.dt), stream), "jmpc_obstacle_step")
@@ -103,6 +103,8 @@ class BatchedEpisodes:
                    iterations=self.iteration)
         if self.history is not None:
             n = min(self.iteration, self.max_steps)
-            res["history"] = self.history[:n].cpu().numpy()          # [steps, B, 8]: x, y, yaw, v, t, delta, a, xref_dev
+            # [steps, B, 8]: x, y, yaw, v, t, delta, a, xref_dev; row i is what History.store appends after step i
+            # (t = (i + 2) dt: HistorySimulation stores the initial state first, at t = dt; simulation.py:53-61)
+            res["history"] = self.history[:n].cpu().numpy()
             res["flags"] = self.flags[:n].cpu().numpy()
         return res

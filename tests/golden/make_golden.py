@@ -13,6 +13,8 @@ What it does (recipe of SURVEY.md Appendix B):
   * calls the reference's numpy functions on seeded random inputs -> `functions.npz`
     (nearest index, reference sampling, rollout, Jacobians, projector, smooth_yaw, resample_curve,
     obstacle prediction, collision check, cut lookup);
+  * runs four runs of the sensitivity sweep (`mpc_sensitivity_analysis_comulative.py`, `lib.mpc_sensitivity.MPC`)
+    -> `sensitivity_runs.npz` (full History tables);
   * runs the literal `mpc_intersection.py` / `mpc_roundabout.py` loops with
     `lib.mpc._linear_mpc_control` monkey-patched to the oracle QP solve (cvxpy+ECOS cannot be installed
     here; that one function is the only non-reference arithmetic in the loop) and records every step
@@ -318,6 +320,60 @@ def run_episode(kind, courses, max_steps=400):
     return out
 
 
+def run_sensitivity_runs(courses):
+    """mpc_sensitivity_analysis_comulative.py:178-266 for a few parameter values: `lib.mpc_sensitivity.MPC` (no
+    `speed` argument), no obstacles, History recorded by HistorySimulation.  The JSON the reference re-reads in every
+    solve lives in the read-only reference tree, so the values of `reset_config` (:32-51) plus the one parameter
+    under study are handed to the patched QP solve directly."""
+    import lib.mpc_sensitivity as MS
+    from lib.car_dimensions import BicycleModelDimensions
+    from lib.simulation import State, HistorySimulation
+    from lib.trajectories import calc_nearest_index_in_direction
+    from oracle import mpc_oracle as O
+
+    DT = 0.2
+    cd = BicycleModelDimensions(skip_back_circle_collision_checking=False)
+    base = {"NX": 4, "NU": 2, "T": 13, "w_perp": 20.0, "w_para": 1.0, "R": [0.1, 0.01], "Rd": [10, 1.0],
+            "Q_v_yaw": [0.0, 0.5], "Qf": [1.0, 1.0, 0.0, 0.5], "GOAL_DIS": 1.5, "STOP_SPEED": 0.1389, "MAX_TIME": 13.0,
+            "MAX_ITER": 1, "DU_TH": 0.1, "MAX_DSTEER": 30.0, "MAX_ACCEL": 2.0, "MAX_DECEL": -10}
+    out = {}
+    for tag, override in [("default", {}), ("w_para_0p1", {"w_para": 0.1}), ("R_acc_10", {"R": [10, 0.01]}),
+                          ("Rd_steer_0", {"Rd": [10, 0]})]:
+        cfg = dict(base)
+        cfg.update(override)
+        trajectory_full = courses["intersection"].copy()
+        dl = np.linalg.norm(trajectory_full[0, :2] - trajectory_full[1, :2])
+        params = O.Params.from_config(cfg, dl=float(dl), dt=DT, L=cd.distance_back_to_front_wheel, speed=30 / 3.6)
+
+        def qp_patch(xref, xbar, x0, dref, reaches_end, dt, car_dimensions):
+            status, oa, od, ox, oy, oyaw, ov, cost, res = O.linear_mpc_control(params, xref, xbar, x0, reaches_end)
+            assert status == O.STATUS_OPTIMAL
+            return oa, od, ox, oy, oyaw, ov
+
+        MS._linear_mpc_control = qp_patch
+        mpc = MS.MPC(cx=trajectory_full[:, 0], cy=trajectory_full[:, 1], cyaw=trajectory_full[:, 2], dl=dl, dt=DT,
+                     car_dimensions=cd)
+        state = State(x=trajectory_full[0, 0], y=trajectory_full[0, 1], yaw=trajectory_full[0, 2], v=0.0)
+        simulation = HistorySimulation(car_dimensions=cd, sample_time=DT, initial_state=state)
+        traj_agent_idx, tmp_trajectory = 0, None
+        for i in range(600):
+            if mpc.is_goal(state):
+                break
+            if tmp_trajectory is None or np.any(tmp_trajectory[traj_agent_idx, :] != tmp_trajectory[-1, :]):
+                traj_agent_idx = calc_nearest_index_in_direction(state, trajectory_full[:, 0], trajectory_full[:, 1],
+                                                                 start_index=traj_agent_idx, forward=True)
+            tmp_trajectory = trajectory_full            # no obstacles: check_collision_moving_cars returns None
+            mpc.set_trajectory_fromarray(tmp_trajectory)
+            delta, acceleration = mpc.step(state)
+            state = simulation.step(a=acceleration, delta=delta, xref_deviation=mpc.get_current_xref_deviation())
+        h = simulation.history
+        out[tag] = np.array([h.x, h.y, h.yaw, h.v, h.t, h.delta, h.a, h.xref_deviation]).T
+        print(f"sensitivity run {tag}: {len(h.x) - 1} steps, sim time {h.t[-1]:.1f} s")
+    out["config_R"] = np.array(base["R"])
+    out["config_Rd"] = np.array(base["Rd"])
+    return out
+
+
 def main():
     install_shims()
     rng = np.random.default_rng(20261018)
@@ -326,6 +382,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "functions.npz"), **function_vectors(courses, rng))
     for kind in ["intersection", "roundabout"]:
         np.savez_compressed(os.path.join(HERE, f"episode_{kind}.npz"), **run_episode(kind, courses))
+    np.savez_compressed(os.path.join(HERE, "sensitivity_runs.npz"), **run_sensitivity_runs(courses))
 
 
 if __name__ == "__main__":
