@@ -252,7 +252,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
     }
     int idx = 0;
     bool at_end = false;
-    double xr = 0.0, yr = 0.0, psir = 0.0;
+    double xr = 0.0, yr = 0.0, psir = 0.0, vr = 0.0;
     if (lane <= T) {
       const long long hop = (long long)rint(travel / dl);
       long long id = hop + (long long)target;
@@ -261,6 +261,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
       idx = (int)id;
       at_end = (idx == n_course - 1);
       xr = cx[idx]; yr = cy[idx]; psir = cyaw[idx];
+      vr = ((double)idx < P(JMPC_P_V_REF_CUT)) ? P(JMPC_P_V_REF) : 0.0;     // mpc_with_speed.py:104; 0 for lib.mpc
     }
     const unsigned end_mask = __ballot_sync(kFull, at_end);    // bit t = reaches_end[t]
 
@@ -315,11 +316,12 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
         wv = P(JMPC_P_Q_V); wpsi = P(JMPC_P_Q_YAW);
       }
     }
-    const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 /* xref speed row is 0 */, eps = yaw0 - psir;
+    const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 - vr, eps = yaw0 - psir;
     if (lane <= T) {
       M.ca[lane] = ca_t; M.cb[lane] = cb_t; M.cc[lane] = cc_t; M.ck[lane] = ck_t;
       M.W11[lane] = w11; M.W12[lane] = w12; M.W22[lane] = w22; M.qv[lane] = wv; M.qpsi[lane] = wpsi;
       M.WeX[lane] = w11 * ex + w12 * ey; M.WeY[lane] = w12 * ex + w22 * ey; M.epsi[lane] = eps;
+      M.grad[lane] = ev;                 // speed error per stage (grad is free until the solver starts)
     }
     if (lane < T) M.wA[lane] = gk;      // borrow wA for g_k during condensing
     if (lane <= T) { M.vb[lane] = vb; M.th[lane] = th; }       // operating point, reused by the epilogue
@@ -394,7 +396,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
       const double ai = M.ca[k + 1], ci = M.cc[k + 1], bi = M.cb[k + 1], kki = M.ck[k + 1];
       double qa = 0.0, qd = 0.0;
       for (int t = k + 1; t <= T; ++t) {
-        qa += dt * ((M.ca[t] - ai) * M.WeX[t] + (M.cc[t] - ci) * M.WeY[t]) + dt * M.qv[t] * ev;
+        qa += dt * ((M.ca[t] - ai) * M.WeX[t] + (M.cc[t] - ci) * M.WeY[t]) + dt * M.qv[t] * M.grad[t];
         qd += gk * (-(M.cb[t] - bi) * M.WeX[t] + (M.ck[t] - kki) * M.WeY[t]) + gk * M.qpsi[t] * M.epsi[t];
       }
       M.q[k] = 2.0 * qa; M.q[T + k] = 2.0 * qd;
@@ -409,7 +411,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
       // xref / target are still reported, as the reference assigns them before the solve result
       if (lane <= T) {
         double* xo = A.xref + (size_t)b * 4 * T1;
-        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = 0.0; xo[3 * T1 + lane] = psir;
+        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = vr; xo[3 * T1 + lane] = psir;
       }
       if (lane == 0) {
         A.status[b] = status; A.target_ind[b] = target; if (A.iters) A.iters[b] = total_iters;
@@ -631,10 +633,11 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
   const double dt = P(JMPC_P_DT), Lw = P(JMPC_P_L);
   // per-lane data of phase A, re-read instead of being held in registers across the solve
   const int cid = A.course_id ? A.course_id[b] : 0;
-  double xr = 0.0, yr = 0.0, psir = 0.0, vb = 0.0, th = 0.0, w11 = 0.0, w12 = 0.0, w22 = 0.0, wv = 0.0, wpsi = 0.0;
+  double xr = 0.0, yr = 0.0, psir = 0.0, vr = 0.0, vb = 0.0, th = 0.0, w11 = 0.0, w12 = 0.0, w22 = 0.0, wv = 0.0, wpsi = 0.0;
   if (lane <= T) {
     const size_t off = (size_t)cid * A.course_stride + idx;
     xr = A.cx[off]; yr = A.cy[off]; psir = A.cyaw[off];
+    vr = ((double)idx < P(JMPC_P_V_REF_CUT)) ? P(JMPC_P_V_REF) : 0.0;
     vb = M.vb[lane]; th = M.th[lane];
     w11 = M.W11[lane]; w12 = M.W12[lane]; w22 = M.W22[lane]; wv = M.qv[lane]; wpsi = M.qpsi[lane];
   }
@@ -659,7 +662,7 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
       // objective value, evaluated term by term as mpc.py:159-187 writes it
       double cterm = 0.0;
       if (lane >= 1 && lane <= T) {
-        const double dx = xr - X_t, dy = yr - Y_t, dv = 0.0 - v_t, dp = psir - psi_t;
+        const double dx = xr - X_t, dy = yr - Y_t, dv = vr - v_t, dp = psir - psi_t;
         cterm = dx * (w11 * dx + w12 * dy) + dy * (w12 * dx + w22 * dy) + wv * dv * dv + wpsi * dp * dp;
       }
       if (lane < T) {
@@ -674,7 +677,7 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
         A.ox[(size_t)b * T1 + lane] = X_t; A.oy[(size_t)b * T1 + lane] = Y_t;
         A.ov[(size_t)b * T1 + lane] = v_t; A.oyaw[(size_t)b * T1 + lane] = psi_t;
         double* xo = A.xref + (size_t)b * 4 * T1;
-        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = 0.0; xo[3 * T1 + lane] = psir;
+        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = vr; xo[3 * T1 + lane] = psir;
       }
       const double v1 = __shfl_sync(kFull, v_t, 1), yaw1 = __shfl_sync(kFull, psi_t, 1);
       if (lane == 0) {

@@ -22,7 +22,7 @@ import numpy as np
 PARAM_NAMES = (
     "dt", "dl", "L", "speed", "w_perp", "w_para", "R_a", "R_d", "Rd_a", "Rd_d", "Q_v", "Q_yaw",
     "Qf_x", "Qf_y", "Qf_v", "Qf_yaw", "Rend_a", "Rend_d", "max_dsteer", "max_accel", "max_decel",
-    "max_steer", "sim_max_speed", "min_speed", "v_ref_min",
+    "max_steer", "sim_max_speed", "min_speed", "v_ref_min", "v_ref", "v_ref_cut",
 )
 PARAM_INDEX = {k: i for i, k in enumerate(PARAM_NAMES)}
 NPARAM = len(PARAM_NAMES)
@@ -104,7 +104,7 @@ class MPCConfig:
             ("Qf_v", qf[2]), ("Qf_yaw", qf[3]), ("Rend_a", R_END[0]), ("Rend_d", R_END[1]),
             ("max_dsteer", self.max_dsteer), ("max_accel", self.max_accel), ("max_decel", self.max_decel),
             ("max_steer", SIM_MAX_STEER), ("sim_max_speed", SIM_MAX_SPEED), ("min_speed", SIM_MIN_SPEED),
-            ("v_ref_min", V_REF_MIN),
+            ("v_ref_min", V_REF_MIN), ("v_ref", 0.0), ("v_ref_cut", 1e9),
         ]:
             v[PARAM_INDEX[key]] = val
         return v

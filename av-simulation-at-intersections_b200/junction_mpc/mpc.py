@@ -10,7 +10,8 @@ Everything a scenario runner touches keeps its name, signature and types (SURVEY
     mpc.ox, mpc.oy, mpc.xref, mpc.di                                      mpc_intersection.py:301-306
 
 A single ego is a batch of one: `step` runs the same CUDA kernel as `BatchedMPC` through `jmpc_step_host`.
-`install()` registers this module as `lib.mpc` (and the sensitivity flavour as `lib.mpc_sensitivity`) so the
+`install()` registers this module as `lib.mpc` (and the sensitivity / speed-profile flavours as
+`lib.mpc_sensitivity` / `lib.mpc_with_speed`) so the
 reference's scenario scripts run unmodified; see INTEGRATION.md.
 """
 from __future__ import annotations
@@ -108,6 +109,9 @@ class MPC:
         self._engine = self._make_engine(self._cfg_used)
         return n
 
+    def _instance_params(self):
+        return None                        # handle defaults; flavours with per-step parameters override this
+
     # ---- reference interface --------------------------------------------------------------------------------
     def set_trajectory_fromarray(self, trajectory: np.ndarray):
         self.cx = trajectory[:, 0]
@@ -128,7 +132,8 @@ class MPC:
             x0, np.array([self.target_ind], np.int32),
             oa=np.asarray(self.oa, float).reshape(1, Th) if warm else np.zeros((1, Th)),
             od=np.asarray(self.odelta, float).reshape(1, Th) if warm else np.zeros((1, Th)),
-            course_len=np.array([n], np.int32), warm=np.array([1 if warm else 0], np.int32))
+            course_len=np.array([n], np.int32), warm=np.array([1 if warm else 0], np.int32),
+            params=self._instance_params())
         self.status = int(out.status[0])
         self.iterations = int(out.iters[0])
         if self.status == _cabi.STATUS_INDEX_RULE:
@@ -138,7 +143,7 @@ class MPC:
         if self.status == _cabi.STATUS_INFEASIBLE:
             print("Error: Cannot solve mpc...", file=sys.stderr)   # mpc.py:207-209
             self.oa = self.odelta = self.ox = self.oy = self.oyaw = self.ov = None
-            self.ai = MAX_DECEL if not self._reload_config_each_step else self._cfg_used.max_decel
+            self.ai = self._cfg_used.max_decel
             return self.di, self.ai
         self.oa, self.odelta = out.oa[0], out.od[0]
         self.ox, self.oy, self.ov, self.oyaw = out.ox[0], out.oy[0], out.ov[0], out.oyaw[0]
@@ -178,6 +183,48 @@ class _SensitivityMPC(MPC):
     def _load_config(cls) -> MPCConfig:
         path = cls._config_file or os.environ.get("JMPC_CONFIG_SENSITIVITY")
         return MPCConfig.from_json(path) if path else MPCConfig.default()
+
+
+# ---- the speed-profile flavour (main/lib/mpc_with_speed.py) --------------------------------------------------
+_WITH_SPEED_CONFIG = MPCConfig.from_dict({
+    # constants hard-coded at mpc_with_speed.py:16-36 and :161,165 (xy weights 10 / 1)
+    "NX": 4, "NU": 2, "T": 13, "w_perp": 10.0, "w_para": 1.0, "R": [0.01, 0.01], "Rd": [0.01, 1.0],
+    "Q_v_yaw": [20, 0.5], "Qf": [1.0, 1.0, 0.0, 0.5], "GOAL_DIS": 1.5, "STOP_SPEED": 0.5 / 3.6, "MAX_TIME": 13.0,
+    "MAX_ITER": 1, "DU_TH": 0.1, "MAX_DSTEER": 30.0, "MAX_ACCEL": 2.0, "MAX_DECEL": -5})
+WITH_SPEED_MAX_SPEED = 25 / 3.6                     # mpc_with_speed.py:36
+
+
+class _WithSpeedMPC(MPC):
+    """`lib.mpc_with_speed.MPC(cx, cy, cv, cyaw, dl, car_dimensions, dt)`: the reference speed profile `cv` enters
+    xref[2] (mpc_with_speed.py:104) and is tracked with Q_v = 20; `set_trajectory_fromarray(trajectory, cutoff_idx)`
+    rebuilds it as MAX_SPEED before `cutoff_idx` and 0 from there on (:276-282).  The speed cap of the QP is
+    Simulation.MAX_SPEED (:187)."""
+    _config = _WITH_SPEED_CONFIG
+
+    def __init__(self, cx, cy, cv, cyaw, dl, car_dimensions, dt: float = 0.2):
+        super().__init__(cx, cy, cyaw, dl, car_dimensions, speed=SIM_MAX_SPEED, dt=dt)
+        self.cv = cv
+        cv = np.asarray(cv, float)
+        if cv.size and not np.all(cv == cv[0]):
+            raise ValueError("only the reference's two-level speed profiles are supported (constant, or constant "
+                             "up to a cut index as set_trajectory_fromarray builds them)")
+        self._v_ref = float(cv[0]) if cv.size else 0.0
+        self._v_cut = 1e9
+
+    def set_trajectory_fromarray(self, trajectory: np.ndarray, cutoff_idx: int = 999):
+        super().set_trajectory_fromarray(trajectory)
+        self.cv = np.full_like(self.cyaw, WITH_SPEED_MAX_SPEED)
+        self._v_ref, self._v_cut = WITH_SPEED_MAX_SPEED, 1e9
+        if cutoff_idx != 999:
+            self.cv[cutoff_idx:] = 0
+            self._v_cut = float(cutoff_idx)
+
+    def _instance_params(self):
+        from .config import PARAM_INDEX
+        p = self._engine.default_params.copy()
+        p[PARAM_INDEX["v_ref"]] = self._v_ref
+        p[PARAM_INDEX["v_ref_cut"]] = self._v_cut
+        return p[None, :]
 
 
 def _module_from(cls, cfg: MPCConfig, name: str) -> types.ModuleType:
@@ -224,12 +271,17 @@ def install(reference_main: Optional[str] = None) -> None:
     sys.modules["lib.mpc"] = _module_from(_MPC, cfg, "lib.mpc")
     sens_cfg = MPCConfig.from_json(sens_cfg_path) if sens_cfg_path else cfg
     sys.modules["lib.mpc_sensitivity"] = _module_from(_SMPC, sens_cfg, "lib.mpc_sensitivity")
+    ws = _module_from(_WithSpeedMPC, _WITH_SPEED_CONFIG, "lib.mpc_with_speed")
+    ws.MAX_SPEED = WITH_SPEED_MAX_SPEED
+    ws.MPC = type("MPC", (_WithSpeedMPC,), {})
+    sys.modules["lib.mpc_with_speed"] = ws
     try:                                   # `import lib.mpc` also needs the attribute on the package
         import lib                         # the reference's package, when reference_main is on sys.path
         lib.mpc = sys.modules["lib.mpc"]
         lib.mpc_sensitivity = sys.modules["lib.mpc_sensitivity"]
+        lib.mpc_with_speed = ws
     except ImportError:
         pkg = types.ModuleType("lib")
         pkg.__path__ = []
-        pkg.mpc, pkg.mpc_sensitivity = sys.modules["lib.mpc"], sys.modules["lib.mpc_sensitivity"]
+        pkg.mpc, pkg.mpc_sensitivity, pkg.mpc_with_speed = sys.modules["lib.mpc"], sys.modules["lib.mpc_sensitivity"], ws
         sys.modules["lib"] = pkg

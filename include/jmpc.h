@@ -57,6 +57,9 @@ enum jmpc_param {
   JMPC_P_SIM_MAX_SPEED, /* Simulation.MAX_SPEED (rollout clamp, not the QP cap)        simulation.py:24 */
   JMPC_P_MIN_SPEED,     /* Simulation.MIN_SPEED                                        simulation.py:25 */
   JMPC_P_V_REF_MIN,     /* 10/3.6: floor of the reference-sampling speed                     mpc.py:99 */
+  JMPC_P_V_REF,         /* reference speed profile, main/lib/mpc_with_speed.py:104,280-282: xref[2, t] = V_REF     */
+  JMPC_P_V_REF_CUT,     /*   while the sampled course index is < V_REF_CUT, 0 beyond it (cv[cutoff_idx:] = 0);      */
+                        /*   defaults 0 and 1e9 reproduce lib.mpc, whose xref speed row is always 0 (mpc.py:107)    */
   JMPC_NPARAM
 };
 

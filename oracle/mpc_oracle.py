@@ -48,6 +48,8 @@ class Params:
     sim_max_speed: float = 30.0 / 3.6                # simulation.py:24 (rollout clamp, NOT `speed`)
     min_speed: float = -5.0                          # simulation.py:25
     v_ref_min: float = 10.0 / 3.6                    # mpc.py:99
+    v_ref: float = 0.0                               # speed profile of mpc_with_speed.py:104,280-282: xref[2] = v_ref
+    v_ref_cut: float = 1e9                           #   for course indices < v_ref_cut, 0 beyond (lib.mpc: always 0)
     goal_dis: float = 1.5
     stop_speed: float = 0.1389
     max_iter: int = 1
@@ -134,7 +136,8 @@ def ref_trajectory(p: Params, x: float, y: float, v: float, cx, cy, cyaw, start:
     xref = np.zeros((4, p.T + 1))
     xref[0] = cx[idx]
     xref[1] = cy[idx]
-    xref[3] = cyaw[idx]                                   # row 2 (speed) stays 0: never tracked
+    xref[3] = cyaw[idx]
+    xref[2] = np.where(idx < p.v_ref_cut, p.v_ref, 0.0)   # 0 in lib.mpc (never tracked); cv[idx] in mpc_with_speed
     reaches_end = idx == n_course - 1
     return xref, int(start), reaches_end
 

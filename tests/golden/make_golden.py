@@ -15,6 +15,7 @@ What it does (recipe of SURVEY.md Appendix B):
     obstacle prediction, collision check, cut lookup);
   * runs four runs of the sensitivity sweep (`mpc_sensitivity_analysis_comulative.py`, `lib.mpc_sensitivity.MPC`)
     -> `sensitivity_runs.npz` (full History tables);
+  * runs the `mpc_intersection_new_ref.py` loop with `lib.mpc_with_speed.MPC` -> `episode_new_ref.npz`;
   * runs the literal `mpc_intersection.py` / `mpc_roundabout.py` loops with
     `lib.mpc._linear_mpc_control` monkey-patched to the oracle QP solve (cvxpy+ECOS cannot be installed
     here; that one function is the only non-reference arithmetic in the loop) and records every step
@@ -374,6 +375,108 @@ def run_sensitivity_runs(courses):
     return out
 
 
+def run_new_ref_episode(courses, max_steps=400):
+    """main/scenarios/mpc_intersection_new_ref.py:62-160 with `lib.mpc_with_speed.MPC` (speed profile cv in xref[2],
+    Q_v_yaw = diag(20, .5), w = 10 / 1, MAX_DECEL = -5): the course is never truncated, the cut index only zeroes
+    the speed profile behind it."""
+    import lib.mpc_with_speed as MW
+    from lib.car_dimensions import BicycleModelDimensions
+    from lib.simulation import State, Simulation, HistorySimulation
+    from lib.trajectories import calc_nearest_index_in_direction, resample_curve
+    from lib.collision_avoidance import check_collision_moving_cars, get_cutoff_curve_by_position_idx
+    from lib.moving_obstacles import MovingObstacleTIntersection
+    from lib.moving_obstacles_prediction import MovingObstaclesPrediction
+    from oracle import mpc_oracle as O
+
+    DT = 0.2
+    cd = BicycleModelDimensions(skip_back_circle_collision_checking=False)
+    trajectory_full = courses["intersection"].copy()
+    obstacles = [MovingObstacleTIntersection(cd, direction=1, offset=1., turning=False, speed=25 / 3.6, dt=DT),
+                 MovingObstacleTIntersection(cd, direction=-1, offset=4., turning=True, speed=25 / 3.6, dt=DT)]
+    dl = np.linalg.norm(trajectory_full[0, :2] - trajectory_full[1, :2])
+    params = O.Params(T=MW.T, dt=DT, dl=float(dl), L=cd.distance_back_to_front_wheel, speed=Simulation.MAX_SPEED,
+                      w_perp=10.0, w_para=1.0, R=(0.01, 0.01), Rd=(0.01, 1.0), Q_v_yaw=(20.0, 0.5),
+                      Qf=(1.0 * MW.T, 1.0 * MW.T, 0.0, 0.5 * MW.T), max_decel=float(MW.MAX_DECEL),
+                      max_accel=float(MW.MAX_ACCEL), max_dsteer=float(MW.MAX_DSTEER))
+    log = {k: [] for k in ["state", "target_in", "warm", "oa_in", "od_in", "agent_idx", "obs", "flag", "cutoff",
+                           "target_out", "xref", "oa", "od", "ox", "oy", "ov", "oyaw", "cost", "di", "ai", "dev"]}
+    cur = {}
+
+    def qp_patch(xref, xbar, x0, dref, reaches_end, dt, car_dimensions):
+        status, oa, od, ox, oy, oyaw, ov, cost, res = O.linear_mpc_control(params, xref, xbar, x0, reaches_end)
+        assert status == O.STATUS_OPTIMAL
+        cur.update(xref=xref.copy(), cost=cost)
+        return oa, od, ox, oy, oyaw, ov
+
+    MW._linear_mpc_control = qp_patch
+    cv = np.full(trajectory_full[:, 1].shape, 30 / 3.6)
+    mpc = MW.MPC(cx=trajectory_full[:, 0], cy=trajectory_full[:, 1], cv=cv, cyaw=trajectory_full[:, 2], dl=dl, dt=DT,
+                 car_dimensions=cd)
+    state = State(x=trajectory_full[0, 0], y=trajectory_full[0, 1], yaw=trajectory_full[0, 2], v=0.0)
+    simulation = HistorySimulation(car_dimensions=cd, sample_time=DT, initial_state=state)
+    FRAME_WINDOW = 20
+    EXTRA_CUTOFF_MARGIN = 4 * int(math.ceil(cd.radius / dl))
+    traj_agent_idx, tmp_trajectory = 0, None
+    for i in range(max_steps):
+        if mpc.is_goal(state):
+            break
+        if tmp_trajectory is None or np.any(tmp_trajectory[traj_agent_idx, :] != tmp_trajectory[-1, :]):
+            traj_agent_idx = calc_nearest_index_in_direction(state, trajectory_full[:, 0], trajectory_full[:, 1],
+                                                             start_index=traj_agent_idx, forward=True)
+        trajectory_res = trajectory = trajectory_full[traj_agent_idx:]
+        if state.v < Simulation.MAX_SPEED:
+            resample_dl = np.zeros((trajectory_res.shape[0],)) + MW.MAX_ACCEL
+            resample_dl = np.cumsum(resample_dl) + state.v
+            resample_dl = DT * np.minimum(resample_dl, Simulation.MAX_SPEED)
+            trajectory_res = resample_curve(trajectory_res, dl=resample_dl)
+        else:
+            trajectory_res = resample_curve(trajectory_res, dl=DT * Simulation.MAX_SPEED)
+        obs_now = [list(o.get()) for o in obstacles]
+        trajs = [np.vstack(MovingObstaclesPrediction(*o, sample_time=DT, car_dimensions=cd).state_prediction(7.)).T
+                 for o in obs_now]
+        collision_xy = check_collision_moving_cars(cd, trajectory_res, trajectory, trajs, frame_window=FRAME_WINDOW)
+        cutoff_idx = 999
+        if collision_xy is not None:
+            cutoff_idx = get_cutoff_curve_by_position_idx(trajectory_full, collision_xy[0],
+                                                          collision_xy[1]) - EXTRA_CUTOFF_MARGIN
+            cutoff_idx = max(traj_agent_idx + 1, cutoff_idx)
+        tmp_trajectory = trajectory_full
+        mpc.set_trajectory_fromarray(tmp_trajectory, cutoff_idx=cutoff_idx)
+        log["state"].append([state.x, state.y, state.v, state.yaw])
+        log["target_in"].append(mpc.target_ind)
+        log["warm"].append(0 if mpc.oa is None else 1)
+        log["oa_in"].append(np.zeros(MW.T) if mpc.oa is None else np.array(mpc.oa))
+        log["od_in"].append(np.zeros(MW.T) if mpc.odelta is None else np.array(mpc.odelta))
+        log["agent_idx"].append(traj_agent_idx)
+        log["obs"].append(obs_now)
+        log["flag"].append(0 if collision_xy is None else 1)
+        log["cutoff"].append(cutoff_idx)
+        delta, acceleration = mpc.step(state)
+        log["xref"].append(cur["xref"])
+        log["cost"].append(cur["cost"])
+        log["target_out"].append(mpc.target_ind)
+        for k, v in [("oa", mpc.oa), ("od", mpc.odelta), ("ox", mpc.ox), ("oy", mpc.oy), ("ov", mpc.ov),
+                     ("oyaw", mpc.oyaw)]:
+            log[k].append(np.array(v))
+        log["di"].append(delta)
+        log["ai"].append(acceleration)
+        dev = mpc.get_current_xref_deviation()
+        log["dev"].append(dev)
+        for o in obstacles:
+            o.step()
+        state = simulation.step(a=acceleration, delta=delta, xref_deviation=dev)
+    out = {k: np.array(v) for k, v in log.items()}
+    out["final_state"] = np.array([state.x, state.y, state.v, state.yaw])
+    out["dl"] = np.array(dl)
+    out["margin"] = np.array(EXTRA_CUTOFF_MARGIN)
+    out["frame_window"] = np.array(FRAME_WINDOW)
+    out["v_profile"] = np.array(MW.MAX_SPEED)
+    out["course_smoothed"] = trajectory_full
+    print(f"episode new_ref (mpc_with_speed): {len(out['state'])} steps, collision flag on {int(out['flag'].sum())}, "
+          f"max speed {out['state'][:, 2].max():.3f}")
+    return out
+
+
 def main():
     install_shims()
     rng = np.random.default_rng(20261018)
@@ -383,6 +486,7 @@ def main():
     for kind in ["intersection", "roundabout"]:
         np.savez_compressed(os.path.join(HERE, f"episode_{kind}.npz"), **run_episode(kind, courses))
     np.savez_compressed(os.path.join(HERE, "sensitivity_runs.npz"), **run_sensitivity_runs(courses))
+    np.savez_compressed(os.path.join(HERE, "episode_new_ref.npz"), **run_new_ref_episode(courses))
 
 
 if __name__ == "__main__":

@@ -26,7 +26,8 @@ def params_from_vector(v, T, max_iter=1):
         R_end=(float(v[PI["Rend_a"]]), float(v[PI["Rend_d"]])), max_dsteer=float(v[PI["max_dsteer"]]),
         max_accel=float(v[PI["max_accel"]]), max_decel=float(v[PI["max_decel"]]), max_steer=float(v[PI["max_steer"]]),
         sim_max_speed=float(v[PI["sim_max_speed"]]), min_speed=float(v[PI["min_speed"]]),
-        v_ref_min=float(v[PI["v_ref_min"]]), max_iter=max_iter)
+        v_ref_min=float(v[PI["v_ref_min"]]), v_ref=float(v[PI["v_ref"]]), v_ref_cut=float(v[PI["v_ref_cut"]]),
+        max_iter=max_iter)
 
 
 def default_vector(w, cfg=None):

@@ -74,5 +74,6 @@ def test_workloads_are_seeded_and_valid():
         n = a["course_len"][k]
         O.nearest_index_forward(a["state"][k, 0], a["state"][k, 1], c[:n, 0], c[:n, 1], int(a["target_ind"][k]))
     s = synth.make_sweep(8, states_per_point=2, max_points=16)
-    assert s["params"].shape == (32, 25) and s["B"] == 32
+    from junction_mpc.config import NPARAM
+    assert s["params"].shape == (32, NPARAM) and s["B"] == 32
     assert len(np.unique(s["params"], axis=0)) == 16

@@ -101,3 +101,44 @@ def test_infeasible_single_instance_matches_reference_failure_path(capsys):
     assert "Cannot solve mpc" in capsys.readouterr().err
     di, ai = mpc.step(State(x=c[10, 0], y=c[10, 1], yaw=c[10, 2], v=4.0))      # recovers with a cold start
     assert mpc.oa is not None and len(mpc.oa) == 13
+
+
+def test_speed_profile_flavour_retraces_reference_episode(golden_dir):
+    """`lib.mpc_with_speed.MPC` in the loop of mpc_intersection_new_ref.py."""
+    import __graft_entry__ as g
+    g.build()
+    from junction_mpc import mpc as M
+    e = np.load(os.path.join(golden_dir, "episode_new_ref.npz"))
+    raw = np.load(os.path.join(golden_dir, "courses.npz"))["intersection"]
+    trajectory_full = raw.copy()
+    dl = np.linalg.norm(trajectory_full[0, :2] - trajectory_full[1, :2])
+    cv = np.full(trajectory_full[:, 1].shape, 30 / 3.6)
+    mpc = M._WithSpeedMPC(cx=trajectory_full[:, 0], cy=trajectory_full[:, 1], cv=cv, cyaw=trajectory_full[:, 2], dl=dl,
+                          dt=0.2, car_dimensions=Car())
+    geo = C.CarGeometry()
+    p = O.Params(dl=float(dl))
+    margin, fw = int(e["margin"]), int(e["frame_window"])
+    state = State(x=trajectory_full[0, 0], y=trajectory_full[0, 1], yaw=trajectory_full[0, 2], v=0.0)
+    agent_idx, steps = 0, 0
+    for i in range(400):
+        if mpc.is_goal(state):
+            break
+        # the course is never truncated in this scenario, so the index update always runs
+        agent_idx = O.nearest_index_forward(state.x, state.y, trajectory_full[:, 0], trajectory_full[:, 1], agent_idx)
+        flag, cut = C.collision_cut(geo, trajectory_full, agent_idx, state.v, e["obs"][i], dt=0.2, frame_window=fw,
+                                    max_accel=2.0, max_speed=30 / 3.6, margin=margin)
+        cutoff = cut if flag else 999
+        assert int(flag) == e["flag"][i] and cutoff == e["cutoff"][i], i
+        mpc.set_trajectory_fromarray(trajectory_full, cutoff_idx=cutoff)
+        np.testing.assert_allclose([state.x, state.y, state.v, state.yaw], e["state"][i], rtol=0, atol=1e-6)
+        delta, acc = mpc.step(state)
+        assert np.array_equal(mpc.xref, e["xref"][i])                 # includes the speed row cv[idx]
+        assert abs(delta - e["di"][i]) <= 1e-4 + 1e-3 * abs(e["di"][i])
+        assert abs(acc - e["ai"][i]) <= 1e-4 + 1e-3 * abs(e["ai"][i])
+        assert abs(mpc.cost - e["cost"][i]) <= 1e-4 * abs(e["cost"][i])
+        steps += 1
+        x, y, v, yaw = O.plant_step(p, (state.x, state.y, state.v, state.yaw), acc, delta)
+        state = State(x=x, y=y, yaw=yaw, v=v)
+    assert steps == len(e["state"]) == 88
+    np.testing.assert_allclose([state.x, state.y, state.v, state.yaw], e["final_state"], rtol=0, atol=1e-5)
+    assert e["xref"][:, 2].max() == 25 / 3.6 and (e["xref"][:, 2] == 0).any()      # both levels of the profile occur
