@@ -1,5 +1,5 @@
 """IPM variants on cached condensed instances: separate step lengths, step fraction, initial point."""
-import sys; sys.path.insert(0,'/root/repo/scratch')
+import sys; sys.path.insert(0,'/root/repo/tests/tools/prototypes')
 from proto import *
 import pickle
 from oracle.condensed_model import _rows_apply, _rows_apply_T, _assemble_K

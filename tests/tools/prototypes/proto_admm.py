@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0,'/root/repo/scratch')
+import sys; sys.path.insert(0,'/root/repo/tests/tools/prototypes')
 from proto import *
 
 def ruiz(P,A,iters=10):

@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0,'/root/repo/scratch')
+import sys; sys.path.insert(0,'/root/repo/tests/tools/prototypes')
 from proto import *
 from multiprocessing import Pool
 def work(args):
