@@ -730,7 +730,10 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, doub
 
 // Persistent kernel: every resident warp pulls instances from a global counter.
 template <int TT>
-__global__ void __launch_bounds__(128, 4) mpc_step_kernel(const StepArgs A) {
+#ifndef JMPC_MINBLOCKS
+#define JMPC_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const StepArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
