@@ -55,6 +55,10 @@ struct jmpc_handle_s {
   char* h_stage = nullptr; size_t h_stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
   long long launches = 0;
+  // fused all-gather targets (jmpc_set_record_peers)
+  double* peer_rec[JMPC_MAX_PEERS] = {};
+  int n_peers = 0;
+  long long rank_offset = 0;
 };
 
 namespace {
@@ -314,6 +318,8 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
   memcpy(a.defaults, h->defaults, sizeof a.defaults);
   a.target_ind = target_ind; a.oa = oa; a.od = od; a.ox = ox; a.oy = oy; a.ov = ov; a.oyaw = oyaw; a.xref = xref;
   a.cost = cost; a.status = status; a.iters = iters; a.record = record;
+  a.n_peers = h->n_peers; a.rank_offset = h->rank_offset;
+  for (int p = 0; p < JMPC_MAX_PEERS; ++p) a.peer_rec[p] = h->peer_rec[p];
   a.pscratch = h->d_pscratch; a.counter = h->d_counter;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
   step_kernel_for(T)<<<g.blocks, g.threads, g.smem, s>>>(a);
@@ -342,6 +348,16 @@ bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 }  // namespace
+
+int32_t jmpc_set_record_peers(jmpc_handle h, int32_t n_peers, const uint64_t* peer_tables, int64_t rank_offset) {
+  if (!h) return fail("jmpc_set_record_peers: NULL handle");
+  if (n_peers < 0 || n_peers > JMPC_MAX_PEERS) return fail("jmpc_set_record_peers: n_peers out of range");
+  if (n_peers > 0 && !peer_tables) return fail("jmpc_set_record_peers: NULL table list");
+  if (rank_offset < 0) return fail("jmpc_set_record_peers: negative rank_offset");
+  for (int p = 0; p < JMPC_MAX_PEERS; ++p) h->peer_rec[p] = (p < n_peers) ? reinterpret_cast<double*>(peer_tables[p]) : nullptr;
+  h->n_peers = n_peers; h->rank_offset = rank_offset;
+  return 0;
+}
 
 int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,

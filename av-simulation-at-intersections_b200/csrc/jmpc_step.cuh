@@ -43,6 +43,12 @@ struct StepArgs {
   int* target_ind; double* oa; double* od;
   double* ox; double* oy; double* ov; double* oyaw; double* xref; double* cost; int* status; int* iters;
   double* record;           // [B][JMPC_RECORD_LEN] or nullptr
+  // fused all-gather: the epilogue also stores the record into every peer GPU's gathered table (NVLink peer
+  // memory, jmpc_set_record_peers); peer p's table is [world * B][JMPC_RECORD_LEN], this rank owns rows
+  // rank_offset .. rank_offset + B - 1
+  double* peer_rec[JMPC_MAX_PEERS];
+  int n_peers;
+  long long rank_offset;
   // scratch
   double* pscratch;         // [resident warps][tiles_doubles(n)] condensed Hessian on tiles, L2 resident
   unsigned int* counter;    // dynamic work queue
@@ -98,6 +104,21 @@ __device__ __forceinline__ double warp_rscan(double v, int lane) {
     if (lane + o < 32) v += t;
   }
   return v;
+}
+
+// Lane 0 writes the instance's result record locally and, when peers are set, into every peer's gathered table
+// (one 64-byte store each; with NVSwitch every peer is one hop away, and the stores are the only communication of
+// the whole step -- the all-gather is fused into the solve kernel's epilogue).
+__device__ __forceinline__ void write_record(const StepArgs& A, int b, double r0, double r1, double r2, double r3,
+                                             double r4, double r5, double r6, double r7) {
+  if (A.record) {
+    double2* rec = reinterpret_cast<double2*>(A.record + (size_t)b * JMPC_RECORD_LEN);
+    rec[0] = make_double2(r0, r1); rec[1] = make_double2(r2, r3); rec[2] = make_double2(r4, r5); rec[3] = make_double2(r6, r7);
+  }
+  for (int p = 0; p < A.n_peers; ++p) {
+    double2* rec = reinterpret_cast<double2*>(A.peer_rec[p] + ((size_t)A.rank_offset + b) * JMPC_RECORD_LEN);
+    rec[0] = make_double2(r0, r1); rec[1] = make_double2(r2, r3); rec[2] = make_double2(r4, r5); rec[3] = make_double2(r6, r7);
+  }
 }
 
 // ---- candidate list for the 3-nearest rule: ascending by (d2, index) --------------------------------
@@ -227,11 +248,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
     if (near < 0) {
       if (lane == 0) {
         A.status[b] = JMPC_INDEX_RULE; if (A.iters) A.iters[b] = total_iters;
-        if (A.record) {
-          double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
-          rec[0] = nan(""); rec[1] = nan(""); rec[2] = nan(""); rec[3] = JMPC_INDEX_RULE; rec[4] = A.target_ind[b];
-          rec[5] = total_iters; rec[6] = nan(""); rec[7] = nan("");
-        }
+        write_record(A, b, nan(""), nan(""), nan(""), JMPC_INDEX_RULE, A.target_ind[b], total_iters, nan(""), nan(""));
       }
       return JMPC_INDEX_RULE;
     }
@@ -416,11 +433,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
       if (lane == 0) {
         A.status[b] = status; A.target_ind[b] = target; if (A.iters) A.iters[b] = total_iters;
         A.cost[b] = nan("");
-        if (A.record) {
-          double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
-          rec[0] = nan(""); rec[1] = P(JMPC_P_MAX_DECEL); rec[2] = nan(""); rec[3] = status; rec[4] = target;
-          rec[5] = total_iters; rec[6] = nan(""); rec[7] = nan("");
-        }
+        write_record(A, b, nan(""), P(JMPC_P_MAX_DECEL), nan(""), status, target, total_iters, nan(""), nan(""));
       }
       return JMPC_INFEASIBLE;
     }
@@ -683,14 +696,11 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
       if (lane == 0) {
         A.cost[b] = cost; A.status[b] = status; A.target_ind[b] = target;
         if (A.iters) A.iters[b] = total_iters;
-        if (A.record) {
-          double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
-          rec[0] = d_sol; rec[1] = a_sol; rec[2] = cost; rec[3] = status; rec[4] = target; rec[5] = total_iters;
-          rec[6] = v1; rec[7] = yaw1;
 #ifdef JMPC_DEBUG_RESID
-          rec[0] = M.prm[29]; rec[6] = M.prm[30]; rec[7] = M.prm[31];
+        write_record(A, b, M.prm[29], a_sol, cost, status, target, total_iters, M.prm[30], M.prm[31]);
+#else
+        write_record(A, b, d_sol, a_sol, cost, status, target, total_iters, v1, yaw1);
 #endif
-        }
       }
     } else {
       // feed the solution back as the next linearisation point (mpc.py:231-236)

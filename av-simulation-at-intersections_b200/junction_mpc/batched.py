@@ -104,6 +104,15 @@ class BatchedMPC:
         _cabi.check(self._lib.jmpc_set_car_geometry(self._h, float(front_offset), float(rear_offset), float(radius)),
                     "jmpc_set_car_geometry")
 
+    def set_record_peers(self, peer_table_ptrs, rank_offset: int):
+        """Fused all-gather: from now on the step kernel's epilogue also stores every instance's result record into
+        row `rank_offset + b` of each peer GPU's gathered table.  `peer_table_ptrs`: device pointers (ints) of the
+        [world * B, RECORD_LEN] tables of all ranks as seen from this GPU (symmetric memory `buffer_ptrs`); an empty
+        list switches it off."""
+        ptrs = (C.c_uint64 * max(len(peer_table_ptrs), 1))(*[int(p) for p in peer_table_ptrs])
+        _cabi.check(self._lib.jmpc_set_record_peers(self._h, len(peer_table_ptrs), ptrs, int(rank_offset)),
+                    "jmpc_set_record_peers")
+
     def close(self):
         if getattr(self, "_h", None):
             self._host_out = {}

@@ -48,6 +48,43 @@ def allgather_records(local, B: Optional[int] = None, group=None):
     return torch.cat([buf[r * m:r * m + sizes[r]] for r in range(world)], 0)
 
 
+class FusedRecordGather:
+    """All-gather of the result records fused into the step kernel (no collective call on the data path).
+
+    Every rank allocates the gathered table [world * B, RECORD_LEN] in symmetric memory; after the rendezvous each
+    GPU holds NVLink peer pointers to all tables, and `BatchedMPC.set_record_peers` makes the step kernel's epilogue
+    store each instance's record straight into row `rank * B + b` of every table.  What is left after the launch is
+    a cross-GPU barrier (symmetric-memory signal pads) so that readers see the peers' stores."""
+
+    def __init__(self, engine, B_local: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _cabi
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("fused record gather addresses the GPUs of one NVSwitch box (<= 8)")
+        dev = torch.device("cuda", engine.device)
+        self.table = symm_mem.empty(self.world * B_local, _cabi.RECORD_LEN, dtype=torch.float64, device=dev)
+        self.table.zero_()
+        self.handle = symm_mem.rendezvous(self.table, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric-memory rendezvous returned no peer pointers")
+        self.engine = engine
+        engine.set_record_peers(ptrs, self.rank * B_local)
+
+    def finish(self):
+        """Call after `engine.step(...)` (same stream): returns the gathered table, valid once the stream has passed
+        the barrier."""
+        self.handle.barrier(channel=0)
+        return self.table
+
+    def close(self):
+        self.engine.set_record_peers([], 0)
+
+
 class ShardedMPC:
     """Runs this rank's slice of a global batch and gathers the result records.
 

@@ -188,13 +188,30 @@ def main():
     out = mpc.alloc_outputs(B)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
+    # multi-GPU gather of the result records: fused into the kernel epilogue over NVLink peer memory when symmetric
+    # memory is available, otherwise one NCCL all-gather straight from the kernel's record buffer
+    fused, gather_kind = None, "none (single GPU)"
+    if world > 1:
+        gather_kind = "nccl all_gather_into_tensor of the record buffer"
+        if os.environ.get("JMPC_NO_FUSED_GATHER") is None:
+            try:
+                from junction_mpc.distributed import FusedRecordGather
+                fused = FusedRecordGather(mpc, B)
+                gather_kind = "fused: step-kernel epilogue stores into every peer's table (NVLink symmetric memory) + signal-pad barrier"
+            except Exception as exc:            # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] fused gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                fused = None
+
     def one_step(e0=None, e1=None):
         flush.zero_()
         tgt.copy_(tgt0); oa.copy_(oa0); od.copy_(od0)
         if e0 is not None:
             e0.record()
         mpc.step(state, tgt, oa, od, out, course_len=clen)
-        if world > 1:
+        if fused is not None:
+            fused.finish()                     # cross-GPU barrier; the records are already in every peer's table
+        elif world > 1:
             allgather_records(out.record)      # [world * B, 8] on every rank, straight from the kernel's buffer
         if e1 is not None:
             e1.record()
@@ -202,6 +219,11 @@ def main():
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
+    if fused is not None:                      # the fused table must equal what the NCCL all-gather delivers
+        ref = allgather_records(out.record)
+        torch.cuda.synchronize()
+        same = torch.equal(torch.nan_to_num(fused.table, nan=-1.0), torch.nan_to_num(ref, nan=-1.0))
+        assert same, "fused record gather differs from the NCCL all-gather"
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -290,7 +312,7 @@ def main():
                                f"(BASELINE.json configs[{args.config - 1}])", "instances_per_gpu": B, "T": T,
                    "l2": "flushed with a 256 MiB write before every timed step",
                    "solver": "condensed QP, Mehrotra predictor-corrector interior point, fp64",
-                   "mean_solver_iters": mean_iters, "max_solver_iters": int(iters.max())},
+                   "mean_solver_iters": mean_iters, "max_solver_iters": int(iters.max()), "gather": gather_kind},
         "p50_ms": float(np.percentile(per_step, 50)), "p99_ms": float(np.percentile(per_step, 99)),
         "single_instance_step_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                     "api": "step_host, B=1, host in / host out"},

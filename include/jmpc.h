@@ -36,6 +36,7 @@ extern "C" {
 
 #define JMPC_ABI_VERSION 1
 #define JMPC_RECORD_LEN 8         /* doubles per instance in the packed result record, see jmpc_step */
+#define JMPC_MAX_PEERS 8          /* GPUs of one NVSwitch box */
 #define JMPC_MAX_T 31           /* horizon limit of the warp-per-instance kernels (reference GUI range 5..25) */
 
 /* Row order of a parameter vector.  Derivations as in main/lib/mpc.py:14-39 and main/lib/simulation.py:23-25:
@@ -125,6 +126,14 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
                   const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa, double* od,
                   const double* params, double* ox, double* oy, double* ov, double* oyaw, double* xref,
                   double* cost, int32_t* status, int32_t* iters, double* record, void* stream);
+
+/* Fused all-gather of the result records (multi-GPU): after this call every jmpc_step on the handle also stores each
+ * instance's record into row `rank_offset + b` of every table in `peer_tables` (DEVICE pointers valid on this GPU
+ * for all `n_peers` ranks including this one -- NVLink peer / symmetric memory, e.g. the `buffer_ptrs` of a
+ * torch.distributed._symmetric_memory rendezvous).  Each table is [world * B][JMPC_RECORD_LEN].  The stores are
+ * issued by the step kernel's epilogue; the caller only has to run a cross-GPU barrier before reading the
+ * tables.  n_peers = 0 switches it off. */
+int32_t jmpc_set_record_peers(jmpc_handle h, int32_t n_peers, const uint64_t* peer_tables, int64_t rank_offset);
 
 /* Same with HOST pointers: copies in, runs, copies out, synchronises. */
 int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,

@@ -237,3 +237,23 @@ def test_pinned_host_outputs_equal_plain_host_path(jm):
     # the packed record is what the multi-GPU all-gather ships
     assert np.array_equal(got.record[:, 0], got.od[:, 0]) and np.array_equal(got.record[:, 1], got.oa[:, 0])
     assert np.array_equal(got.record[:, 3], got.status) and np.array_equal(got.record[:, 4], got.target_ind)
+
+
+def test_fused_record_stores_reach_the_peer_tables(jm):
+    """The kernel-epilogue all-gather on one GPU: two 'peer' tables that both live on this device."""
+    import torch
+    synth, BatchedMPC = jm
+    w = synth.make_workload(2, B=200)
+    mpc, host = _run(BatchedMPC, w)
+    dev = torch.device("cuda", 0)
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)  # noqa: E731
+    tables = [torch.full((3 * 200, 8), -7.0, dtype=torch.float64, device=dev) for _ in range(2)]
+    mpc.set_record_peers([tb.data_ptr() for tb in tables], 200)          # this "rank" owns rows 200..399
+    out = mpc.step(t(w["state"], torch.float64), t(w["target_ind"], torch.int32), t(w["oa"], torch.float64),
+                   t(w["od"], torch.float64), mpc.alloc_outputs(200), course_len=t(w["course_len"], torch.int32))
+    torch.cuda.synchronize()
+    for tb in tables:
+        got = tb.cpu().numpy()
+        assert np.array_equal(got[200:400], host.record) and np.array_equal(got[200:400], out.record.cpu().numpy())
+        assert (got[:200] == -7.0).all() and (got[400:] == -7.0).all()
+    mpc.set_record_peers([], 0)
