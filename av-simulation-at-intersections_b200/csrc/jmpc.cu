@@ -59,6 +59,8 @@ struct jmpc_handle_s {
   double* peer_rec[JMPC_MAX_PEERS] = {};
   int n_peers = 0;
   long long rank_offset = 0;
+  bool collision_attr_set = false;
+  const int* skip = nullptr;           // jmpc_set_skip_mask
 };
 
 namespace {
@@ -318,7 +320,7 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
   memcpy(a.defaults, h->defaults, sizeof a.defaults);
   a.target_ind = target_ind; a.oa = oa; a.od = od; a.ox = ox; a.oy = oy; a.ov = ov; a.oyaw = oyaw; a.xref = xref;
   a.cost = cost; a.status = status; a.iters = iters; a.record = record;
-  a.n_peers = h->n_peers; a.rank_offset = h->rank_offset;
+  a.n_peers = h->n_peers; a.rank_offset = h->rank_offset; a.skip = h->skip;
   for (int p = 0; p < JMPC_MAX_PEERS; ++p) a.peer_rec[p] = h->peer_rec[p];
   a.pscratch = h->d_pscratch; a.counter = h->d_counter;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
@@ -348,6 +350,12 @@ bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 }  // namespace
+
+int32_t jmpc_set_skip_mask(jmpc_handle h, const int32_t* skip) {
+  if (!h) return fail("jmpc_set_skip_mask: NULL handle");
+  h->skip = skip;
+  return 0;
+}
 
 int32_t jmpc_set_record_peers(jmpc_handle h, int32_t n_peers, const uint64_t* peer_tables, int64_t rank_offset) {
   if (!h) return fail("jmpc_set_record_peers: NULL handle");
@@ -458,14 +466,13 @@ int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const
   a.obstacles = obstacles; a.n_obs = n_obs; a.frame_window = frame_window; a.margin = margin;
   a.horizon_s = horizon_s; a.params = params;
   memcpy(a.defaults.v, h->defaults, sizeof h->defaults);
-  a.flag = flag; a.course_len_out = course_len_out;
+  a.flag = flag; a.course_len_out = course_len_out; a.skip = h->skip;
   const int wpb = 4;
   const int blocks = (B + wpb - 1) / wpb;
   const size_t smem = wpb * jmpc::collision_warp_smem_bytes(h->max_N, n_obs);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->collision_attr_set) {             // per handle: function attributes are per device
     CK(cudaFuncSetAttribute(jmpc::collision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    h->collision_attr_set = true;
   }
   if (smem > 200 * 1024) return fail("jmpc_collision: course too long for the shared-memory arc scan");
   jmpc::collision_kernel<<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(a);

@@ -38,6 +38,7 @@ struct CollisionArgs {
   const double* params; ParamBlock defaults;
   int* flag; int* course_len_out;
   int arc_cap;                                       // course points the arc-length scan can hold (handle max_N)
+  const int* skip;                                   // [B] or nullptr: skip[b] != 0 -> instance left untouched
 };
 
 // dynamic shared memory of one warp: arc[arc_cap] | ocx[n_obs][kMaxObsFrames][2] | ocy[...] | ego_idx[kMaxEgoFrames]
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int b = blockIdx.x * (blockDim.x >> 5) + wib;
   if (b >= A.B) return;
+  if (A.skip && A.skip[b] != 0) return;
   CollisionSmem S(smem_raw + (size_t)wib * collision_warp_smem_bytes(A.arc_cap, A.n_obs), A.arc_cap, A.n_obs);
   const unsigned full = 0xffffffffu;
 

@@ -46,6 +46,7 @@ struct StepArgs {
   // fused all-gather: the epilogue also stores the record into every peer GPU's gathered table (NVLink peer
   // memory, jmpc_set_record_peers); peer p's table is [world * B][JMPC_RECORD_LEN], this rank owns rows
   // rank_offset .. rank_offset + B - 1
+  const int* skip;          // [B] or nullptr: instances with skip[b] != 0 are left untouched (finished episodes)
   double* peer_rec[JMPC_MAX_PEERS];
   int n_peers;
   long long rank_offset;
@@ -757,6 +758,7 @@ __global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const Ste
     if (lane == 0) b = atomicAdd(A.counter, 1u);
     b = __shfl_sync(kFull, b, 0);
     if (b >= (unsigned)A.B) break;
+    if (A.skip && A.skip[b] != 0) continue;
     mpc_step_instance<TT>(A, (int)b, base, pscr, lane);
     __syncwarp();
   }

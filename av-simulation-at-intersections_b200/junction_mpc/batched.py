@@ -104,6 +104,12 @@ class BatchedMPC:
         _cabi.check(self._lib.jmpc_set_car_geometry(self._h, float(front_offset), float(rear_offset), float(radius)),
                     "jmpc_set_car_geometry")
 
+    def set_skip_mask(self, mask):
+        """`mask`: CUDA int32 tensor [B] (kept alive by the caller) or None.  Instances with mask != 0 are skipped by
+        the step and collision kernels."""
+        _cabi.check(self._lib.jmpc_set_skip_mask(self._h, None if mask is None else C.c_void_p(mask.data_ptr())),
+                    "jmpc_set_skip_mask")
+
     def set_record_peers(self, peer_table_ptrs, rank_offset: int):
         """Fused all-gather: from now on the step kernel's epilogue also stores every instance's result record into
         row `rank_offset + b` of each peer GPU's gathered table.  `peer_table_ptrs`: device pointers (ints) of the

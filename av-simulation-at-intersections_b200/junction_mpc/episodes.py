@@ -51,6 +51,7 @@ class BatchedEpisodes:
         self.history = torch.full((self.max_steps, B, 8), float("nan"), dtype=f64, device=self.dev) if record_history else None
         self.flags = torch.zeros(self.max_steps, B, dtype=i32, device=self.dev) if record_history else None
         self.iteration = 0
+        engine.set_skip_mask(self.done)          # finished episodes cost nothing in the step / collision kernels
 
     def _p(self, ten):
         return None if ten is None else C.c_void_p(ten.data_ptr())
@@ -99,6 +100,7 @@ class BatchedEpisodes:
                                          self._p(self.done), float(e.config.goal_dis), float(e.config.stop_speed), stream),
                     "jmpc_episode_pre")
         self.torch.cuda.synchronize(e.device)
+        e.set_skip_mask(None)
         res = dict(steps=self.steps.cpu().numpy(), done=self.done.cpu().numpy(), state=self.state.cpu().numpy(),
                    iterations=self.iteration)
         if self.history is not None:

@@ -127,6 +127,10 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
                   const double* params, double* ox, double* oy, double* ov, double* oyaw, double* xref,
                   double* cost, int32_t* status, int32_t* iters, double* record, void* stream);
 
+/* Skip mask (DEVICE pointer, [B] int32, or NULL to clear): instances with skip[b] != 0 are left untouched by
+ * subsequent jmpc_step / jmpc_collision calls on the handle -- finished episodes of a closed-loop batch cost nothing. */
+int32_t jmpc_set_skip_mask(jmpc_handle h, const int32_t* skip);
+
 /* Fused all-gather of the result records (multi-GPU): after this call every jmpc_step on the handle also stores each
  * instance's record into row `rank_offset + b` of every table in `peer_tables` (DEVICE pointers valid on this GPU
  * for all `n_peers` ranks including this one -- NVLink peer / symmetric memory, e.g. the `buffer_ptrs` of a
