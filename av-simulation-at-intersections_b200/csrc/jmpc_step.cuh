@@ -68,7 +68,8 @@ __host__ __device__ inline int warp_smem_doubles(int T) {
          + 4 * n4               // u, q, rhs, grad
          + 14 * T1e             // prefix sums ca, cb, cc, ck; stage weights W11, W12, W22, qv, qpsi; WeX, WeY, epsi; vb, th
          + 4 * Te               // per-iteration row weights wA, wD, wR, SW
-         + kParamSlots;         // the instance's parameter vector + derived row bounds
+         + kParamSlots          // the instance's parameter vector + derived row bounds
+         + 2;                   // mbarrier of the TMA Hessian copy (8 bytes, padded to 16)
 }
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -184,6 +185,7 @@ struct WarpMem {
   double *WeX, *WeY, *epsi, *vb, *th;
   double *wA, *wD, *wR, *SW;
   double *prm;
+  unsigned long long* mbar;
   __device__ WarpMem(double* base, int T) {
     const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
     double* p = base;
@@ -194,17 +196,32 @@ struct WarpMem {
     W11 = p; p += T1e; W12 = p; p += T1e; W22 = p; p += T1e; qv = p; p += T1e; qpsi = p; p += T1e;
     WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e; vb = p; p += T1e; th = p; p += T1e;
     wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; SW = p; p += Te;
-    prm = p;
+    prm = p; p += kParamSlots;
+    mbar = reinterpret_cast<unsigned long long*>(p);
   }
 };
 
-// 16-byte asynchronous global -> shared copy (LDGSTS); both addresses 16-byte aligned
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+// ---- TMA 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier --------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// one lane: order the warp's earlier generic-proxy accesses before the async proxy, arm the barrier with the byte
+// count and issue the copy (bytes: multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("fence.proxy.async;\n" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
 
 // z = A u for the stage rows (u in shared memory)
 __device__ __forceinline__ void rows_apply(const double* u, int T, int lane, double z[4]) {
@@ -421,6 +438,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
       M.u[k] = 0.0; M.u[T + k] = 0.0;
     }
     if (lane < n4 - n) { M.q[n + lane] = 0.0; M.u[n + lane] = 0.0; M.rhs[n + lane] = 0.0; M.grad[n + lane] = 0.0; }
+    __threadfence();                     // the Hessian scratch is read back by TMA (async proxy) in the solver
     __syncwarp();
 
     // feasibility predicate: the t = 0 speed rows act on the fixed v0
@@ -449,7 +467,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
 // Returns the iteration count; `converged` says whether the KKT tolerances were met.
 template <int TT>
 __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, const double* pscr, int lane,
-                                       bool& converged_out) {
+                                       bool& converged_out, unsigned& tma_parity) {
   const int T = (TT > 0) ? TT : A.T;
   const int n = 2 * T, nb = nblk(n);
   WarpMem M(smem_base, T);
@@ -484,9 +502,10 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
 #endif
     int it = 0;
     for (it = 0; it < A.max_iters; ++it) {
-      // P -> shared, asynchronously (the scratch copy is L2 resident): the copy runs under the row work below
-      for (int e = lane * 2; e < ntd; e += 64) cp_async16(M.K + e, pscr + e);
-      cp_async_commit();
+      // P -> shared with one TMA bulk copy (the scratch copy is L2 resident); it runs under the row work below.
+      // The previous iteration's last reads of K are behind a __syncwarp, the fence inside orders them (generic
+      // proxy) before the copy (async proxy).
+      if (lane == 0) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
       double z[4], rph[4], rpl[4], ish[4], isl[4], t4[4];
       rows_apply(M.u, T, lane, z);
       double mu = 0.0, rpmax = 0.0;
@@ -513,7 +532,8 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       rpmax = warp_max(rpmax);
       // P u is formed from the clean Hessian: folding the barrier weights in first and subtracting them again
       // would cancel catastrophically once w ~ 1e12
-      cp_async_wait_all();
+      mbar_wait(M.mbar, tma_parity);
+      tma_parity ^= 1u;
       __syncwarp();
       double pu0, pu1;
       symv_tiles(M.K, M.u, nb, lane, pu0, pu1);
@@ -715,7 +735,8 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
 // phases are separate functions so that the solver's register allocation is not burdened by the values the
 // preparation and the epilogue need; they communicate through the warp's shared memory.
 template <int TT>
-__device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane) {
+__device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane,
+                                                  unsigned& tma_parity) {
   const int T = (TT > 0) ? TT : A.T;
   WarpMem M(smem_base, T);
   // the instance's parameter vector lives in shared memory (uniform reads, no registers held across phases)
@@ -732,7 +753,7 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, doub
     const int st = step_prep<TT>(A, b, smem_base, pscr, lane, lin, total_iters, oa_k, od_k, ov_k, target, idx, end_mask);
     if (st != JMPC_OPTIMAL) return;
     bool converged = false;
-    total_iters += step_solve<TT>(A, smem_base, pscr, lane, converged);
+    total_iters += step_solve<TT>(A, smem_base, pscr, lane, converged, tma_parity);
     step_output<TT>(A, b, smem_base, lane, lin == A.lin_iters - 1, converged ? JMPC_OPTIMAL : JMPC_MAX_ITER, target, idx,
                     end_mask, total_iters, oa_k, od_k, ov_k);
     __syncwarp();
@@ -753,13 +774,19 @@ __global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const Ste
   const int gw = blockIdx.x * warps_per_block + wib;
   const int n = 2 * T;
   double* pscr = A.pscratch + (size_t)gw * tiles_doubles(n);
+  unsigned tma_parity = 0;
+  {
+    WarpMem M0(base, T);
+    if (lane == 0) mbar_init(M0.mbar, 1);
+    __syncwarp();
+  }
   for (;;) {
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(A.counter, 1u);
     b = __shfl_sync(kFull, b, 0);
     if (b >= (unsigned)A.B) break;
     if (A.skip && A.skip[b] != 0) continue;
-    mpc_step_instance<TT>(A, (int)b, base, pscr, lane);
+    mpc_step_instance<TT>(A, (int)b, base, pscr, lane, tma_parity);
     __syncwarp();
   }
 }
