@@ -257,3 +257,19 @@ def test_fused_record_stores_reach_the_peer_tables(jm):
         assert np.array_equal(got[200:400], host.record) and np.array_equal(got[200:400], out.record.cpu().numpy())
         assert (got[:200] == -7.0).all() and (got[400:] == -7.0).all()
     mpc.set_record_peers([], 0)
+
+
+@pytest.mark.parametrize("T", [5, 10, 31])
+def test_generic_horizons(jm, T):
+    """Horizons without a compile-time specialisation run the generic kernel; T = 31 is the limit of the
+    lane-per-stage mapping (T + 1 = 32 horizon points)."""
+    synth, BatchedMPC = jm
+    from junction_mpc.config import MPCConfig
+    rng = np.random.default_rng(T)
+    course = synth.load_course("roundabout")
+    w = synth.make_states(rng, course, 40, T)
+    w.update(T=T, courses=[course], params=None, B=40, dl=float(np.linalg.norm(course[0, :2] - course[1, :2])))
+    mpc = BatchedMPC([course], dl=w["dl"], T=T, max_batch=64, max_T=31)
+    out = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"])
+    refs = oracle_batch(w, range(40))
+    assert compare_step(out, refs, range(40)) <= 1.0
