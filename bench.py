@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's own size)")
     ap.add_argument("--ref-sample", type=int, default=256)
-    ap.add_argument("--cpu-sample", type=int, default=512)
+    ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -296,7 +296,7 @@ def main():
         pass
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1d_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as f:
             tr = json.load(f)
         if B == 4096 and T == 20:
             traffic = tr["dram_bytes_per_launch"]          # from the committed ncu --set full capture, per launch
@@ -323,7 +323,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
-                     "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1d_traffic.json)",
+                     "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1e_traffic.json)",
                      "peak_source": "jmpc_measure_fma_peak: register-resident FP64 FMA loop on all SMs, measured in this run "
                                     "(MEASURED_PEAKS.json holds no FP64 figure)",
                      "flops_per_solve": flops_per_solve(T, mean_iters), "kernel": "jmpc::mpc_step_kernel",
