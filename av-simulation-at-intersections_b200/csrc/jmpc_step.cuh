@@ -59,11 +59,24 @@ constexpr int kSlotHi3 = JMPC_NPARAM, kSlotLo3 = JMPC_NPARAM + 1, kSlotLim = JMP
 constexpr int kParamSlots = 32;
 static_assert(JMPC_NPARAM + 3 <= kParamSlots, "parameter block too small");
 
+// suffix-moment slots of the Hessian assembly (step_prep): weight x centred prefix products
+enum MomentSlot {
+  MOM_11, MOM_11_A, MOM_11_B, MOM_11_AA, MOM_11_AB, MOM_11_BB,
+  MOM_12, MOM_12_A, MOM_12_B, MOM_12_C, MOM_12_K, MOM_12_AC, MOM_12_AK, MOM_12_BC, MOM_12_BK,
+  MOM_22, MOM_22_C, MOM_22_K, MOM_22_CC, MOM_22_CK, MOM_22_KK,
+  MOM_QV, MOM_QPSI, MOM_COUNT
+};
+
 // shared-memory doubles one warp needs for horizon T (every sub-array starts 16-byte aligned)
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
+// the K region also hosts the suffix moments during the condensing (short horizons need more room for those)
+__host__ __device__ inline int k_region_doubles(int T) {
+  const int a = tiles_doubles(2 * T), b = MOM_COUNT * even_up(T + 1);
+  return a > b ? a : b;
+}
 __host__ __device__ inline int warp_smem_doubles(int T) {
   const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
-  return tiles_doubles(n)       // K / L on 4x4 tiles
+  return k_region_doubles(T)    // K / L on 4x4 tiles (and the condensing's moment tables)
          + 16 * nblk(n)         // inverses of the factor's diagonal blocks
          + 4 * n4               // u, q, rhs, grad
          + 14 * T1e             // prefix sums ca, cb, cc, ck; stage weights W11, W12, W22, qv, qpsi; WeX, WeY, epsi; vb, th
@@ -189,7 +202,7 @@ struct WarpMem {
   __device__ WarpMem(double* base, int T) {
     const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
     double* p = base;
-    K = p; p += tiles_doubles(n);
+    K = p; p += k_region_doubles(T);
     Dinv = p; p += 16 * nblk(n);
     u = p; p += n4; q = p; p += n4; rhs = p; p += n4; grad = p; p += n4;
     ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
@@ -327,9 +340,13 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
     if (lane < T) {
       al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw;
     }
-    // exclusive prefix sums c*[t] = sum_{j<t} (.)  for t = 0..T  (lane t)
-    const double ca_t = warp_scan(al, lane) - al, cb_t = warp_scan(be, lane) - be;
-    const double cc_t = warp_scan(ga, lane) - ga, ck_t = warp_scan(ka, lane) - ka;
+    // exclusive prefix sums c*[t] = sum_{j<t} (.)  for t = 0..T  (lane t).  Only differences c[t] - c[k] are ever
+    // used, so each array is centred on its mid-horizon value: that halves the magnitudes entering the moment
+    // expansion of the Hessian below.
+    double ca_t = warp_scan(al, lane) - al, cb_t = warp_scan(be, lane) - be;
+    double cc_t = warp_scan(ga, lane) - ga, ck_t = warp_scan(ka, lane) - ka;
+    ca_t -= __shfl_sync(kFull, ca_t, T >> 1); cb_t -= __shfl_sync(kFull, cb_t, T >> 1);
+    cc_t -= __shfl_sync(kFull, cc_t, T >> 1); ck_t -= __shfl_sync(kFull, ck_t, T >> 1);
     // free response (u = 0): v = v0, psi = yaw0
     const double fx_term = (lane < T) ? (al * v0 - be * (yaw0 - th)) : 0.0;
     const double fy_term = (lane < T) ? (ga * v0 + ka * (yaw0 - th)) : 0.0;
@@ -350,6 +367,23 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
         w22 = (s1 * s1) * wp + (s2 * s2) * wl;
         wv = P(JMPC_P_Q_V); wpsi = P(JMPC_P_Q_YAW);
       }
+    }
+    // Suffix moments  mom[m][t0] = sum_{t >= t0} W_t * (product of centred prefix values at t),  23 sequences, kept
+    // in the K region (free until the solver starts).  With them every Hessian entry is O(1):
+    //   sum_{t>=t0} W (F_t - F0)(G_t - G0) = M_WFG - G0 M_WF - F0 M_WG + F0 G0 M_W.
+    {
+      const bool vt = (lane >= 1 && lane <= T);
+      const double A_ = vt ? ca_t : 0.0, B_ = vt ? cb_t : 0.0, C_ = vt ? cc_t : 0.0, K_ = vt ? ck_t : 0.0;
+      double* mom = M.K;
+      const int ms = even_up(T + 1);
+      auto put = [&](int m, double v) { const double sfx = warp_rscan(v, lane); if (lane <= T) mom[m * ms + lane] = sfx; };
+      put(MOM_11, w11); put(MOM_11_A, w11 * A_); put(MOM_11_B, w11 * B_);
+      put(MOM_11_AA, w11 * A_ * A_); put(MOM_11_AB, w11 * A_ * B_); put(MOM_11_BB, w11 * B_ * B_);
+      put(MOM_12, w12); put(MOM_12_A, w12 * A_); put(MOM_12_B, w12 * B_); put(MOM_12_C, w12 * C_); put(MOM_12_K, w12 * K_);
+      put(MOM_12_AC, w12 * A_ * C_); put(MOM_12_AK, w12 * A_ * K_); put(MOM_12_BC, w12 * B_ * C_); put(MOM_12_BK, w12 * B_ * K_);
+      put(MOM_22, w22); put(MOM_22_C, w22 * C_); put(MOM_22_K, w22 * K_);
+      put(MOM_22_CC, w22 * C_ * C_); put(MOM_22_CK, w22 * C_ * K_); put(MOM_22_KK, w22 * K_ * K_);
+      put(MOM_QV, wv); put(MOM_QPSI, wpsi);
     }
     const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 - vr, eps = yaw0 - psir;
     if (lane <= T) {
@@ -384,27 +418,29 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
         const bool id = i >= T, jd = j >= T;
         const int ki = id ? i - T : i, kj = jd ? j - T : j;
         const int t0 = max(ki, kj) + 1;
-        double acc = 0.0;
-        if (!id) {                       // accel x accel
+        // S(W; F, G)(F0, G0) = sum_{t >= t0} W_t (F_t - F0)(G_t - G0) from the suffix moments
+        const double* mom = M.K + t0;
+        const int ms = even_up(T + 1);
+        auto S = [&](int mW, int mWF, int mWG, int mWFG, double F0, double G0) -> double {
+          return mom[mWFG * ms] - G0 * mom[mWF * ms] - F0 * mom[mWG * ms] + F0 * G0 * mom[mW * ms];
+        };
+        double acc;
+        if (!id) {                       // accel x accel: sX = dt (A - A0), sY = dt (C - C0), sV = dt
           const double ai = M.ca[ki + 1], ci = M.cc[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-          for (int t = t0; t <= T; ++t) {
-            const double dAi = M.ca[t] - ai, dCi = M.cc[t] - ci, dAj = M.ca[t] - aj, dCj = M.cc[t] - cj;
-            acc += dAi * (M.W11[t] * dAj + M.W12[t] * dCj) + dCi * (M.W12[t] * dAj + M.W22[t] * dCj) + M.qv[t];
-          }
+          acc = S(MOM_11, MOM_11_A, MOM_11_A, MOM_11_AA, ai, aj) + S(MOM_12, MOM_12_A, MOM_12_C, MOM_12_AC, ai, cj)
+              + S(MOM_12, MOM_12_C, MOM_12_A, MOM_12_AC, ci, aj) + S(MOM_22, MOM_22_C, MOM_22_C, MOM_22_CC, ci, cj)
+              + mom[MOM_QV * ms];
           acc *= dt2;
-        } else if (!jd) {                // steer (row) x accel (col)
+        } else if (!jd) {                // steer (row) x accel (col): sX_i = -g (B - B0), sY_i = g (K - K0)
           const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-          for (int t = t0; t <= T; ++t) {
-            const double sx = -(M.cb[t] - bi), sy = M.ck[t] - kki, dAj = M.ca[t] - aj, dCj = M.cc[t] - cj;
-            acc += sx * (M.W11[t] * dAj + M.W12[t] * dCj) + sy * (M.W12[t] * dAj + M.W22[t] * dCj);
-          }
+          acc = -S(MOM_11, MOM_11_B, MOM_11_A, MOM_11_AB, bi, aj) - S(MOM_12, MOM_12_B, MOM_12_C, MOM_12_BC, bi, cj)
+              + S(MOM_12, MOM_12_K, MOM_12_A, MOM_12_AK, kki, aj) + S(MOM_22, MOM_22_K, MOM_22_C, MOM_22_CK, kki, cj);
           acc *= M.wA[ki] * dt;
-        } else {                         // steer x steer
+        } else {                         // steer x steer, plus the yaw weight
           const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], bj = M.cb[kj + 1], kkj = M.ck[kj + 1];
-          for (int t = t0; t <= T; ++t) {
-            const double sxi = -(M.cb[t] - bi), syi = M.ck[t] - kki, sxj = -(M.cb[t] - bj), syj = M.ck[t] - kkj;
-            acc += sxi * (M.W11[t] * sxj + M.W12[t] * syj) + syi * (M.W12[t] * sxj + M.W22[t] * syj) + M.qpsi[t];
-          }
+          acc = S(MOM_11, MOM_11_B, MOM_11_B, MOM_11_BB, bi, bj) - S(MOM_12, MOM_12_B, MOM_12_K, MOM_12_BK, bi, kkj)
+              - S(MOM_12, MOM_12_K, MOM_12_B, MOM_12_BK, kki, bj) + S(MOM_22, MOM_22_K, MOM_22_K, MOM_22_KK, kki, kkj)
+              + mom[MOM_QPSI * ms];
           acc *= M.wA[ki] * M.wA[kj];
         }
         acc *= 2.0;

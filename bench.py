@@ -34,7 +34,7 @@ def flops_per_solve(T: int, iters: float) -> float:
     """Algorithmic flop count of the implemented algorithm."""
     n = 2 * T
     f_prep = 64.0 * T
-    f_cond = 15.0 * (T * (T + 1) * (T + 2) / 3.0 + T * (T + 1) * (2 * T + 1) / 6.0) + 12.0 * T * (T + 1)
+    f_cond = 45.0 * n * (n + 1) / 2.0 + 70.0 * (T + 1) + 12.0 * T * (T + 1)   # O(1) entries from 23 suffix moments
     f_iter = n ** 3 / 3.0 + 7.0 * n * n + 240.0 * T
     return f_prep + f_cond + iters * f_iter
 
