@@ -638,8 +638,11 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
         solve_tiles(M.K, M.Dinv, M.rhs, nb, lane);
         double dz[4];
         rows_apply(M.rhs, T, lane, dz);
-        // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l)
-        double worst = 0.0;
+        // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l).  The maximum ratio is tracked as a
+        // (numerator, denominator) pair compared by cross-multiplication, so the 16 candidates per lane cost no
+        // division (fp64 division is ~20 instructions); one division remains after the warp reduction.
+        double wn = 0.0, wd = 1.0;
+        auto cand = [&](double num, double den) { if (num * wd > wn * den) { wn = num; wd = den; } };
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const bool lv = is_live(r);
@@ -648,13 +651,14 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
           dsl[r] = lv ? (-rpl[r] + dz[r]) : 0.0;
           dlh[r] = lv ? (-(fma(lh[r], dsh[r], rch)) * ish[r]) : 0.0;
           dll[r] = lv ? (-(fma(ll[r], dsl[r], rcl)) * isl[r]) : 0.0;
-          if (lv) {
-            worst = fmax(worst, fmax(-dsh[r] * ish[r], -dsl[r] * isl[r]));
-            worst = fmax(worst, fmax(-dlh[r] / lh[r], -dll[r] / ll[r]));
-          }
+          if (lv) { cand(-dsh[r], sh[r]); cand(-dsl[r], sl[r]); cand(-dlh[r], lh[r]); cand(-dll[r], ll[r]); }
         }
-        worst = warp_max(worst);
-        const double amax = (worst > 0.0) ? 1.0 / worst : INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double on = __shfl_xor_sync(kFull, wn, o), od = __shfl_xor_sync(kFull, wd, o);
+          if (on * wd > wn * od) { wn = on; wd = od; }
+        }
+        const double amax = (wn > 0.0) ? wd / wn : INFINITY;
         if (phase == 0) {
           const double aa = fmin(1.0, amax);
           aff_step = aa;
