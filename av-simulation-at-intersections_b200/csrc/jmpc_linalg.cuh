@@ -37,11 +37,31 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
   *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
 }
 
+// Task table of the trailing update: for block column J, task q (half a tile) -> (a, b, half) with tile row
+// I = J + 1 + a, tile column Kc = J + 1 + b (b <= a).  It only depends on m = nb - J - 1, so one table of
+// sum_{m=1}^{nb-1} m (m + 1) 16-bit entries serves every factorisation of the launch; it is built once per block in
+// shared memory.  (Decoding q arithmetically -- float sqrt plus fix-up loops -- was 4 % of the kernel's instructions.)
+__host__ __device__ inline int chol_lut_entries(int nb) { return ((nb - 1) * nb * (nb + 1)) / 3; }
+__host__ __device__ __forceinline__ int chol_lut_offset(int m) { return ((m - 1) * m * (m + 1)) / 3; }   // tasks of all m' < m
+__device__ inline void chol_lut_build(unsigned short* lut, int nb, int tid, int nthreads) {
+  for (int m = 1; m < nb; ++m) {
+    const int ntasks = m * (m + 1), off = chol_lut_offset(m);
+    for (int q = tid; q < ntasks; q += nthreads) {
+      const int t = q >> 1;
+      int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while (((a + 1) * (a + 2) >> 1) <= t) ++a;
+      while (((a * (a + 1)) >> 1) > t) --a;
+      const int b = t - ((a * (a + 1)) >> 1);
+      lut[off + q] = (unsigned short)(a | (b << 4) | ((q & 1) << 8));
+    }
+  }
+}
+
 // In-place Cholesky K = L L' on tiles.  Dinv receives the inverses of the diagonal blocks of L (nb x 16 doubles,
 // lower triangular), which turn the panel and the triangular solves into multiplications.
 // Returns false when some pivot was not positive and had to be replaced (all lanes agree); the factor is usable
 // either way.
-__device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane) {
+__device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, const unsigned short* lut) {
   bool all_clean = true;
   for (int J = 0; J < nb; ++J) {
     // ---- diagonal block: every lane factors it redundantly in registers (no broadcast needed)
@@ -100,13 +120,10 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane) {
     // ---- trailing update: C(I, Kc) -= L(I, J) L(Kc, J)'; a task is half a tile (two rows), so the 45 / 36 / 28 ...
     // tiles of the first block columns fill the 32 lanes better than whole tiles would
     const int m = nb - J - 1, ntasks = m * (m + 1);
+    const unsigned short* tasks = lut + chol_lut_offset(m);
     for (int q = lane; q < ntasks; q += 32) {
-      const int t = q >> 1, h = (q & 1) << 1;
-      int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-      while (((a + 1) * (a + 2) >> 1) <= t) ++a;
-      while (((a * (a + 1)) >> 1) > t) --a;
-      const int b = t - ((a * (a + 1)) >> 1);
-      const int I = J + 1 + a, Kc = J + 1 + b;
+      const unsigned e = tasks[q];
+      const int I = J + 1 + (int)(e & 15u), Kc = J + 1 + (int)((e >> 4) & 15u), h = (int)((e >> 8) & 1u) << 1;
       const double* LI = K + tile_off(I, J) + 4 * h;
       const double* LK = K + tile_off(Kc, J);
       double* C = K + tile_off(I, Kc) + 4 * h;
@@ -210,6 +227,8 @@ __global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, cons
   double* Dinv = K + tiles_doubles(n);
   double* rhs = Dinv + 16 * nb;
   double* xv = rhs + n4;
+  unsigned short* lut = reinterpret_cast<unsigned short*>(xv + n4);
+  chol_lut_build(lut, nb, lane, 32);
   for (int e = lane; e < tiles_doubles(n); e += 32) K[e] = 0.0;
   __syncwarp();
   for (int e = lane; e < n4 * n4; e += 32) {
@@ -225,7 +244,7 @@ __global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, cons
   if (lane < n) prod[lane] = y0;
   if (lane + 32 < n) prod[lane + 32] = y1;
   __syncwarp();
-  const bool good = chol_tiles(K, Dinv, nb, lane);
+  const bool good = chol_tiles(K, Dinv, nb, lane, lut);
   solve_tiles(K, Dinv, rhs, nb, lane);
   __syncwarp();
   for (int i = lane; i < n; i += 32) sol[i] = rhs[i];

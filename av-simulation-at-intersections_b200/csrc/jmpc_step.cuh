@@ -85,6 +85,11 @@ __host__ __device__ inline int warp_smem_doubles(int T) {
          + 2;                   // mbarrier of the TMA Hessian copy (8 bytes, padded to 16)
 }
 
+// dynamic shared memory of a block of `wpb` warps: the warps' regions plus the block-shared Cholesky task table
+__host__ __device__ inline size_t step_block_smem_bytes(int T, int wpb) {
+  return (size_t)wpb * warp_smem_doubles(T) * sizeof(double) + (((size_t)chol_lut_entries(nblk(2 * T)) * 2 + 15) & ~(size_t)15);
+}
+
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -503,7 +508,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
 // Returns the iteration count; `converged` says whether the KKT tolerances were met.
 template <int TT>
 __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, const double* pscr, int lane,
-                                       bool& converged_out, unsigned& tma_parity) {
+                                       bool& converged_out, unsigned& tma_parity, const unsigned short* lut) {
   const int T = (TT > 0) ? TT : A.T;
   const int n = 2 * T, nb = nblk(n);
   WarpMem M(smem_base, T);
@@ -615,7 +620,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       dbg_mu = mu; dbg_rp = rpmax; dbg_rd = rdmax / gscale;
 #endif
 
-      chol_tiles(M.K, M.Dinv, nb, lane);          // non-positive pivots are replaced, never fatal
+      chol_tiles(M.K, M.Dinv, nb, lane, lut);     // non-positive pivots are replaced, never fatal
 
       double dsh[4], dsl[4], dlh[4], dll[4];
       double sigma_mu = 0.0, aff_step = 0.0;
@@ -776,7 +781,7 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
 // preparation and the epilogue need; they communicate through the warp's shared memory.
 template <int TT>
 __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane,
-                                                  unsigned& tma_parity) {
+                                                  unsigned& tma_parity, const unsigned short* lut) {
   const int T = (TT > 0) ? TT : A.T;
   WarpMem M(smem_base, T);
   // the instance's parameter vector lives in shared memory (uniform reads, no registers held across phases)
@@ -793,7 +798,7 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, doub
     const int st = step_prep<TT>(A, b, smem_base, pscr, lane, lin, total_iters, oa_k, od_k, ov_k, target, idx, end_mask);
     if (st != JMPC_OPTIMAL) return;
     bool converged = false;
-    total_iters += step_solve<TT>(A, smem_base, pscr, lane, converged, tma_parity);
+    total_iters += step_solve<TT>(A, smem_base, pscr, lane, converged, tma_parity, lut);
     step_output<TT>(A, b, smem_base, lane, lin == A.lin_iters - 1, converged ? JMPC_OPTIMAL : JMPC_MAX_ITER, target, idx,
                     end_mask, total_iters, oa_k, od_k, ov_k);
     __syncwarp();
@@ -820,13 +825,17 @@ __global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const Ste
     if (lane == 0) mbar_init(M0.mbar, 1);
     __syncwarp();
   }
+  // block-shared task table of the Cholesky trailing update, behind the warps' regions
+  unsigned short* lut = reinterpret_cast<unsigned short*>(smem + (size_t)warps_per_block * warp_smem_doubles(T));
+  chol_lut_build(lut, nblk(n), threadIdx.x, blockDim.x);
+  __syncthreads();
   for (;;) {
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(A.counter, 1u);
     b = __shfl_sync(kFull, b, 0);
     if (b >= (unsigned)A.B) break;
     if (A.skip && A.skip[b] != 0) continue;
-    mpc_step_instance<TT>(A, (int)b, base, pscr, lane, tma_parity);
+    mpc_step_instance<TT>(A, (int)b, base, pscr, lane, tma_parity, lut);
     __syncwarp();
   }
 }

@@ -11,6 +11,9 @@ for p in (ROOT, PKG):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# development scripts and the fixture generator are not tests (some need a GPU or /root/reference at import)
+collect_ignore_glob = ["tools/*", "golden/*"]
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
