@@ -294,6 +294,39 @@ int32_t jmpc_set_car_geometry(jmpc_handle h, double front_offset, double rear_of
   return h->n_courses ? refresh_circle_tables(h) : 0;
 }
 
+namespace {
+// Launch of the step kernel.  The in-out arrays have separate read and write pointers: jmpc_step passes the same
+// array twice, jmpc_step_host reads device copies and writes page-locked host memory.
+int launch_step(jmpc_handle h, int B, int T, const double* state, const int* course_id, const int* course_len,
+                const int* target_in, int* target_out, const int* warm, const double* oa_in, const double* od_in,
+                double* oa_out, double* od_out, const double* params, double* ox, double* oy, double* ov,
+                double* oyaw, double* xref, double* cost, int* status, int* iters, double* record, cudaStream_t s) {
+  StepGeom g;
+  if (step_geometry(h, B, T, &g)) return -1;
+  const int n = 2 * T;
+  if (ensure_scratch(h, (size_t)g.warps * jmpc::tiles_doubles(n))) return -1;
+  jmpc::StepArgs a;
+  a.B = B; a.T = T; a.lin_iters = h->opt.linearisation_iters; a.max_iters = h->opt.max_solver_iters;
+  a.mu_tol = h->opt.mu_tol;
+  a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
+  a.course_stride = h->course_stride; a.n_courses = h->n_courses;
+  a.state = state; a.course_id = course_id; a.course_len = course_len; a.warm = warm; a.params = params;
+  memcpy(a.defaults, h->defaults, sizeof a.defaults);
+  a.target_ind = target_in; a.oa = oa_in; a.od = od_in;
+  a.target_out = target_out; a.oa_out = oa_out; a.od_out = od_out;
+  a.ox = ox; a.oy = oy; a.ov = ov; a.oyaw = oyaw; a.xref = xref;
+  a.cost = cost; a.status = status; a.iters = iters; a.record = record;
+  a.n_peers = h->n_peers; a.rank_offset = h->rank_offset; a.skip = h->skip;
+  for (int p = 0; p < JMPC_MAX_PEERS; ++p) a.peer_rec[p] = h->peer_rec[p];
+  a.pscratch = h->d_pscratch; a.counter = h->d_counter;
+  CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
+  step_kernel_for(T)<<<g.blocks, g.threads, g.smem, s>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+}  // namespace
+
 int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                   const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa, double* od,
                   const double* params, double* ox, double* oy, double* ov, double* oyaw, double* xref,
@@ -306,28 +339,8 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
   if (h->n_courses < 1) return fail("jmpc_step: no courses uploaded (jmpc_set_courses)");
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = (cudaStream_t)stream;
-  StepGeom g;
-  if (step_geometry(h, B, T, &g)) return -1;
-  const int n = 2 * T;
-  if (ensure_scratch(h, (size_t)g.warps * jmpc::tiles_doubles(n))) return -1;
-  jmpc::StepArgs a;
-  a.B = B; a.T = T; a.lin_iters = h->opt.linearisation_iters; a.max_iters = h->opt.max_solver_iters;
-  a.mu_tol = h->opt.mu_tol;
-  a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
-  a.course_stride = h->course_stride; a.n_courses = h->n_courses;
-  a.state = state; a.course_id = course_id; a.course_len = course_len; a.warm = warm; a.params = params;
-  memcpy(a.defaults, h->defaults, sizeof a.defaults);
-  a.target_ind = target_ind; a.oa = oa; a.od = od; a.ox = ox; a.oy = oy; a.ov = ov; a.oyaw = oyaw; a.xref = xref;
-  a.cost = cost; a.status = status; a.iters = iters; a.record = record;
-  a.n_peers = h->n_peers; a.rank_offset = h->rank_offset; a.skip = h->skip;
-  for (int p = 0; p < JMPC_MAX_PEERS; ++p) a.peer_rec[p] = h->peer_rec[p];
-  a.pscratch = h->d_pscratch; a.counter = h->d_counter;
-  CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
-  step_kernel_for(T)<<<g.blocks, g.threads, g.smem, s>>>(a);
-  CK(cudaGetLastError());
-  h->launches++;
-  return 0;
+  return launch_step(h, B, T, state, course_id, course_len, target_ind, target_ind, warm, oa, od, oa, od, params, ox, oy,
+                     ov, oyaw, xref, cost, status, iters, record, (cudaStream_t)stream);
 }
 
 int32_t jmpc_host_alloc(jmpc_handle h, size_t bytes, void** out) {
@@ -371,74 +384,145 @@ int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
                        double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
                        double* xref, double* cost, int32_t* status, int32_t* iters, double* record) {
+  return jmpc_step_host_io(h, B, T, state, course_id, course_len, target_ind, warm, oa, od, params, target_ind, oa, od,
+                           ox, oy, ov, oyaw, xref, cost, status, iters, record);
+}
+
+int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
+                          const int32_t* course_len, const int32_t* target_in, const int32_t* warm,
+                          const double* oa_in, const double* od_in, const double* params, int32_t* target_out,
+                          double* oa_out, double* od_out, double* ox, double* oy, double* ov, double* oyaw,
+                          double* xref, double* cost, int32_t* status, int32_t* iters, double* record) {
   if (!h) return fail("jmpc_step_host: NULL handle");
   if (B < 0 || B > h->max_B) return fail("jmpc_step_host: B out of range");
   if (T < 2 || T > h->max_T) return fail("jmpc_step_host: T out of range");
-  if (!state || !target_ind || !oa || !od || !ox || !oy || !ov || !oyaw || !xref || !cost || !status)
+  if (!state || !target_in || !oa_in || !od_in || !target_out || !oa_out || !od_out || !ox || !oy || !ov || !oyaw ||
+      !xref || !cost || !status)
     return fail("jmpc_step_host: NULL array");
+  if (h->n_courses < 1) return fail("jmpc_step_host: no courses uploaded (jmpc_set_courses)");
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   const size_t T1 = T + 1, b = (size_t)B;
-  // Device side: one contiguous block [inputs | in-out | outputs].  Host side: arrays that live in page-locked
-  // memory (jmpc_host_alloc, cudaHostAlloc, torch pin_memory) are copied straight to / from the device; pageable
-  // ones go through the handle's pinned staging block (one memcpy each way).
-  struct Seg { size_t off, bytes; void* host; bool pinned; bool out; };
+  // Staging block layout [inputs | outputs], the same offsets on the device (d_stage) and in the handle's
+  // page-locked host block (h_stage).  Transfer modes (JMPC_ZEROCOPY, default 2):
+  //   2  no copy engine at all.  The kernel reads its inputs from, and stores its results into, page-locked host
+  //      memory through the device mapping (unified addressing): the caller's own array where that is page-locked
+  //      (jmpc_host_alloc, cudaHostAlloc, torch pin_memory), the h_stage slot otherwise (one host memcpy on that
+  //      side).  A warp reads ~0.4 KB when it picks an instance up and writes ~1.7 KB when it is done; both ride
+  //      under the other warps' solves, and at ~6 GB/s of results the PCIe link is far from saturated, so the
+  //      transfers leave the critical path.
+  //   1  inputs by cudaMemcpyAsync into d_stage, results stored directly into host memory as above.
+  //   0  staged DMA both ways (results to d_stage, cudaMemcpyAsync back).
+  // Instances that fail the index rule or are infeasible leave oa_out / od_out / target_out untouched; these are
+  // pre-filled with the inputs when they are different arrays, so "in-out arrays keep their values" holds.
+  struct Seg { size_t off, bytes; void* host; bool pinned; void* mapped; };
   size_t off = 0;
-  Seg segs[17];
+  Seg segs[20];
   int ns = 0;
-  auto seg = [&](size_t bytes, const void* host, bool out) -> Seg& {
+  const char* mode_env = getenv("JMPC_ZEROCOPY");       // read per call: tests switch it
+  const int mode = mode_env ? atoi(mode_env) : 2;
+  auto seg = [&](size_t bytes, const void* host) -> Seg& {
     Seg& s = segs[ns++];
-    s.off = off; s.bytes = host ? bytes : 0; s.host = const_cast<void*>(host); s.out = out;
+    s.off = off; s.bytes = host ? bytes : 0; s.host = const_cast<void*>(host);
     s.pinned = host ? is_pinned(host) : false;
+    s.mapped = nullptr;
     off += (s.bytes + 15) & ~size_t(15);
     return s;
   };
-  const Seg& s_state = seg(b * 4 * 8, state, false);
-  const Seg& s_params = seg(b * JMPC_NPARAM * 8, params, false);
-  const Seg& s_cid = seg(b * 4, course_id, false);
-  const Seg& s_clen = seg(b * 4, course_len, false);
-  const Seg& s_warm = seg(b * 4, warm, false);
-  const int first_inout = ns;
-  const Seg& s_oa = seg(b * T * 8, oa, true);
-  const Seg& s_od = seg(b * T * 8, od, true);
-  const Seg& s_tgt = seg(b * 4, target_ind, true);
+  const Seg& s_state = seg(b * 4 * 8, state);
+  const Seg& s_params = seg(b * JMPC_NPARAM * 8, params);
+  const Seg& s_cid = seg(b * 4, course_id);
+  const Seg& s_clen = seg(b * 4, course_len);
+  const Seg& s_warm = seg(b * 4, warm);
+  const Seg& s_oa_in = seg(b * T * 8, oa_in);
+  const Seg& s_od_in = seg(b * T * 8, od_in);
+  const Seg& s_tgt_in = seg(b * 4, target_in);
   const int first_out = ns;
-  const Seg& s_ox = seg(b * T1 * 8, ox, true);
-  const Seg& s_oy = seg(b * T1 * 8, oy, true);
-  const Seg& s_ov = seg(b * T1 * 8, ov, true);
-  const Seg& s_oyaw = seg(b * T1 * 8, oyaw, true);
-  const Seg& s_xref = seg(b * 4 * T1 * 8, xref, true);
-  const Seg& s_cost = seg(b * 8, cost, true);
-  const Seg& s_status = seg(b * 4, status, true);
-  const Seg& s_iters = seg(b * 4, iters, true);
-  const Seg& s_rec = seg(b * JMPC_RECORD_LEN * 8, record, true);
+  const size_t in_end = off;
+  const Seg& s_oa = seg(b * T * 8, oa_out);
+  const Seg& s_od = seg(b * T * 8, od_out);
+  const Seg& s_tgt = seg(b * 4, target_out);
+  const Seg& s_ox = seg(b * T1 * 8, ox);
+  const Seg& s_oy = seg(b * T1 * 8, oy);
+  const Seg& s_ov = seg(b * T1 * 8, ov);
+  const Seg& s_oyaw = seg(b * T1 * 8, oyaw);
+  const Seg& s_xref = seg(b * 4 * T1 * 8, xref);
+  const Seg& s_cost = seg(b * 8, cost);
+  const Seg& s_status = seg(b * 4, status);
+  const Seg& s_iters = seg(b * 4, iters);
+  const Seg& s_rec = seg(b * JMPC_RECORD_LEN * 8, record);
   const size_t total = off;
   if (ensure_stage(h, total)) return -1;
   char* hs = h->h_stage; char* ds = h->d_stage;
   cudaStream_t st = h->own_stream;
-  // host -> device: inputs and in-out arrays
-  for (int k = 0; k < first_out; ++k) {
-    const Seg& s = segs[k];
+  // device mappings of the page-locked arrays
+  char* hs_dev = nullptr;
+  bool map_ok = mode >= 1;
+  if (map_ok && cudaHostGetDevicePointer((void**)&hs_dev, hs, 0) != cudaSuccess) { cudaGetLastError(); map_ok = false; }
+  for (int k = 0; k < ns && map_ok; ++k) {
+    Seg& s = segs[k];
     if (!s.bytes) continue;
-    const void* src = s.host;
-    if (!s.pinned) { memcpy(hs + s.off, s.host, s.bytes); src = hs + s.off; }
-    CK(cudaMemcpyAsync(ds + s.off, src, s.bytes, cudaMemcpyHostToDevice, st));
+    if (s.pinned) {
+      if (cudaHostGetDevicePointer(&s.mapped, s.host, 0) != cudaSuccess) { cudaGetLastError(); map_ok = false; }
+    } else {
+      s.mapped = hs_dev + s.off;
+    }
   }
-  auto dp = [&](const Seg& s) -> char* { return s.bytes ? ds + s.off : nullptr; };
-  int rc = jmpc_step(h, B, T, (const double*)dp(s_state), (const int*)dp(s_cid), (const int*)dp(s_clen), (int*)dp(s_tgt),
-                     (const int*)dp(s_warm), (double*)dp(s_oa), (double*)dp(s_od), (const double*)dp(s_params),
-                     (double*)dp(s_ox), (double*)dp(s_oy), (double*)dp(s_ov), (double*)dp(s_oyaw), (double*)dp(s_xref),
-                     (double*)dp(s_cost), (int*)dp(s_status), (int*)dp(s_iters), (double*)dp(s_rec), (void*)st);
+  const bool zc_out = map_ok, zc_in = map_ok && mode >= 2;
+  // failed instances keep the in-out values
+  const bool same_oa = (oa_out == oa_in), same_od = (od_out == od_in), same_tgt = (target_out == target_in);
+  // ---- inputs
+  if (zc_in) {
+    for (int k = 0; k < first_out; ++k)
+      if (segs[k].bytes && !segs[k].pinned) memcpy(hs + segs[k].off, segs[k].host, segs[k].bytes);
+  } else {
+    bool any_pinned_in = false;
+    for (int k = 0; k < first_out; ++k) any_pinned_in = any_pinned_in || (segs[k].bytes && segs[k].pinned);
+    if (!any_pinned_in) {
+      for (int k = 0; k < first_out; ++k)
+        if (segs[k].bytes) memcpy(hs + segs[k].off, segs[k].host, segs[k].bytes);
+      CK(cudaMemcpyAsync(ds, hs, in_end, cudaMemcpyHostToDevice, st));
+    } else {
+      for (int k = 0; k < first_out; ++k) {
+        const Seg& s = segs[k];
+        if (!s.bytes) continue;
+        const void* src = s.host;
+        if (!s.pinned) { memcpy(hs + s.off, s.host, s.bytes); src = hs + s.off; }
+        CK(cudaMemcpyAsync(ds + s.off, src, s.bytes, cudaMemcpyHostToDevice, st));
+      }
+    }
+  }
+  // pre-fill of the result side of the in-out arrays (host memory the kernel stores into, or d_stage)
+  auto prefill = [&](const Seg& out, const Seg& in, bool same) -> int {
+    if (same) {
+      // one array for both directions: zero-copy keeps the values in place; the staged path must seed d_stage
+      if (!zc_out) CK(cudaMemcpyAsync(ds + out.off, ds + in.off, in.bytes, cudaMemcpyDeviceToDevice, st));
+      else if (!out.pinned) memcpy(hs + out.off, in.host, in.bytes);
+      return 0;
+    }
+    if (zc_out) memcpy(out.pinned ? out.host : (void*)(hs + out.off), in.host, in.bytes);
+    else CK(cudaMemcpyAsync(ds + out.off, ds + in.off, in.bytes, cudaMemcpyDeviceToDevice, st));     // staged: inputs are in d_stage
+    return 0;
+  };
+  if (prefill(s_oa, s_oa_in, same_oa) || prefill(s_od, s_od_in, same_od) || prefill(s_tgt, s_tgt_in, same_tgt)) return -1;
+  auto rp = [&](const Seg& s) -> char* { return s.bytes ? (zc_in ? (char*)s.mapped : ds + s.off) : nullptr; };    // read side
+  auto wp = [&](const Seg& s) -> char* { return s.bytes ? (zc_out ? (char*)s.mapped : ds + s.off) : nullptr; };   // write side
+  int rc = launch_step(h, B, T, (const double*)rp(s_state), (const int*)rp(s_cid), (const int*)rp(s_clen),
+                       (const int*)rp(s_tgt_in), (int*)wp(s_tgt), (const int*)rp(s_warm), (const double*)rp(s_oa_in),
+                       (const double*)rp(s_od_in), (double*)wp(s_oa), (double*)wp(s_od), (const double*)rp(s_params),
+                       (double*)wp(s_ox), (double*)wp(s_oy), (double*)wp(s_ov), (double*)wp(s_oyaw), (double*)wp(s_xref),
+                       (double*)wp(s_cost), (int*)wp(s_status), (int*)wp(s_iters), (double*)wp(s_rec), st);
   if (rc) return rc;
-  // device -> host.  Instances that fail the index rule or are infeasible keep their input values in the in-out
-  // arrays, so copying those back wholesale is safe.
-  for (int k = first_inout; k < ns; ++k) {
-    const Seg& s = segs[k];
-    if (!s.bytes) continue;
-    CK(cudaMemcpyAsync(s.pinned ? s.host : (void*)(hs + s.off), ds + s.off, s.bytes, cudaMemcpyDeviceToHost, st));
+  // ---- results
+  if (!zc_out) {
+    for (int k = first_out; k < ns; ++k) {
+      const Seg& s = segs[k];
+      if (!s.bytes) continue;
+      CK(cudaMemcpyAsync(s.pinned ? s.host : (void*)(hs + s.off), ds + s.off, s.bytes, cudaMemcpyDeviceToHost, st));
+    }
   }
   CK(cudaStreamSynchronize(st));
-  for (int k = first_inout; k < ns; ++k) {
+  for (int k = first_out; k < ns; ++k) {
     const Seg& s = segs[k];
     if (s.bytes && !s.pinned) memcpy(s.host, hs + s.off, s.bytes);
   }

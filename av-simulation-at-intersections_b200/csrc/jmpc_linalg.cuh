@@ -19,6 +19,17 @@
 
 namespace jmpc {
 
+// Unrolling of the block-column loops (experiments: -DJMPC_UNROLL_J=1 keeps them rolled, which shrinks the solver loop's
+// code at the price of run-time tile offsets)
+#ifndef JMPC_UNROLL_J
+#define JMPC_UNROLL_J 0
+#endif
+#if JMPC_UNROLL_J > 0
+#define JMPC_PRAGMA_J _Pragma("unroll 1")
+#else
+#define JMPC_PRAGMA_J
+#endif
+
 constexpr int kTS = 18;                               // doubles per tile slot
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -63,6 +74,7 @@ __device__ inline void chol_lut_build(unsigned short* lut, int nb, int tid, int 
 // either way.
 __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, const unsigned short* lut) {
   bool all_clean = true;
+  JMPC_PRAGMA_J
   for (int J = 0; J < nb; ++J) {
     // ---- diagonal block: every lane factors it redundantly in registers (no broadcast needed)
     const double* D = K + tile_off(J, J);
@@ -150,6 +162,7 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
 // Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).
 __device__ inline void solve_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
   const int n4 = nb << 2;
+  JMPC_PRAGMA_J
   for (int J = 0; J < nb; ++J) {                      // forward: L y = b
     const double* Mw = Dinv + (J << 4);
     double b0, b1, b2, b3;
@@ -168,6 +181,7 @@ __device__ inline void solve_tiles(const double* K, const double* Dinv, double* 
     if (lane == 0) st4(b + (J << 2), y0, y1, y2, y3);
     __syncwarp();
   }
+  JMPC_PRAGMA_J
   for (int J = nb - 1; J >= 0; --J) {                 // backward: L' x = y
     const double* Mw = Dinv + (J << 4);
     double y0, y1, y2, y3;

@@ -39,8 +39,10 @@ struct StepArgs {
   const double* state; const int* course_id; const int* course_len; const int* warm;
   const double* params;     // [B][NPARAM] or nullptr
   double defaults[JMPC_NPARAM];
-  // in-out / outputs
-  int* target_ind; double* oa; double* od;
+  // in-out: read from target_ind / oa / od, written to the *_out twins (the same arrays for jmpc_step; the host
+  // entry point reads device copies and writes page-locked host memory directly)
+  const int* target_ind; const double* oa; const double* od;
+  int* target_out; double* oa_out; double* od_out;
   double* ox; double* oy; double* ov; double* oyaw; double* xref; double* cost; int* status; int* iters;
   double* record;           // [B][JMPC_RECORD_LEN] or nullptr
   // fused all-gather: the epilogue also stores the record into every peer GPU's gathered table (NVLink peer
@@ -491,7 +493,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
         xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = vr; xo[3 * T1 + lane] = psir;
       }
       if (lane == 0) {
-        A.status[b] = status; A.target_ind[b] = target; if (A.iters) A.iters[b] = total_iters;
+        A.status[b] = status; A.target_out[b] = target; if (A.iters) A.iters[b] = total_iters;
         A.cost[b] = nan("");
         write_record(A, b, nan(""), P(JMPC_P_MAX_DECEL), nan(""), status, target, total_iters, nan(""), nan(""));
       }
@@ -751,7 +753,7 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
       const double a_next = __shfl_down_sync(kFull, a_sol, 1), d_next = __shfl_down_sync(kFull, d_sol, 1);
       if (lane < T - 1) cterm += Rda * (a_next - a_sol) * (a_next - a_sol) + Rdd * (d_next - d_sol) * (d_next - d_sol);
       const double cost = warp_sum(cterm);
-      if (lane < T) { A.oa[(size_t)b * T + lane] = a_sol; A.od[(size_t)b * T + lane] = d_sol; }
+      if (lane < T) { A.oa_out[(size_t)b * T + lane] = a_sol; A.od_out[(size_t)b * T + lane] = d_sol; }
       if (lane <= T) {
         A.ox[(size_t)b * T1 + lane] = X_t; A.oy[(size_t)b * T1 + lane] = Y_t;
         A.ov[(size_t)b * T1 + lane] = v_t; A.oyaw[(size_t)b * T1 + lane] = psi_t;
@@ -760,7 +762,7 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
       }
       const double v1 = __shfl_sync(kFull, v_t, 1), yaw1 = __shfl_sync(kFull, psi_t, 1);
       if (lane == 0) {
-        A.cost[b] = cost; A.status[b] = status; A.target_ind[b] = target;
+        A.cost[b] = cost; A.status[b] = status; A.target_out[b] = target;
         if (A.iters) A.iters[b] = total_iters;
 #ifdef JMPC_DEBUG_RESID
         write_record(A, b, M.prm[29], a_sol, cost, status, target, total_iters, M.prm[30], M.prm[31]);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "jmpc_set_skip_mask": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "jmpc_set_record_peers": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     "jmpc_step_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 17),
+    "jmpc_step_host_io": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 20),
     "jmpc_host_alloc": (C.c_int32, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "jmpc_host_free": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "jmpc_collision": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -211,6 +211,8 @@ class BatchedMPC:
         return StepOutput(oa_b, od_b, ox, oy, ov, oyaw, xref, cost, status, iters, tgt, record)
 
     def _step_host_into(self, out, T, state, target_ind, oa, od, course_id, course_len, warm, params) -> StepOutput:
+        """Results into the caller's (page-locked) `out`; the inputs are only read.  `oa` / `od` / `target_ind` may be
+        `out`'s own arrays (a closed loop feeding its previous solution back), in which case nothing is copied."""
         state = _f64(state)
         B = state.shape[0]
         if out.oa.shape != (B, T):
@@ -218,19 +220,21 @@ class BatchedMPC:
         if oa is None or od is None:
             out.oa[...] = 0.0
             out.od[...] = 0.0
+            oa_in, od_in = out.oa, out.od
             warm = np.zeros(B, np.int32)
         else:
-            np.copyto(out.oa, oa)
-            np.copyto(out.od, od)
-        np.copyto(out.target_ind, target_ind)
+            oa_in = oa if oa is out.oa else _f64(oa, (B, T))
+            od_in = od if od is out.od else _f64(od, (B, T))
+        tgt_in = target_ind if target_ind is out.target_ind else _i32(target_ind, (B,))
         cid = None if course_id is None else _i32(course_id, (B,))
         clen = None if course_len is None else _i32(course_len, (B,))
         wrm = None if warm is None else _i32(warm, (B,))
         prm = None if params is None else _f64(params, (B, NPARAM))
-        _cabi.check(self._lib.jmpc_step_host(self._h, B, T, _ptr(state), _ptr(cid), _ptr(clen), _ptr(out.target_ind),
-                                             _ptr(wrm), _ptr(out.oa), _ptr(out.od), _ptr(prm), _ptr(out.ox), _ptr(out.oy),
-                                             _ptr(out.ov), _ptr(out.oyaw), _ptr(out.xref), _ptr(out.cost),
-                                             _ptr(out.status), _ptr(out.iters), _ptr(out.record)), "jmpc_step_host")
+        _cabi.check(self._lib.jmpc_step_host_io(
+            self._h, B, T, _ptr(state), _ptr(cid), _ptr(clen), _ptr(tgt_in), _ptr(wrm), _ptr(oa_in), _ptr(od_in),
+            _ptr(prm), _ptr(out.target_ind), _ptr(out.oa), _ptr(out.od), _ptr(out.ox), _ptr(out.oy), _ptr(out.ov),
+            _ptr(out.oyaw), _ptr(out.xref), _ptr(out.cost), _ptr(out.status), _ptr(out.iters), _ptr(out.record)),
+            "jmpc_step_host_io")
         return out
 
     def collision_host(self, agent_idx, v, obstacles, frame_window: int, margin: int, course_id=None,

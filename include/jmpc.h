@@ -10,8 +10,9 @@
  * Memory convention
  *   - `jmpc_step` / `jmpc_collision` take DEVICE pointers (e.g. torch tensors' data_ptr()) and only enqueue
  *     work on `stream`; they never synchronise.
- *   - `jmpc_step_host` / `jmpc_collision_host` take HOST pointers, stage through pinned buffers owned by the
- *     handle, run the same kernels and return after the results are back on the host.
+ *   - `jmpc_step_host[_io]` / `jmpc_collision_host` take HOST pointers, run the same kernels and return after the
+ *     results are on the host (step: the kernel accesses page-locked host memory directly; collision: staged
+ *     through pinned buffers owned by the handle).
  *   - Arrays are instance-major ("batch first"), float64 / int32, densely packed:
  *       state      [B][4]         x, y, v, yaw            (main/lib/mpc.py:291)
  *       oa, od     [B][T]         accelerations / steering angles; in: previous solution (the linearisation
@@ -139,11 +140,26 @@ int32_t jmpc_set_skip_mask(jmpc_handle h, const int32_t* skip);
  * tables.  n_peers = 0 switches it off. */
 int32_t jmpc_set_record_peers(jmpc_handle h, int32_t n_peers, const uint64_t* peer_tables, int64_t rank_offset);
 
-/* Same with HOST pointers: copies in, runs, copies out, synchronises. */
+/* Same with HOST pointers: runs the step and returns when the results are in the host arrays.  By default no copy
+ * engine is involved: the kernel reads the inputs from and stores the results into page-locked host memory through
+ * its device mapping -- the caller's arrays where they are page-locked (jmpc_host_alloc), the handle's staging block
+ * otherwise (one host memcpy per such array).  Environment JMPC_ZEROCOPY=1 copies the inputs with cudaMemcpyAsync,
+ * =0 stages both directions through device memory. */
 int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
                        double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
                        double* xref, double* cost, int32_t* status, int32_t* iters, double* record);
+
+/* jmpc_step_host with separate read and write arrays for the in-out quantities: the previous solution and search
+ * start are read from target_in / oa_in / od_in (never written), the new ones go to target_out / oa_out / od_out
+ * (which receive the input values for instances that are not solved).  *_out may alias *_in, which is exactly
+ * jmpc_step_host.  A controller that keeps its warm start (mpc.py:293-296) in one place and its outputs in another
+ * (fresh arrays each step, mpc.py:199-205) saves a copy per step this way. */
+int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
+                          const int32_t* course_len, const int32_t* target_in, const int32_t* warm,
+                          const double* oa_in, const double* od_in, const double* params, int32_t* target_out,
+                          double* oa_out, double* od_out, double* ox, double* oy, double* ov, double* oyaw,
+                          double* xref, double* cost, int32_t* status, int32_t* iters, double* record);
 
 /* Page-locked host memory for the *_host entry points: arrays placed in it are transferred without the staging
  * memcpy (any page-locked memory is recognised, e.g. cudaHostAlloc or torch pin_memory). */

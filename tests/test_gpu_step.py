@@ -239,6 +239,44 @@ def test_pinned_host_outputs_equal_plain_host_path(jm):
     assert np.array_equal(got.record[:, 3], got.status) and np.array_equal(got.record[:, 4], got.target_ind)
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_host_transfer_modes_agree(jm, mode, monkeypatch):
+    """jmpc_step_host[_io]: staged DMA (0), zero-copy results (1), zero-copy both ways (2, default) give the same
+    arrays, for pageable and page-locked callers, including instances that are not solved (in-out values kept)."""
+    synth, BatchedMPC = jm
+    w = synth.make_workload(2, B=130)
+    state = w["state"].copy()
+    state[3, 2] = 30.0            # v0 above the speed cap -> infeasible (status 2)
+    monkeypatch.setenv("JMPC_ZEROCOPY", "0")
+    mpc = BatchedMPC(w["courses"], dl=w["dl"], T=w["T"], max_batch=256)
+    ref = mpc.step_host(state, w["target_ind"], w["oa"], w["od"], course_len=w["course_len"])
+    assert ref.status[3] == 2 and np.array_equal(ref.oa[3], w["oa"][3])
+    monkeypatch.setenv("JMPC_ZEROCOPY", mode)
+    keys = ["oa", "od", "cost", "status", "iters", "target_ind", "record"]
+    solved = ref.status == 0
+    def same(got):
+        for key in keys:
+            assert np.array_equal(getattr(got, key), getattr(ref, key), equal_nan=True), (mode, key)
+        for key in ["ox", "oy", "ov", "oyaw"]:           # only defined for solved instances
+            assert np.array_equal(getattr(got, key)[solved], getattr(ref, key)[solved]), (mode, key)
+        assert np.array_equal(got.xref, ref.xref), mode
+    same(mpc.step_host(state, w["target_ind"], w["oa"], w["od"], course_len=w["course_len"]))          # pageable
+    out = mpc.host_outputs(130)
+    same(mpc.step_host(state, w["target_ind"], w["oa"], w["od"], course_len=w["course_len"], out=out))   # pinned results
+    pin = {k: mpc.pinned_empty(v.shape, v.dtype) for k, v in
+           dict(state=state, target_ind=w["target_ind"], oa=w["oa"], od=w["od"], course_len=w["course_len"]).items()}
+    for k, v in dict(state=state, target_ind=w["target_ind"], oa=w["oa"], od=w["od"], course_len=w["course_len"]).items():
+        pin[k][...] = v
+    same(mpc.step_host(pin["state"], pin["target_ind"], pin["oa"], pin["od"], course_len=pin["course_len"], out=out))
+    assert np.array_equal(pin["oa"], w["oa"]) and np.array_equal(pin["target_ind"], w["target_ind"])     # inputs only read
+    # closed loop on one set of arrays: the previous results are the next inputs, nothing is copied
+    nxt_ref = mpc.step_host(state, ref.target_ind, ref.oa, ref.od, course_len=w["course_len"])
+    got = mpc.step_host(pin["state"], out.target_ind, out.oa, out.od, course_len=pin["course_len"], out=out)
+    for key in keys:
+        assert np.array_equal(getattr(got, key), getattr(nxt_ref, key), equal_nan=True), (mode, key)
+    mpc.close()
+
+
 def test_fused_record_stores_reach_the_peer_tables(jm):
     """The kernel-epilogue all-gather on one GPU: two 'peer' tables that both live on this device."""
     import torch
