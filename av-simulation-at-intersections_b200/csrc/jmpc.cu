@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/jmpc.h"
@@ -61,6 +62,8 @@ struct jmpc_handle_s {
   long long rank_offset = 0;
   bool collision_attr_set = false;
   const int* skip = nullptr;           // jmpc_set_skip_mask
+  struct HostBlock { char* base; size_t bytes; char* dev; };
+  std::vector<HostBlock> host_blocks;   // page-locked blocks from jmpc_host_alloc (+ h_stage) with their device mapping
 };
 
 namespace {
@@ -308,6 +311,9 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
   jmpc::StepArgs a;
   a.B = B; a.T = T; a.lin_iters = h->opt.linearisation_iters; a.max_iters = h->opt.max_solver_iters;
   a.mu_tol = h->opt.mu_tol;
+  a.tol_res = 1e-9; a.init_mu = 0.0;
+  if (const char* e = getenv("JMPC_TOL_RES")) a.tol_res = atof(e);          // solver experiments (tests/tools/tune_solver.py)
+  if (const char* e = getenv("JMPC_INIT_MU")) a.init_mu = atof(e);
   a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
   a.course_stride = h->course_stride; a.n_courses = h->n_courses;
   a.state = state; a.course_id = course_id; a.course_len = course_len; a.warm = warm; a.params = params;
@@ -347,20 +353,34 @@ int32_t jmpc_host_alloc(jmpc_handle h, size_t bytes, void** out) {
   if (!h || !out) return fail("jmpc_host_alloc: NULL argument");
   CK(cudaSetDevice(h->device));
   CK(cudaMallocHost(out, bytes ? bytes : 1));
+  void* dev = nullptr;
+  if (cudaHostGetDevicePointer(&dev, *out, 0) != cudaSuccess) { cudaGetLastError(); dev = nullptr; }
+  if (dev) h->host_blocks.push_back({(char*)*out, bytes ? bytes : 1, (char*)dev});
   return 0;
 }
 
 int32_t jmpc_host_free(jmpc_handle h, void* p) {
   if (!h) return fail("jmpc_host_free: NULL handle");
-  if (p) CK(cudaFreeHost(p));
+  if (p) {
+    for (size_t k = 0; k < h->host_blocks.size(); ++k)
+      if (h->host_blocks[k].base == (char*)p) { h->host_blocks.erase(h->host_blocks.begin() + k); break; }
+    CK(cudaFreeHost(p));
+  }
   return 0;
 }
 
 namespace {
-bool is_pinned(const void* p) {
+// Page-locked?  If so `mapped` receives the device-side address.  Blocks handed out by jmpc_host_alloc are recognised
+// from the handle's own list (no driver call: cudaPointerGetAttributes costs ~1.5 us, twenty of them per step add up).
+bool is_pinned(jmpc_handle h, const void* p, void** mapped) {
+  const char* c = (const char*)p;
+  for (const auto& r : h->host_blocks)
+    if (c >= r.base && c < r.base + r.bytes) { *mapped = r.dev + (c - r.base); return true; }
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return at.type == cudaMemoryTypeHost;
+  if (at.type != cudaMemoryTypeHost) return false;
+  *mapped = at.devicePointer;
+  return true;
 }
 }  // namespace
 
@@ -405,27 +425,31 @@ int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* sta
   const size_t T1 = T + 1, b = (size_t)B;
   // Staging block layout [inputs | outputs], the same offsets on the device (d_stage) and in the handle's
   // page-locked host block (h_stage).  Transfer modes (JMPC_ZEROCOPY, default 2):
-  //   2  no copy engine at all.  The kernel reads its inputs from, and stores its results into, page-locked host
-  //      memory through the device mapping (unified addressing): the caller's own array where that is page-locked
-  //      (jmpc_host_alloc, cudaHostAlloc, torch pin_memory), the h_stage slot otherwise (one host memcpy on that
-  //      side).  A warp reads ~0.4 KB when it picks an instance up and writes ~1.7 KB when it is done; both ride
-  //      under the other warps' solves, and at ~6 GB/s of results the PCIe link is far from saturated, so the
-  //      transfers leave the critical path.
-  //   1  inputs by cudaMemcpyAsync into d_stage, results stored directly into host memory as above.
+  //   1  (default) inputs by cudaMemcpyAsync into d_stage; the kernel stores its results directly into page-locked
+  //      host memory through the device mapping (unified addressing): the caller's own array where that is
+  //      page-locked (jmpc_host_alloc, cudaHostAlloc, torch pin_memory), the h_stage slot otherwise (one host
+  //      memcpy).  A warp writes ~1.7 KB when it is done with an instance; the stores ride under the other warps'
+  //      solves, and at ~6 GB/s of results the PCIe link is far from saturated, so the device -> host transfer
+  //      leaves the critical path (measured: 1.61 -> 1.43 ms per 4096-instance step).
+  //   2  the kernel also reads its inputs from page-locked host memory (no copy engine at all).  Measured slower
+  //      than 1: every warp waits a PCIe round trip when it picks an instance up (kernel 1.24 -> 1.30 ms).
   //   0  staged DMA both ways (results to d_stage, cudaMemcpyAsync back).
-  // Instances that fail the index rule or are infeasible leave oa_out / od_out / target_out untouched; these are
-  // pre-filled with the inputs when they are different arrays, so "in-out arrays keep their values" holds.
+  // Instances that fail the index rule or are infeasible get their input values in oa_out / od_out / target_out
+  // (the kernel carries them over), so "in-out arrays keep their values" holds whether or not the arrays alias.
   struct Seg { size_t off, bytes; void* host; bool pinned; void* mapped; };
   size_t off = 0;
   Seg segs[20];
   int ns = 0;
+  const bool timing = getenv("JMPC_TIMING") != nullptr;                 // host-side breakdown on stderr
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = timing ? now() : 0.0;
   const char* mode_env = getenv("JMPC_ZEROCOPY");       // read per call: tests switch it
-  const int mode = mode_env ? atoi(mode_env) : 2;
+  const int mode = mode_env ? atoi(mode_env) : 1;
   auto seg = [&](size_t bytes, const void* host) -> Seg& {
     Seg& s = segs[ns++];
     s.off = off; s.bytes = host ? bytes : 0; s.host = const_cast<void*>(host);
-    s.pinned = host ? is_pinned(host) : false;
     s.mapped = nullptr;
+    s.pinned = host ? is_pinned(h, host, &s.mapped) : false;
     off += (s.bytes + 15) & ~size_t(15);
     return s;
   };
@@ -462,15 +486,10 @@ int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* sta
   for (int k = 0; k < ns && map_ok; ++k) {
     Seg& s = segs[k];
     if (!s.bytes) continue;
-    if (s.pinned) {
-      if (cudaHostGetDevicePointer(&s.mapped, s.host, 0) != cudaSuccess) { cudaGetLastError(); map_ok = false; }
-    } else {
-      s.mapped = hs_dev + s.off;
-    }
+    if (s.pinned) { if (!s.mapped) map_ok = false; }
+    else s.mapped = hs_dev + s.off;
   }
   const bool zc_out = map_ok, zc_in = map_ok && mode >= 2;
-  // failed instances keep the in-out values
-  const bool same_oa = (oa_out == oa_in), same_od = (od_out == od_in), same_tgt = (target_out == target_in);
   // ---- inputs
   if (zc_in) {
     for (int k = 0; k < first_out; ++k)
@@ -492,27 +511,19 @@ int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* sta
       }
     }
   }
-  // pre-fill of the result side of the in-out arrays (host memory the kernel stores into, or d_stage)
-  auto prefill = [&](const Seg& out, const Seg& in, bool same) -> int {
-    if (same) {
-      // one array for both directions: zero-copy keeps the values in place; the staged path must seed d_stage
-      if (!zc_out) CK(cudaMemcpyAsync(ds + out.off, ds + in.off, in.bytes, cudaMemcpyDeviceToDevice, st));
-      else if (!out.pinned) memcpy(hs + out.off, in.host, in.bytes);
-      return 0;
-    }
-    if (zc_out) memcpy(out.pinned ? out.host : (void*)(hs + out.off), in.host, in.bytes);
-    else CK(cudaMemcpyAsync(ds + out.off, ds + in.off, in.bytes, cudaMemcpyDeviceToDevice, st));     // staged: inputs are in d_stage
-    return 0;
-  };
-  if (prefill(s_oa, s_oa_in, same_oa) || prefill(s_od, s_od_in, same_od) || prefill(s_tgt, s_tgt_in, same_tgt)) return -1;
   auto rp = [&](const Seg& s) -> char* { return s.bytes ? (zc_in ? (char*)s.mapped : ds + s.off) : nullptr; };    // read side
   auto wp = [&](const Seg& s) -> char* { return s.bytes ? (zc_out ? (char*)s.mapped : ds + s.off) : nullptr; };   // write side
+  const double t_prep = timing ? now() : 0.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (timing) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
   int rc = launch_step(h, B, T, (const double*)rp(s_state), (const int*)rp(s_cid), (const int*)rp(s_clen),
                        (const int*)rp(s_tgt_in), (int*)wp(s_tgt), (const int*)rp(s_warm), (const double*)rp(s_oa_in),
                        (const double*)rp(s_od_in), (double*)wp(s_oa), (double*)wp(s_od), (const double*)rp(s_params),
                        (double*)wp(s_ox), (double*)wp(s_oy), (double*)wp(s_ov), (double*)wp(s_oyaw), (double*)wp(s_xref),
                        (double*)wp(s_cost), (int*)wp(s_status), (int*)wp(s_iters), (double*)wp(s_rec), st);
   if (rc) return rc;
+  if (timing) cudaEventRecord(ev1, st);
+  const double t_launch = timing ? now() : 0.0;
   // ---- results
   if (!zc_out) {
     for (int k = first_out; k < ns; ++k) {
@@ -522,9 +533,17 @@ int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* sta
     }
   }
   CK(cudaStreamSynchronize(st));
+  const double t_sync = timing ? now() : 0.0;
   for (int k = first_out; k < ns; ++k) {
     const Seg& s = segs[k];
     if (s.bytes && !s.pinned) memcpy(s.host, hs + s.off, s.bytes);
+  }
+  if (timing) {
+    float kms = 0.f;
+    cudaEventElapsedTime(&kms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    fprintf(stderr, "[jmpc] step_host B=%d mode=%d: prep %.1f us, launch %.1f us, wait %.1f us (kernel %.1f us by events), post %.1f us\n",
+            B, mode, t_prep - t_begin, t_launch - t_prep, t_sync - t_launch, kms * 1e3, now() - t_sync);
   }
   return 0;
 }

@@ -32,6 +32,8 @@ struct StepArgs {
   int lin_iters;            // MAX_ITER of the reference config
   int max_iters;            // interior-point iteration cap
   double mu_tol;
+  double tol_res;           // primal / (scaled) dual residual tolerance of the strict exit
+  double init_mu;           // > 0: centred start lambda = init_mu / s ; 0: lambda = 1
   // course tables
   const double* cx; const double* cy; const double* cyaw;
   const int* course_n; int course_stride; int n_courses;
@@ -141,6 +143,14 @@ __device__ __forceinline__ void write_record(const StepArgs& A, int b, double r0
     double2* rec = reinterpret_cast<double2*>(A.peer_rec[p] + ((size_t)A.rank_offset + b) * JMPC_RECORD_LEN);
     rec[0] = make_double2(r0, r1); rec[1] = make_double2(r2, r3); rec[2] = make_double2(r4, r5); rec[3] = make_double2(r6, r7);
   }
+}
+
+// An instance that is not solved keeps its in-out values: when the write side is a different array (host entry
+// points) they are carried over here.
+__device__ __forceinline__ void carry_inout(const StepArgs& A, int b, int T, int lane) {
+  if (A.oa_out != A.oa && lane < T) A.oa_out[(size_t)b * T + lane] = A.oa[(size_t)b * T + lane];
+  if (A.od_out != A.od && lane < T) A.od_out[(size_t)b * T + lane] = A.od[(size_t)b * T + lane];
+  if (A.target_out != A.target_ind && lane == 0) A.target_out[b] = A.target_ind[b];
 }
 
 // ---- candidate list for the 3-nearest rule: ascending by (d2, index) --------------------------------
@@ -284,6 +294,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
     // ---------------- 1. nearest index --------------------------------------------------------------
     const int near = nearest_index(cx, cy, n_course, target, x0, y0, lane);
     if (near < 0) {
+      carry_inout(A, b, T, lane);
       if (lane == 0) {
         A.status[b] = JMPC_INDEX_RULE; if (A.iters) A.iters[b] = total_iters;
         write_record(A, b, nan(""), nan(""), nan(""), JMPC_INDEX_RULE, A.target_ind[b], total_iters, nan(""), nan(""));
@@ -487,6 +498,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
     // feasibility predicate: the t = 0 speed rows act on the fixed v0
     if (!(min_speed <= v0 && v0 <= speed)) {
       const int status = JMPC_INFEASIBLE;
+      carry_inout(A, b, T, lane);
       // xref / target are still reported, as the reference assigns them before the solve result
       if (lane <= T) {
         double* xo = A.xref + (size_t)b * 4 * T1;
@@ -531,7 +543,8 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       sh[r] = fmax(bound_hi(r), 1e-2); sl[r] = fmax(-bound_lo(r), 1e-2);      // u = 0 -> A u = 0
-      lh[r] = is_live(r) ? 1.0 : 0.0; ll[r] = lh[r];
+      if (A.init_mu > 0.0) { lh[r] = is_live(r) ? A.init_mu / sh[r] : 0.0; ll[r] = is_live(r) ? A.init_mu / sl[r] : 0.0; }
+      else { lh[r] = is_live(r) ? 1.0 : 0.0; ll[r] = lh[r]; }
     }
     const double inv_rows = 1.0 / (double)(2 * (4 * T - 1));
     double gscale = 0.0;
@@ -608,12 +621,12 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       }
       rdmax = warp_max(rdmax);
       __syncwarp();
-      if (mu <= A.mu_tol && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) { converged = true; break; }
+      if (mu <= A.mu_tol && rpmax <= A.tol_res && rdmax <= A.tol_res * gscale) { converged = true; break; }
       // Complementarity three orders below its target with the primal rows satisfied: the iterate has converged;
       // what is left in the dual residual is multiplier noise on the active rows (w ~ 1e16 by now, their slacks are
       // at roundoff), which lies in the span of the active normals and does not move u.  Iterating further only
       // amplifies it.  Measured on 200k instances: controls at such exits are within 1e-8 of the oracle.
-      if (mu <= 1e-3 * A.mu_tol && rpmax <= 1e-9) { converged = true; break; }
+      if (mu <= 1e-3 * A.mu_tol && rpmax <= A.tol_res) { converged = true; break; }
       // Reduced tolerances, the analogue of the OPTIMAL_INACCURATE status the reference accepts (mpc.py:199): used
       // when the factorisation breaks down numerically a step or two before the strict target (w ~ 1e13 by then),
       // or the iteration cap is hit.  Measured: such iterates are still 5-6x inside the control tolerance.

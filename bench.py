@@ -324,9 +324,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": float(e2e_ms.item()), "steps": e2e_steps,
                 "api": "BatchedMPC.step_host(out=host_outputs) -> jmpc_step_host_io: numpy inputs and results in page-locked host "
-                       "memory; the step kernel reads the inputs and stores the results over PCIe through the arrays' "
-                       "device mapping (no copy-engine transfer, JMPC_ZEROCOPY=2); wall clock around the call, results "
-                       "readable on the host when it returns"},
+                       "memory; inputs copied host->device with cudaMemcpyAsync, results stored by the step kernel "
+                       "straight into the host arrays over PCIe (device mapping of the page-locked memory, no "
+                       "device->host copy pass); wall clock around the call, results readable on the host when it returns"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
