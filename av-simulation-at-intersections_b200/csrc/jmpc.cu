@@ -62,6 +62,10 @@ struct jmpc_handle_s {
   long long rank_offset = 0;
   bool collision_attr_set = false;
   const int* skip = nullptr;           // jmpc_set_skip_mask
+  // longest-first scheduling (jmpc_set_schedule)
+  int schedule = 0;                     // 0 index order, 1 a-priori key, 2 previous step's iteration counts (+ 1 as fallback)
+  int* d_order = nullptr; int* d_hint = nullptr;
+  int hint_B = 0, hint_T = 0;           // batch the hints were recorded for (0 = none)
   struct HostBlock { char* base; size_t bytes; char* dev; };
   std::vector<HostBlock> host_blocks;   // page-locked blocks from jmpc_host_alloc (+ h_stage) with their device mapping
 };
@@ -259,7 +263,7 @@ int32_t jmpc_destroy(jmpc_handle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_cx); cudaFree(h->d_cy); cudaFree(h->d_cyaw); cudaFree(h->d_course_n);
   cudaFree(h->d_ccfx); cudaFree(h->d_ccfy); cudaFree(h->d_ccrx); cudaFree(h->d_ccry);
-  cudaFree(h->d_pscratch); cudaFree(h->d_counter); cudaFree(h->d_stage);
+  cudaFree(h->d_pscratch); cudaFree(h->d_counter); cudaFree(h->d_stage); cudaFree(h->d_order); cudaFree(h->d_hint);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -325,6 +329,25 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
   a.n_peers = h->n_peers; a.rank_offset = h->rank_offset; a.skip = h->skip;
   for (int p = 0; p < JMPC_MAX_PEERS; ++p) a.peer_rec[p] = h->peer_rec[p];
   a.pscratch = h->d_pscratch; a.counter = h->d_counter;
+  a.order = nullptr; a.work_hint = nullptr;
+  if (h->schedule > 0) {
+    if (!h->d_order) {
+      CK(cudaMalloc(&h->d_order, (size_t)h->max_B * sizeof(int)));
+      CK(cudaMalloc(&h->d_hint, (size_t)h->max_B * sizeof(int)));
+      CK(cudaMemsetAsync(h->d_hint, 0, (size_t)h->max_B * sizeof(int), s));
+    }
+    // ordering only matters while the batch is a few waves of the resident warps deep
+    if (B > g.warps && B <= 16 * g.warps) {
+      const bool have_hint = h->schedule >= 2 && h->hint_B == B && h->hint_T == T;
+      jmpc::ParamVec dv;
+      memcpy(dv.v, h->defaults, sizeof dv.v);
+      jmpc::schedule_kernel<<<1, 1024, 0, s>>>(B, T, have_hint ? h->d_hint : nullptr, state, params, dv, h->d_order);
+      CK(cudaGetLastError());
+      h->launches++;
+      a.order = h->d_order;
+    }
+    if (h->schedule >= 2) { a.work_hint = h->d_hint; h->hint_B = B; h->hint_T = T; }
+  }
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
   step_kernel_for(T)<<<g.blocks, g.threads, g.smem, s>>>(a);
   CK(cudaGetLastError());
@@ -383,6 +406,19 @@ bool is_pinned(jmpc_handle h, const void* p, void** mapped) {
   return true;
 }
 }  // namespace
+
+int32_t jmpc_set_schedule(jmpc_handle h, int32_t mode) {
+  if (!h) return fail("jmpc_set_schedule: NULL handle");
+  if (mode < 0 || mode > 2) return fail("jmpc_set_schedule: mode must be 0, 1 or 2");
+  h->schedule = mode; h->hint_B = 0; h->hint_T = 0;
+  return 0;
+}
+
+int32_t jmpc_reset_schedule_hints(jmpc_handle h) {
+  if (!h) return fail("jmpc_reset_schedule_hints: NULL handle");
+  h->hint_B = 0; h->hint_T = 0;
+  return 0;
+}
 
 int32_t jmpc_set_skip_mask(jmpc_handle h, const int32_t* skip) {
   if (!h) return fail("jmpc_set_skip_mask: NULL handle");

@@ -59,7 +59,7 @@ class BatchedMPC:
                  config: Optional[MPCConfig] = None, dt: float = 0.2, L: float = 2.86, speed: float = 30.0 / 3.6,
                  max_batch: int = 1 << 20, device: int = 0, max_solver_iters: int = 40,
                  linearisation_iters: Optional[int] = None, mu_tol: float = 1e-13, warps_per_sm: int = 0,
-                 max_T: Optional[int] = None):
+                 max_T: Optional[int] = None, schedule: str = "history"):
         """courses: list of (N_c, >=3) arrays [x, y, yaw(smoothed)]."""
         self._lib = _cabi.load()
         cfg = config or MPCConfig.default()
@@ -81,6 +81,7 @@ class BatchedMPC:
         self._pinned = []
         self._host_out = {}
         self.set_courses(courses)
+        self.set_schedule(schedule)
 
     # ---- configuration ----------------------------------------------------------------------------------
     def set_courses(self, courses: Sequence[np.ndarray]):
@@ -103,6 +104,18 @@ class BatchedMPC:
     def set_car_geometry(self, front_offset: float, rear_offset: float, radius: float):
         _cabi.check(self._lib.jmpc_set_car_geometry(self._h, float(front_offset), float(rear_offset), float(radius)),
                     "jmpc_set_car_geometry")
+
+    SCHEDULES = {"index": 0, "apriori": 1, "history": 2}
+
+    def set_schedule(self, mode: str):
+        """Order of the solver's work queue: "index", "apriori" (longest first by a key computed from the inputs) or
+        "history" (by the iteration count of the same instance index in the previous step, a-priori key when there
+        is none) -- see jmpc_set_schedule in include/jmpc.h."""
+        _cabi.check(self._lib.jmpc_set_schedule(self._h, self.SCHEDULES[mode]), "jmpc_set_schedule")
+        self.schedule = mode
+
+    def reset_schedule_hints(self):
+        _cabi.check(self._lib.jmpc_reset_schedule_hints(self._h), "jmpc_reset_schedule_hints")
 
     def set_skip_mask(self, mask):
         """`mask`: CUDA int32 tensor [B] (kept alive by the caller) or None.  Instances with mask != 0 are skipped by

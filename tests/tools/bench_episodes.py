@@ -8,7 +8,9 @@ from oracle import collision_oracle as C
 course = synth.load_course("intersection")
 dl = float(np.linalg.norm(course[0,:2]-course[1,:2]))
 B=int(sys.argv[1]) if len(sys.argv)>1 else 4096
-engine = BatchedMPC([course], dl=dl, T=13, max_batch=B)
+T=int(sys.argv[2]) if len(sys.argv)>2 else 13
+sched=sys.argv[3] if len(sys.argv)>3 else "history"
+engine = BatchedMPC([course], dl=dl, T=T, max_batch=B, schedule=sched)
 rng=np.random.default_rng(11)
 state0=np.repeat(np.array([[course[0,0],course[0,1],0.0,course[0,2]]]),B,axis=0); state0[:,2]=rng.uniform(0,3,B)
 obst=np.zeros((B,2,6))
@@ -20,5 +22,5 @@ for rep in range(2):
     torch.cuda.synchronize(); t0=time.perf_counter()
     res=ep.run(max_steps=400)
     dt=time.perf_counter()-t0
-print(json.dumps(dict(B=B, wall_s=dt, iterations=res["iterations"], episodes_per_s=B/dt, done=int((res["done"]==1).sum()), index_rule=int((res["done"]==2).sum()),
+print(json.dumps(dict(B=B, T=T, schedule=sched, wall_s=dt, iterations=res["iterations"], episodes_per_s=B/dt, done=int((res["done"]==1).sum()), index_rule=int((res["done"]==2).sum()),
       steps_mean=float(res["steps"].mean()), steps_max=int(res["steps"].max()), control_steps_per_s=float(res["steps"].sum()/dt))))
