@@ -407,6 +407,20 @@ bool is_pinned(jmpc_handle h, const void* p, void** mapped) {
 }
 }  // namespace
 
+int32_t jmpc_debug_cycles(jmpc_handle h, uint64_t* out32, int32_t reset) {
+  if (!h || !out32) return fail("jmpc_debug_cycles: NULL argument");
+#ifdef JMPC_CYCLES
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out32, jmpc::g_cycles, 32 * sizeof(uint64_t)));
+  if (reset) { uint64_t z[32] = {}; CK(cudaMemcpyToSymbol(jmpc::g_cycles, z, sizeof z)); }
+  return 0;
+#else
+  (void)reset;
+  return fail("jmpc_debug_cycles: library built without -DJMPC_CYCLES");
+#endif
+}
+
 int32_t jmpc_set_schedule(jmpc_handle h, int32_t mode) {
   if (!h) return fail("jmpc_set_schedule: NULL handle");
   if (mode < 0 || mode > 2) return fail("jmpc_set_schedule: mode must be 0, 1 or 2");
@@ -742,22 +756,23 @@ int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const doubl
   if (n < 1 || n > 2 * JMPC_MAX_T) return fail("jmpc_debug_linalg: n out of range");
   CK(cudaSetDevice(h->device));
   const size_t nn = (size_t)n * n;
-  if (ensure_stage(h, (nn + 4 * (size_t)n + 2) * sizeof(double))) return -1;
+  if (ensure_stage(h, (nn + 6 * (size_t)n + 2) * sizeof(double))) return -1;
   double* d = (double*)h->d_stage;
-  double *dA = d, *db = dA + nn, *dx = db + n, *dsol = dx + n, *dprod = dsol + n;
-  int* dok = (int*)(dprod + n);
+  double *dA = d, *db = dA + nn, *dx = db + n, *dsol = dx + n, *dprod = dsol + 2 * n;
+  int* dok = (int*)(dprod + 2 * n);
+  CK(cudaMemset(dsol, 0xff, 4 * (size_t)n * sizeof(double)));          // NaN where the kernel writes nothing
   CK(cudaMemcpy(dA, A, nn * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
   const int nb = jmpc::nblk(n);
-  const size_t smem = (jmpc::tiles_doubles(n) + 16 * nb + 8 * nb) * sizeof(double) + (size_t)jmpc::chol_lut_entries(nb) * 2 + 16;
+  const size_t smem = (jmpc::tiles_doubles(n) + 16 * nb + 8 * nb) * sizeof(double) + (size_t)jmpc::chol_lut_entries(nb + 1) * 2 + 16;
   jmpc::linalg_selftest_kernel<<<1, 32, smem, h->own_stream>>>(n, dA, db, dx, dsol, dprod, dok);
   CK(cudaGetLastError());
   h->launches++;
   CK(cudaStreamSynchronize(h->own_stream));
   int ok = 0;
-  CK(cudaMemcpy(sol, dsol, n * sizeof(double), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(prod, dprod, n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sol, dsol, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(prod, dprod, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost));
   return ok ? 0 : 1;
 }

@@ -30,6 +30,18 @@ namespace jmpc {
 #define JMPC_PRAGMA_J
 #endif
 
+// Cycle accounting of a debug build (-DJMPC_CYCLES): lane 0 accumulates clock64() deltas per code region into
+// g_cycles[]; read back with jmpc_debug_cycles.  Meant for single-instance runs (one warp alone on the GPU), where it
+// gives the latency breakdown of the critical path.
+#ifdef JMPC_CYCLES
+__device__ unsigned long long g_cycles[32];
+#define JMPC_TICK(var) long long var = clock64()
+#define JMPC_TOCK(var, slot) do { long long now_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_cycles[slot], (unsigned long long)(now_ - var)); var = now_; } while (0)
+#else
+#define JMPC_TICK(var)
+#define JMPC_TOCK(var, slot)
+#endif
+
 constexpr int kTS = 18;                               // doubles per tile slot
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -38,6 +50,22 @@ __host__ __device__ inline int tiles_doubles(int n) { const int nb = nblk(n); re
 __host__ __device__ __forceinline__ int tile_off(int I, int J) { return (((I * (I + 1)) >> 1) + J) * kTS; }
 // element (i, j) with j <= i, or any (i, j) inside a diagonal tile
 __host__ __device__ __forceinline__ int elem_off(int i, int j) { return tile_off(i >> 2, j >> 2) + ((i & 3) << 2) + (j & 3); }
+
+// 1 / sqrt(a) for a > 0 in the normal range (pivots here are 1e-2 .. 1e20): the hardware seed (MUFU.RSQ64H, 2^-23) and
+// one cubic correction, as the library's fast path, without its exponent-range test and call.  The library version
+// put two branches and a reconvergence point into each of the four pivots of a diagonal block.
+__device__ __forceinline__ double rsqrt_pos(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double e = fma(-a, y * y, 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+// reciprocal root of a pivot; a non-positive pivot is treated as infinite (see chol_tiles)
+__device__ __forceinline__ double pivot_rsqrt(double a, bool& clean) {
+  const double y = rsqrt_pos(fmax(a, 1e-300));
+  if (!(a > 0.0)) clean = false;
+  return (a > 0.0) ? y : 0.0;
+}
 
 __device__ __forceinline__ void ld4(const double* p, double& a, double& b, double& c, double& d) {
   const double2 x = *reinterpret_cast<const double2*>(p), y = *reinterpret_cast<const double2*>(p + 2);
@@ -76,6 +104,7 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
   bool all_clean = true;
   JMPC_PRAGMA_J
   for (int J = 0; J < nb; ++J) {
+    JMPC_TICK(tc_);
     // ---- diagonal block: every lane factors it redundantly in registers (no broadcast needed)
     const double* D = K + tile_off(J, J);
     double a00, a10, a11, a20, a21, a22, a30, a31, a32, a33;
@@ -89,16 +118,16 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
     // usual interior-point remedy: its reciprocal root is set to 0, which zeroes the column of L and that
     // component of every solve; the outer iteration corrects the step.  `clean` reports whether it happened.
     bool clean = true;
-    const double r0 = (a00 > 0.0) ? rsqrt(a00) : (clean = false, 0.0);
+    const double r0 = pivot_rsqrt(a00, clean);
     const double l00 = a00 * r0, l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
     a11 = fma(-l10, l10, a11);
-    const double r1 = (a11 > 0.0) ? rsqrt(a11) : (clean = false, 0.0);
+    const double r1 = pivot_rsqrt(a11, clean);
     const double l11 = a11 * r1, l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
     a22 = fma(-l21, l21, fma(-l20, l20, a22));
-    const double r2 = (a22 > 0.0) ? rsqrt(a22) : (clean = false, 0.0);
+    const double r2 = pivot_rsqrt(a22, clean);
     const double l22 = a22 * r2, l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
     a33 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
-    const double r3 = (a33 > 0.0) ? rsqrt(a33) : (clean = false, 0.0);
+    const double r3 = pivot_rsqrt(a33, clean);
     all_clean = all_clean && clean;
     const double l33 = a33 * r3;
     // M = L^{-1} (lower triangular)
@@ -110,6 +139,7 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
     const double m31 = -fma(l32, m21, l31 * m11) * r3;
     const double m30 = -fma(l32, m20, fma(l31, m10, l30 * m00)) * r3;
     __syncwarp();                                    // every lane has read the block before it is overwritten
+    JMPC_TOCK(tc_, 13);
     // ---- panel below the block: X = A L^{-T}, one matrix row per lane
     const int prow = (nb - J - 1) << 2;
     for (int r = lane; r < prow; r += 32) {
@@ -129,6 +159,7 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
       st4(Mw + 8, m20, m21, m22, 0.0); st4(Mw + 12, m30, m31, m32, m33);
     }
     __syncwarp();
+    JMPC_TOCK(tc_, 14);
     // ---- trailing update: C(I, Kc) -= L(I, J) L(Kc, J)'; a task is half a tile (two rows), so the 45 / 36 / 28 ...
     // tiles of the first block columns fill the 32 lanes better than whole tiles would
     const int m = nb - J - 1, ntasks = m * (m + 1);
@@ -155,6 +186,7 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
       }
     }
     __syncwarp();
+    JMPC_TOCK(tc_, 15);
   }
   return all_clean;
 }
@@ -231,6 +263,43 @@ __device__ inline void symv_tiles(const double* P, const double* x, int nb, int 
   }
 }
 
+
+// ---- rows k and T + k per lane ------------------------------------------------------------------------------------
+// The stage rows keep their part of an n = 2T vector in registers: lane k < T owns entries k (the acceleration part)
+// and T + k (the steering part).  The symmetric matvec below produces its result in that layout.  (A triangular
+// solve in the same layout -- block entries fetched by shuffle, no __syncwarp -- was measured too: 20 % shorter for
+// a warp that runs alone, but 2.3x the instructions and 3x the shared-memory wavefronts of solve_tiles, and 12 %
+// slower on a full batch; it was dropped.)
+// y = P x for a symmetric P on tiles (diagonal tiles stored full), x in shared memory (4 * nb entries); lane k < T gets
+// rows k (y0) and T + k (y1), four independent accumulators per row.
+template <int NB>
+__device__ __forceinline__ void symv_rows(const double* P, const double* x, int T, int nb_rt, int lane, double& y0,
+                                          double& y1) {
+  const int nb = (NB > 0) ? NB : nb_rt;
+  const bool own = lane < T;
+  const int ia = own ? lane : 0, ib = own ? T + lane : 0;
+  const int Ia = ia >> 2, Ib = ib >> 2;
+  const double* rowa = P + tile_off(Ia, 0) + ((ia & 3) << 2);
+  const double* rowb = P + tile_off(Ib, 0) + ((ib & 3) << 2);
+  const double* cola = P + Ia * kTS + (ia & 3);
+  const double* colb = P + Ib * kTS + (ib & 3);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+  for (int J = 0; J < nb; ++J) {
+    double x0, x1, x2, x3, p0, p1, p2, p3;
+    ld4(x + (J << 2), x0, x1, x2, x3);
+    const int tj = ((J * (J + 1)) >> 1) * kTS;
+    if (J <= Ia) ld4(rowa + J * kTS, p0, p1, p2, p3);
+    else { const double* col = cola + tj; p0 = col[0]; p1 = col[4]; p2 = col[8]; p3 = col[12]; }
+    a0 = fma(p0, x0, a0); a1 = fma(p1, x1, a1); a2 = fma(p2, x2, a2); a3 = fma(p3, x3, a3);
+    if (J <= Ib) ld4(rowb + J * kTS, p0, p1, p2, p3);
+    else { const double* col = colb + tj; p0 = col[0]; p1 = col[4]; p2 = col[8]; p3 = col[12]; }
+    b0 = fma(p0, x0, b0); b1 = fma(p1, x1, b1); b2 = fma(p2, x2, b2); b3 = fma(p3, x3, b3);
+  }
+  y0 = own ? (a0 + a1) + (a2 + a3) : 0.0;
+  y1 = own ? (b0 + b1) + (b2 + b3) : 0.0;
+}
+
 // Self-test kernel: one warp packs a dense symmetric matrix into tiles, multiplies, factors and solves.
 __global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, const double* __restrict__ b,
                                        const double* __restrict__ x, double* __restrict__ sol,
@@ -263,6 +332,25 @@ __global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, cons
   __syncwarp();
   for (int i = lane; i < n; i += 32) sol[i] = rhs[i];
   if (lane == 0) *ok = good ? 1 : 0;
+  // the matvec in the solver's layout (even n only: lane k owns rows k and n/2 + k); its result goes behind the
+  // other one: prod[n .. 2n)
+  if ((n & 1) == 0) {
+    const int T = n >> 1;
+    __syncwarp();
+    // symv needs the matrix again
+    __syncwarp();
+    for (int e = lane; e < tiles_doubles(n); e += 32) K[e] = 0.0;
+    __syncwarp();
+    for (int e = lane; e < n4 * n4; e += 32) {
+      const int i = e / n4, j = e % n4;
+      if (j > i && (i >> 2) != (j >> 2)) continue;
+      K[elem_off(i, j)] = (i < n && j < n) ? A[i * n + j] : ((i == j) ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    double q0, q1;
+    symv_rows<0>(K, xv, T, nb, lane, q0, q1);
+    if (lane < T) { prod[n + lane] = q0; prod[n + T + lane] = q1; }
+  }
 }
 
 }  // namespace jmpc

@@ -95,7 +95,7 @@ __host__ __device__ inline int warp_smem_doubles(int T) {
 
 // dynamic shared memory of a block of `wpb` warps: the warps' regions plus the block-shared Cholesky task table
 __host__ __device__ inline size_t step_block_smem_bytes(int T, int wpb) {
-  return (size_t)wpb * warp_smem_doubles(T) * sizeof(double) + (((size_t)chol_lut_entries(nblk(2 * T)) * 2 + 15) & ~(size_t)15);
+  return (size_t)wpb * warp_smem_doubles(T) * sizeof(double) + (((size_t)chol_lut_entries(nblk(2 * T) + 1) * 2 + 15) & ~(size_t)15);
 }
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -226,9 +226,11 @@ struct WarpMem {
     K = p; p += k_region_doubles(T);
     Dinv = p; p += 16 * nblk(n);
     u = p; p += n4; q = p; p += n4; rhs = p; p += n4; grad = p; p += n4;
+    // grad .. epsi are dead while the solver runs: 4 (2T) + 7 (T + 1) >= 8T doubles, the solver's row stash
     ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
+    WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e;
     W11 = p; p += T1e; W12 = p; p += T1e; W22 = p; p += T1e; qv = p; p += T1e; qpsi = p; p += T1e;
-    WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e; vb = p; p += T1e; th = p; p += T1e;
+    vb = p; p += T1e; th = p; p += T1e;
     wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; SW = p; p += Te;
     prm = p; p += kParamSlots;
     mbar = reinterpret_cast<unsigned long long*>(p);
@@ -261,6 +263,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __device__ __forceinline__ void rows_apply(const double* u, int T, int lane, double z[4]) {
   const double a = (lane < T) ? u[lane] : 0.0;
   const double d = (lane < T) ? u[T + lane] : 0.0;
+  const double dn = __shfl_down_sync(kFull, d, 1);
+  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = warp_scan(a, lane);
+}
+// the same for a vector held in registers (a = entry lane, d = entry T + lane; 0 beyond the horizon)
+__device__ __forceinline__ void rows_apply_reg(double a, double d, int lane, double z[4]) {
   const double dn = __shfl_down_sync(kFull, d, 1);
   z[0] = a; z[1] = d; z[2] = dn - d; z[3] = warp_scan(a, lane);
 }
@@ -565,8 +572,14 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       // P -> shared with one TMA bulk copy (the scratch copy is L2 resident); it runs under the row work below.
       // The previous iteration's last reads of K are behind a __syncwarp, the fence inside orders them (generic
       // proxy) before the copy (async proxy).
+      JMPC_TICK(ts_);
       if (lane == 0) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
-      double z[4], rph[4], rpl[4], ish[4], isl[4], t4[4];
+      // The primal row residuals rph / rpl are needed again in both direction phases.  They are parked in shared memory
+      // (the rhs / grad / prefix-sum arrays are dead during the solve) instead of being held across the factorisation
+      // and the triangular solves: with them in registers the compiler spilled 0.5 KB per thread to local memory,
+      // which misses the small L1 left beside 222 KB of shared memory and waits on L2.
+      double* stash = M.grad;                         // [8][T]: rph[0..3], rpl[0..3] of stage = lane
+      double z[4], ish[4], isl[4], t4[4];
       rows_apply(M.u, T, lane, z);
       double mu = 0.0, rpmax = 0.0;
       double w2, w3;
@@ -576,11 +589,12 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
         for (int r = 0; r < 4; ++r) {
           const bool lv = is_live(r);
           ish[r] = 1.0 / sh[r]; isl[r] = 1.0 / sl[r];
-          rph[r] = lv ? (z[r] + sh[r] - bound_hi(r)) : 0.0;
-          rpl[r] = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
+          const double rph_r = lv ? (z[r] + sh[r] - bound_hi(r)) : 0.0;
+          const double rpl_r = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
+          if (lane < T) { stash[r * T + lane] = rph_r; stash[(4 + r) * T + lane] = rpl_r; }
           w[r] = lv ? fma(lh[r], ish[r], ll[r] * isl[r]) : 0.0;
           mu += lh[r] * sh[r] + ll[r] * sl[r];
-          rpmax = fmax(rpmax, fmax(fabs(rph[r]), fabs(rpl[r])));
+          rpmax = fmax(rpmax, fmax(fabs(rph_r), fabs(rpl_r)));
         }
         w2 = w[2]; w3 = w[3];
         double wup = __shfl_up_sync(kFull, w2, 1);
@@ -592,37 +606,53 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       rpmax = warp_max(rpmax);
       // P u is formed from the clean Hessian: folding the barrier weights in first and subtracting them again
       // would cancel catastrophically once w ~ 1e12
+      JMPC_TOCK(ts_, 0);
       mbar_wait(M.mbar, tma_parity);
       tma_parity ^= 1u;
       __syncwarp();
-      double pu0, pu1;
-      symv_tiles(M.K, M.u, nb, lane, pu0, pu1);
+      JMPC_TOCK(ts_, 1);
+      double pu0, pu1;                              // rows lane and T + lane of P u
+      symv_rows<(TT > 0) ? ((2 * TT + 3) >> 2) : 0>(M.K, M.u, T, nb, lane, pu0, pu1);
 #pragma unroll
       for (int r = 0; r < 4; ++r) t4[r] = is_live(r) ? (lh[r] - ll[r]) : 0.0;
       double ra, rd;
       rows_apply_T(t4, lane, ra, rd);
-      if (lane < n) M.grad[lane] = pu0 + M.q[lane];
-      if (lane + 32 < n) M.grad[lane + 32] = pu1 + M.q[lane + 32];
-      __syncwarp();
+      // gradient of the Lagrangian (dual residual), kept in registers: g0 for a_lane, g1 for delta_lane
+      const double g0 = (lane < T) ? pu0 + M.q[lane] + ra : 0.0, g1 = (lane < T) ? pu1 + M.q[T + lane] + rd : 0.0;
+      __syncwarp();                                 // every lane is done reading P before K is assembled in place
+      JMPC_TOCK(ts_, 2);
       // K = P + A' diag(w) A: only the accel block and the steer tridiagonal change
-      for (int e = lane; e < tri(T); e += 32) {          // accel x accel, lower triangle rows 0..T-1
-        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while (tri(i + 1) <= e) ++i;
-        while (tri(i) > e) --i;
-        const int j = e - tri(i);
-        M.K[elem_off(i, j)] += M.SW[i] + ((i == j) ? M.wA[i] : 0.0);
+      {
+        // accel x accel block: + SW[max(i, j)] (+ wA on the diagonal), done by half tiles; the task table of the
+        // Cholesky update for m = ceil(T / 4) block rows enumerates exactly these tiles
+        const int ma = (T + 3) >> 2, ntasks = ma * (ma + 1);
+        const unsigned short* tasks = lut + chol_lut_offset(ma);
+        for (int q = lane; q < ntasks; q += 32) {
+          const unsigned e = tasks[q];
+          const int I = (int)(e & 15u), Jc = (int)((e >> 4) & 15u), h = (int)((e >> 8) & 1u) << 1;
+          double* tile = M.K + tile_off(I, Jc) + 4 * h;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int i = (I << 2) + h + r, j0 = Jc << 2;
+            if (i < T) {
+              const double sw = M.SW[i], wa = M.wA[i];
+              double c0, c1, c2, c3;
+              ld4(tile + 4 * r, c0, c1, c2, c3);
+              c0 += (j0 <= i) ? sw + ((j0 == i) ? wa : 0.0) : 0.0;
+              c1 += (j0 + 1 <= i) ? sw + ((j0 + 1 == i) ? wa : 0.0) : 0.0;
+              c2 += (j0 + 2 <= i) ? sw + ((j0 + 2 == i) ? wa : 0.0) : 0.0;
+              c3 += (j0 + 3 <= i) ? sw + ((j0 + 3 == i) ? wa : 0.0) : 0.0;
+              st4(tile + 4 * r, c0, c1, c2, c3);
+            }
+          }
+        }
       }
       if (lane < T) {
         const int i = T + lane;
         M.K[elem_off(i, i)] += M.wD[lane];
         if (lane >= 1) M.K[elem_off(i, i - 1)] -= M.wR[lane - 1];
       }
-      double rdmax = 0.0;
-      if (lane < T) {
-        const double g0 = M.grad[lane] + ra, g1 = M.grad[T + lane] + rd;
-        M.grad[lane] = g0; M.grad[T + lane] = g1;
-        rdmax = fmax(fabs(g0), fabs(g1));
-      }
+      double rdmax = fmax(fabs(g0), fabs(g1));
       rdmax = warp_max(rdmax);
       __syncwarp();
       if (mu <= A.mu_tol && rpmax <= A.tol_res && rdmax <= A.tol_res * gscale) { converged = true; break; }
@@ -639,14 +669,25 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       dbg_mu = mu; dbg_rp = rpmax; dbg_rd = rdmax / gscale;
 #endif
 
-      chol_tiles(M.K, M.Dinv, nb, lane, lut);     // non-positive pivots are replaced, never fatal
+      JMPC_TOCK(ts_, 3);
+      const bool clean = chol_tiles(M.K, M.Dinv, nb, lane, lut);     // non-positive pivots are replaced, never fatal
+      JMPC_TOCK(ts_, 4);
+      // Numerical breakdown of the factorisation (a pivot lost to roundoff, w ~ 1e13 by then) on an iterate that is
+      // already two orders inside the reduced tolerances: stop here.  The step computed from the patched factor is
+      // usually harmless, but on a few instances in 10^5 (weakly active speed rows, T = 25) it threw the iterate far
+      // enough out that the iteration cap was reached; which instances depended on the build.
+      if (!clean && mu <= 1e-11 && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) { acceptable = true; break; }
 
       double dsh[4], dsl[4], dlh[4], dll[4];
       double sigma_mu = 0.0, aff_step = 0.0;
 #pragma unroll 1
       for (int phase = 0; phase < 2; ++phase) {
         // complementarity targets: predictor rc = l s ; corrector rc = l s + ds_aff dl_aff - sigma mu
-        double th[4];
+        double th[4], rph[4], rpl[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          rph[r] = (lane < T) ? stash[r * T + lane] : 0.0; rpl[r] = (lane < T) ? stash[(4 + r) * T + lane] : 0.0;
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           double rch = lh[r] * sh[r], rcl = ll[r] * sl[r];
@@ -657,11 +698,16 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
           dlh[r] = rch; dll[r] = rcl;                 // stash rc for the direction recovery below
         }
         rows_apply_T(th, lane, ra, rd);
-        if (lane < T) { M.rhs[lane] = -M.grad[lane] - ra; M.rhs[T + lane] = -M.grad[T + lane] - rd; }
+        double du0 = (lane < T) ? -g0 - ra : 0.0, du1 = (lane < T) ? -g1 - rd : 0.0;       // right-hand side -> direction
+        JMPC_TOCK(ts_, 5);
+        if (lane < T) { M.rhs[lane] = du0; M.rhs[T + lane] = du1; }
         __syncwarp();
         solve_tiles(M.K, M.Dinv, M.rhs, nb, lane);
+        __syncwarp();
+        if (lane < T) { du0 = M.rhs[lane]; du1 = M.rhs[T + lane]; }
+        JMPC_TOCK(ts_, 6);
         double dz[4];
-        rows_apply(M.rhs, T, lane, dz);
+        rows_apply_reg(du0, du1, lane, dz);
         // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l).  The maximum ratio is tracked as a
         // (numerator, denominator) pair compared by cross-multiplication, so the 16 candidates per lane cost no
         // division (fp64 division is ~20 instructions); one division remains after the warp reduction.
@@ -699,7 +745,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
           // one keeps the classical 0.99.  Saves ~13 % of the iterations; a rule driven by mu alone (1 - mu) made
           // a few instances in 10^4 oscillate between a tiny predictor step and a pure centring step.
           const double alpha = fmin(1.0, fmin(0.9999, fmax(0.99, 1.0 - 0.1 * (1.0 - aff_step) * (1.0 - aff_step))) * amax);
-          if (lane < T) { M.u[lane] = fma(alpha, M.rhs[lane], M.u[lane]); M.u[T + lane] = fma(alpha, M.rhs[T + lane], M.u[T + lane]); }
+          if (lane < T) { M.u[lane] = fma(alpha, du0, M.u[lane]); M.u[T + lane] = fma(alpha, du1, M.u[T + lane]); }
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             sh[r] = fma(alpha, dsh[r], sh[r]); sl[r] = fma(alpha, dsl[r], sl[r]);
@@ -707,6 +753,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
           }
         }
         __syncwarp();
+        JMPC_TOCK(ts_, 7);
       }
     }
 #ifdef JMPC_DEBUG_RESID
@@ -815,12 +862,16 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, doub
   int total_iters = 0;
   for (int lin = 0; lin < A.lin_iters; ++lin) {
     int idx = 0; unsigned end_mask = 0;
+    JMPC_TICK(ti_);
     const int st = step_prep<TT>(A, b, smem_base, pscr, lane, lin, total_iters, oa_k, od_k, ov_k, target, idx, end_mask);
     if (st != JMPC_OPTIMAL) return;
+    JMPC_TOCK(ti_, 10);
     bool converged = false;
     total_iters += step_solve<TT>(A, smem_base, pscr, lane, converged, tma_parity, lut);
+    JMPC_TOCK(ti_, 11);
     step_output<TT>(A, b, smem_base, lane, lin == A.lin_iters - 1, converged ? JMPC_OPTIMAL : JMPC_MAX_ITER, target, idx,
                     end_mask, total_iters, oa_k, od_k, ov_k);
+    JMPC_TOCK(ti_, 12);
     __syncwarp();
   }
 }
@@ -870,7 +921,7 @@ template <int TT>
 #ifndef JMPC_MINBLOCKS
 #define JMPC_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const StepArgs A) {
+__global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -887,7 +938,7 @@ __global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const Ste
   }
   // block-shared task table of the Cholesky trailing update, behind the warps' regions
   unsigned short* lut = reinterpret_cast<unsigned short*>(smem + (size_t)warps_per_block * warp_smem_doubles(T));
-  chol_lut_build(lut, nblk(n), threadIdx.x, blockDim.x);
+  chol_lut_build(lut, nblk(n) + 1, threadIdx.x, blockDim.x);     // one more block row than the factorisation needs: the K assembly uses m = ceil(T / 4) <= nb
   __syncthreads();
   for (;;) {
     unsigned b = 0;

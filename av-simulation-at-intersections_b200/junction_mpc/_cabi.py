@@ -33,6 +33,7 @@ SIGNATURES = {
                                      C.c_void_p]),
     "jmpc_set_car_geometry": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "jmpc_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 17 + [C.c_void_p]),
+    "jmpc_debug_cycles": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jmpc_set_schedule": (C.c_int32, [C.c_void_p, C.c_int32]),
     "jmpc_reset_schedule_hints": (C.c_int32, [C.c_void_p]),
     "jmpc_set_skip_mask": (C.c_int32, [C.c_void_p, C.c_void_p]),

@@ -156,16 +156,18 @@ class BatchedMPC:
         _cabi.check(self._lib.jmpc_measure_fma_peak(self._h, C.byref(a), C.byref(b)), "jmpc_measure_fma_peak")
         return a.value, b.value
 
-    def debug_linalg(self, A, b, x):
+    def debug_linalg(self, A, b, x, full: bool = False):
         """Building-block self-test: returns (A^{-1} b, A x, ok) computed by the tiled warp routines."""
         A = _f64(A)
         n = A.shape[0]
         b, x = _f64(b, (n,)), _f64(x, (n,))
-        sol, prod = np.zeros(n), np.zeros(n)
+        sol, prod = np.zeros(2 * n), np.zeros(2 * n)
         rc = self._lib.jmpc_debug_linalg(self._h, n, _ptr(A), _ptr(b), _ptr(x), _ptr(sol), _ptr(prod))
         if rc < 0:
             _cabi.check(rc, "jmpc_debug_linalg")
-        return sol, prod, rc == 0
+        if n % 2 == 0 and not full:         # the matvec in the solver's row layout must agree with the tiled one
+            np.testing.assert_allclose(prod[n:], prod[:n], rtol=1e-13, atol=1e-13 * np.abs(A).max())
+        return (sol, prod, rc == 0) if full else (sol[:n], prod[:n], rc == 0)
 
     # ---- page-locked host arrays --------------------------------------------------------------------------
     def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:

@@ -143,6 +143,10 @@ int32_t jmpc_set_skip_mask(jmpc_handle h, const int32_t* skip);
 int32_t jmpc_set_schedule(jmpc_handle h, int32_t mode);
 int32_t jmpc_reset_schedule_hints(jmpc_handle h);
 
+/* Debug builds only (-DJMPC_CYCLES): per-region clock64() totals accumulated by the step kernel (32 slots), optionally
+ * cleared.  Fails in a regular build. */
+int32_t jmpc_debug_cycles(jmpc_handle h, uint64_t* out32, int32_t reset);
+
 /* Fused all-gather of the result records (multi-GPU): after this call every jmpc_step on the handle also stores each
  * instance's record into row `rank_offset + b` of every table in `peer_tables` (DEVICE pointers valid on this GPU
  * for all `n_peers` ranks including this one -- NVLink peer / symmetric memory, e.g. the `buffer_ptrs` of a
@@ -227,7 +231,9 @@ int32_t jmpc_measure_fma_peak(jmpc_handle h, double* fp64_tflops, double* fp32_t
 
 /* Self-test of the solver's building blocks (4x4-tiled symmetric matvec, Cholesky, triangular solves) on one
  * warp: A is a dense symmetric positive definite n x n matrix (row major, n <= 2*JMPC_MAX_T), HOST pointers.
- * prod = A x, sol = A^{-1} b.  Returns 0 on success, 1 when the factorisation met a non-positive pivot. */
+ * prod = A x, sol = A^{-1} b, each with 2n entries: [0, n) the results; prod[n, 2n) holds A x once more, computed
+ * by the matvec in the solver's own row layout (even n only, NaN otherwise); sol[n, 2n) is unused (NaN).  Returns 0 on success, 1 when the
+ * factorisation met a non-positive pivot. */
 int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const double* b, const double* x, double* sol,
                           double* prod);
 

@@ -14,7 +14,7 @@ def engine():
     return BatchedMPC([synth.load_course("intersection")], dl=0.083, T=13, max_batch=64)
 
 
-@pytest.mark.parametrize("n", [1, 3, 4, 5, 16, 26, 31, 32, 33, 40, 50, 62])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 10, 16, 26, 31, 32, 33, 40, 50, 62])
 def test_tiled_factor_solve_matvec(engine, n):
     rng = np.random.default_rng(n)
     G = rng.normal(size=(n, n))
@@ -22,8 +22,11 @@ def test_tiled_factor_solve_matvec(engine, n):
     # mimic the solver's matrices: a few huge barrier weights on the diagonal
     A[np.diag_indices(n)] += np.where(rng.random(n) < 0.3, 10.0 ** rng.uniform(3, 10, n), 0.0)
     b, x = rng.normal(size=n), rng.normal(size=n)
-    sol, prod, ok = engine.debug_linalg(A, b, x)
+    sol2, prod2, ok = engine.debug_linalg(A, b, x, full=True)
     assert ok
+    sol, prod = sol2[:n], prod2[:n]
+    if n % 2 == 0:          # the matvec in the solver's own layout (lane k owns rows k and n/2 + k)
+        np.testing.assert_allclose(prod2[n:], A @ x, rtol=1e-13, atol=1e-13 * np.abs(A).max())
     np.testing.assert_allclose(prod, A @ x, rtol=1e-13, atol=1e-13 * np.abs(A).max())
     ref = np.linalg.solve(A, b)
     np.testing.assert_allclose(sol, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
