@@ -60,6 +60,17 @@ __device__ __forceinline__ double rsqrt_pos(double a) {
   const double e = fma(-a, y * y, 1.0);
   return fma(fma(e, 0.375, 0.5), y * e, y);
 }
+// 1 / a for a > 0 in the normal range (slacks: 1e-30 .. 1e6): hardware seed (MUFU.RCP64H) and two Newton steps, without the
+// library's exponent-range test and slow-path call.  Not correctly rounded (1 ulp); the interior-point iteration only
+// needs s * (1/s) = 1 to working precision.
+__device__ __forceinline__ double rcp_pos(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
 // reciprocal root of a pivot; a non-positive pivot is treated as infinite (see chol_tiles)
 __device__ __forceinline__ double pivot_rsqrt(double a, bool& clean) {
   const double y = rsqrt_pos(fmax(a, 1e-300));
@@ -199,9 +210,12 @@ __device__ inline void solve_tiles(const double* K, const double* Dinv, double* 
     const double* Mw = Dinv + (J << 4);
     double b0, b1, b2, b3;
     ld4(b + (J << 2), b0, b1, b2, b3);
-    const double m00 = Mw[0], m10 = Mw[4], m11 = Mw[5], m20 = Mw[8], m21 = Mw[9], m22 = Mw[10];
-    double m30, m31, m32, m33;
-    ld4(Mw + 12, m30, m31, m32, m33);
+    const double m00 = Mw[0];
+    const double2 mr1 = *reinterpret_cast<const double2*>(Mw + 4);
+    const double m10 = mr1.x, m11 = mr1.y;
+    double m20, m21, m22, mpad, m30, m31, m32, m33;
+    ld4(Mw + 8, m20, m21, m22, mpad); ld4(Mw + 12, m30, m31, m32, m33);
+    (void)mpad;
     const double y0 = m00 * b0, y1 = fma(m11, b1, m10 * b0), y2 = fma(m22, b2, fma(m21, b1, m20 * b0));
     const double y3 = fma(m33, b3, fma(m32, b2, fma(m31, b1, m30 * b0)));
     __syncwarp();
@@ -218,9 +232,12 @@ __device__ inline void solve_tiles(const double* K, const double* Dinv, double* 
     const double* Mw = Dinv + (J << 4);
     double y0, y1, y2, y3;
     ld4(b + (J << 2), y0, y1, y2, y3);
-    const double m00 = Mw[0], m10 = Mw[4], m11 = Mw[5], m20 = Mw[8], m21 = Mw[9], m22 = Mw[10];
-    double m30, m31, m32, m33;
-    ld4(Mw + 12, m30, m31, m32, m33);
+    const double m00 = Mw[0];
+    const double2 mr1 = *reinterpret_cast<const double2*>(Mw + 4);
+    const double m10 = mr1.x, m11 = mr1.y;
+    double m20, m21, m22, mpad, m30, m31, m32, m33;
+    ld4(Mw + 8, m20, m21, m22, mpad); ld4(Mw + 12, m30, m31, m32, m33);
+    (void)mpad;
     const double x3 = m33 * y3, x2 = fma(m32, y3, m22 * y2), x1 = fma(m31, y3, fma(m21, y2, m11 * y1));
     const double x0 = fma(m30, y3, fma(m20, y2, fma(m10, y1, m00 * y0)));
     __syncwarp();

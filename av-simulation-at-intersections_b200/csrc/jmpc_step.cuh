@@ -568,12 +568,15 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
     double dbg_mu = 0, dbg_rp = 0, dbg_rd = 0;
 #endif
     int it = 0;
+    // P -> shared with one TMA bulk copy per iteration (the scratch copy is L2 resident).  The copy for iteration
+    // it + 1 is issued as soon as the corrector's triangular solves have read the factor for the last time, so it
+    // runs under the direction recovery, the step and the next iteration's row work.  Every exit of the loop lies
+    // behind the wait for the copy in flight (and none is issued for an iteration that will not run), so the
+    // barrier's phase stays in step and nothing lands in K after the solver has left.  The last reads of K are
+    // behind a __syncwarp; the fence inside tma_load_1d orders them (generic proxy) before the copy (async proxy).
+    if (lane == 0 && A.max_iters > 0) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
     for (it = 0; it < A.max_iters; ++it) {
-      // P -> shared with one TMA bulk copy (the scratch copy is L2 resident); it runs under the row work below.
-      // The previous iteration's last reads of K are behind a __syncwarp, the fence inside orders them (generic
-      // proxy) before the copy (async proxy).
       JMPC_TICK(ts_);
-      if (lane == 0) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
       // The primal row residuals rph / rpl are needed again in both direction phases.  They are parked in shared memory
       // (the rhs / grad / prefix-sum arrays are dead during the solve) instead of being held across the factorisation
       // and the triangular solves: with them in registers the compiler spilled 0.5 KB per thread to local memory,
@@ -588,7 +591,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const bool lv = is_live(r);
-          ish[r] = 1.0 / sh[r]; isl[r] = 1.0 / sl[r];
+          ish[r] = rcp_pos(sh[r]); isl[r] = rcp_pos(sl[r]);
           const double rph_r = lv ? (z[r] + sh[r] - bound_hi(r)) : 0.0;
           const double rpl_r = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
           if (lane < T) { stash[r * T + lane] = rph_r; stash[(4 + r) * T + lane] = rpl_r; }
@@ -704,6 +707,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
         __syncwarp();
         solve_tiles(M.K, M.Dinv, M.rhs, nb, lane);
         __syncwarp();
+        if (phase == 1 && lane == 0 && it + 1 < A.max_iters) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
         if (lane < T) { du0 = M.rhs[lane]; du1 = M.rhs[T + lane]; }
         JMPC_TOCK(ts_, 6);
         double dz[4];
