@@ -111,7 +111,12 @@ __device__ inline void chol_lut_build(unsigned short* lut, int nb, int tid, int 
 // lower triangular), which turn the panel and the triangular solves into multiplications.
 // Returns false when some pivot was not positive and had to be replaced (all lanes agree); the factor is usable
 // either way.
-__device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, const unsigned short* lut) {
+// When `rhs` is given (4 * nb doubles in shared memory) the forward substitution L y = rhs rides along: block J of y
+// is the inverted diagonal block times block J of rhs (every lane, registers), and the lane that has just computed a
+// row of the panel subtracts that row times y from its rhs entry -- no extra loads of L and no extra
+// synchronisation; rhs holds y afterwards (solve_backward_tiles completes the solve).
+__device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, const unsigned short* lut,
+                                  double* rhs = nullptr) {
   bool all_clean = true;
   JMPC_PRAGMA_J
   for (int J = 0; J < nb; ++J) {
@@ -149,6 +154,13 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
     const double m20 = -fma(l21, m10, l20 * m00) * r2;
     const double m31 = -fma(l32, m21, l31 * m11) * r3;
     const double m30 = -fma(l32, m20, fma(l31, m10, l30 * m00)) * r3;
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;     // block J of the forward substitution
+    if (rhs) {
+      double b0, b1, b2, b3;
+      ld4(rhs + (J << 2), b0, b1, b2, b3);
+      y0 = m00 * b0; y1 = fma(m11, b1, m10 * b0); y2 = fma(m22, b2, fma(m21, b1, m20 * b0));
+      y3 = fma(m31, b1, m30 * b0) + fma(m33, b3, m32 * b2);
+    }
     __syncwarp();                                    // every lane has read the block before it is overwritten
     JMPC_TOCK(tc_, 13);
     // ---- panel below the block: X = A L^{-T}, one matrix row per lane
@@ -157,8 +169,13 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
       double* row = K + tile_off(J + 1 + (r >> 2), J) + ((r & 3) << 2);
       double a0, a1, a2, a3;
       ld4(row, a0, a1, a2, a3);
-      st4(row, a0 * m00, fma(a1, m11, a0 * m10), fma(a2, m22, fma(a1, m21, a0 * m20)),
-          fma(a3, m33, fma(a2, m32, fma(a1, m31, a0 * m30))));
+      const double x0 = a0 * m00, x1 = fma(a1, m11, a0 * m10), x2 = fma(a2, m22, fma(a1, m21, a0 * m20));
+      const double x3 = fma(a3, m33, fma(a2, m32, fma(a1, m31, a0 * m30)));
+      st4(row, x0, x1, x2, x3);
+      if (rhs) {
+        double* bi = rhs + ((J + 1) << 2) + r;
+        *bi -= fma(x1, y1, x0 * y0) + fma(x3, y3, x2 * y2);
+      }
     }
     if (lane == 0) {
       double* Dw = K + tile_off(J, J);
@@ -168,6 +185,7 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
       double* Mw = Dinv + (J << 4);
       st4(Mw, m00, 0.0, 0.0, 0.0); st4(Mw + 4, m10, m11, 0.0, 0.0);
       st4(Mw + 8, m20, m21, m22, 0.0); st4(Mw + 12, m30, m31, m32, m33);
+      if (rhs) st4(rhs + (J << 2), y0, y1, y2, y3);
     }
     __syncwarp();
     JMPC_TOCK(tc_, 14);
@@ -202,8 +220,9 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
   return all_clean;
 }
 
-// Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).
-__device__ inline void solve_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
+// Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).  The two sweeps are separate
+// functions: the forward one can also ride along with the factorisation (chol_tiles).
+__device__ inline void solve_forward_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
   const int n4 = nb << 2;
   JMPC_PRAGMA_J
   for (int J = 0; J < nb; ++J) {                      // forward: L y = b
@@ -227,6 +246,8 @@ __device__ inline void solve_tiles(const double* K, const double* Dinv, double* 
     if (lane == 0) st4(b + (J << 2), y0, y1, y2, y3);
     __syncwarp();
   }
+}
+__device__ inline void solve_backward_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
   JMPC_PRAGMA_J
   for (int J = nb - 1; J >= 0; --J) {                 // backward: L' x = y
     const double* Mw = Dinv + (J << 4);
@@ -287,6 +308,11 @@ __device__ inline void symv_tiles(const double* P, const double* x, int nb, int 
 // solve in the same layout -- block entries fetched by shuffle, no __syncwarp -- was measured too: 20 % shorter for
 // a warp that runs alone, but 2.3x the instructions and 3x the shared-memory wavefronts of solve_tiles, and 12 %
 // slower on a full batch; it was dropped.)
+__device__ inline void solve_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
+  solve_forward_tiles(K, Dinv, b, nb, lane);
+  solve_backward_tiles(K, Dinv, b, nb, lane);
+}
+
 // y = P x for a symmetric P on tiles (diagonal tiles stored full), x in shared memory (4 * nb entries); lane k < T gets
 // rows k (y0) and T + k (y1), four independent accumulators per row.
 template <int NB>

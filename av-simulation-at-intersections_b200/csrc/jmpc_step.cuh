@@ -595,6 +595,8 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
           const double rph_r = lv ? (z[r] + sh[r] - bound_hi(r)) : 0.0;
           const double rpl_r = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
           if (lane < T) { stash[r * T + lane] = rph_r; stash[(4 + r) * T + lane] = rpl_r; }
+          // predictor (affine) complementarity target rc = lambda s:  (lambda rp - rc) / s = lambda (rp - s) / s
+          t4[r] = lv ? (fma(lh[r], rph_r, -lh[r] * sh[r]) * ish[r] - fma(ll[r], rpl_r, -ll[r] * sl[r]) * isl[r]) : 0.0;
           w[r] = lv ? fma(lh[r], ish[r], ll[r] * isl[r]) : 0.0;
           mu += lh[r] * sh[r] + ll[r] * sl[r];
           rpmax = fmax(rpmax, fmax(fabs(rph_r), fabs(rpl_r)));
@@ -607,6 +609,8 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       }
       mu = warp_sum(mu) * inv_rows;
       rpmax = warp_max(rpmax);
+      double ra_p, rd_p;                              // A' (predictor row terms)
+      rows_apply_T(t4, lane, ra_p, rd_p);
       // P u is formed from the clean Hessian: folding the barrier weights in first and subtracting them again
       // would cancel catastrophically once w ~ 1e12
       JMPC_TOCK(ts_, 0);
@@ -673,7 +677,11 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
 #endif
 
       JMPC_TOCK(ts_, 3);
-      const bool clean = chol_tiles(M.K, M.Dinv, nb, lane, lut);     // non-positive pivots are replaced, never fatal
+      // The predictor's right-hand side needs nothing from the factor, so its forward substitution rides along with
+      // the factorisation (one triangular sweep out of four per iteration saved).
+      if (lane < T) { M.rhs[lane] = -g0 - ra_p; M.rhs[T + lane] = -g1 - rd_p; }
+      __syncwarp();
+      const bool clean = chol_tiles(M.K, M.Dinv, nb, lane, lut, M.rhs);     // non-positive pivots are replaced, never fatal
       JMPC_TOCK(ts_, 4);
       // Numerical breakdown of the factorisation (a pivot lost to roundoff, w ~ 1e13 by then) on an iterate that is
       // already two orders inside the reduced tolerances: stop here.  The step computed from the patched factor is
@@ -686,29 +694,35 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
 #pragma unroll 1
       for (int phase = 0; phase < 2; ++phase) {
         // complementarity targets: predictor rc = l s ; corrector rc = l s + ds_aff dl_aff - sigma mu
-        double th[4], rph[4], rpl[4];
+        double rph[4], rpl[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           rph[r] = (lane < T) ? stash[r * T + lane] : 0.0; rpl[r] = (lane < T) ? stash[(4 + r) * T + lane] : 0.0;
         }
+        if (phase == 1) {
+          double th[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          double rch = lh[r] * sh[r], rcl = ll[r] * sl[r];
-          if (phase == 1) { rch += dsh[r] * dlh[r] - sigma_mu; rcl += dsl[r] * dll[r] - sigma_mu; }
-          const double a_h = fma(lh[r], rph[r], -rch) * ish[r];
-          const double a_l = fma(ll[r], rpl[r], -rcl) * isl[r];
-          th[r] = is_live(r) ? (a_h - a_l) : 0.0;
-          dlh[r] = rch; dll[r] = rcl;                 // stash rc for the direction recovery below
+          for (int r = 0; r < 4; ++r) {
+            const double rch = fma(lh[r], sh[r], dsh[r] * dlh[r] - sigma_mu), rcl = fma(ll[r], sl[r], dsl[r] * dll[r] - sigma_mu);
+            const double a_h = fma(lh[r], rph[r], -rch) * ish[r];
+            const double a_l = fma(ll[r], rpl[r], -rcl) * isl[r];
+            th[r] = is_live(r) ? (a_h - a_l) : 0.0;
+            dlh[r] = rch; dll[r] = rcl;               // stash rc for the direction recovery below
+          }
+          rows_apply_T(th, lane, ra, rd);
+          if (lane < T) { M.rhs[lane] = -g0 - ra; M.rhs[T + lane] = -g1 - rd; }
+          __syncwarp();
+          JMPC_TOCK(ts_, 5);
+          solve_forward_tiles(M.K, M.Dinv, M.rhs, nb, lane);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { dlh[r] = lh[r] * sh[r]; dll[r] = ll[r] * sl[r]; }
+          JMPC_TOCK(ts_, 5);
         }
-        rows_apply_T(th, lane, ra, rd);
-        double du0 = (lane < T) ? -g0 - ra : 0.0, du1 = (lane < T) ? -g1 - rd : 0.0;       // right-hand side -> direction
-        JMPC_TOCK(ts_, 5);
-        if (lane < T) { M.rhs[lane] = du0; M.rhs[T + lane] = du1; }
-        __syncwarp();
-        solve_tiles(M.K, M.Dinv, M.rhs, nb, lane);
+        solve_backward_tiles(M.K, M.Dinv, M.rhs, nb, lane);
         __syncwarp();
         if (phase == 1 && lane == 0 && it + 1 < A.max_iters) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
-        if (lane < T) { du0 = M.rhs[lane]; du1 = M.rhs[T + lane]; }
+        const double du0 = (lane < T) ? M.rhs[lane] : 0.0, du1 = (lane < T) ? M.rhs[T + lane] : 0.0;
         JMPC_TOCK(ts_, 6);
         double dz[4];
         rows_apply_reg(du0, du1, lane, dz);
