@@ -73,9 +73,10 @@ __device__ __forceinline__ double rcp_pos(double a) {
 }
 // reciprocal root of a pivot; a non-positive pivot is treated as infinite (see chol_tiles)
 __device__ __forceinline__ double pivot_rsqrt(double a, bool& clean) {
-  const double y = rsqrt_pos(fmax(a, 1e-300));
-  if (!(a > 0.0)) clean = false;
-  return (a > 0.0) ? y : 0.0;
+  const double y = rsqrt_pos(a);              // NaN for a <= 0, discarded by the select
+  const bool pos = a > 0.0;
+  clean = clean && pos;
+  return pos ? y : 0.0;
 }
 
 __device__ __forceinline__ void ld4(const double* p, double& a, double& b, double& c, double& d) {
