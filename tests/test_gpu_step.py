@@ -277,6 +277,27 @@ def test_host_transfer_modes_agree(jm, mode, monkeypatch):
     mpc.close()
 
 
+def test_results_do_not_depend_on_the_work_queue_order(jm):
+    """jmpc_set_schedule: index order, a-priori key, previous-step iteration counts -- bit-identical results; the
+    batch is larger than the resident warps so that the ordering kernel actually runs."""
+    synth, BatchedMPC = jm
+    w = synth.make_workload(2, B=4096)
+    ref = None
+    for mode in ["index", "apriori", "history", "history"]:         # the second "history" step runs on recorded counts
+        if mode != "history" or ref is None or mpc.schedule != "history":
+            mpc = BatchedMPC(w["courses"], dl=w["dl"], T=w["T"], max_batch=4096, schedule=mode)
+            launches0 = mpc.launch_count
+        out = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"])
+        assert (out.status == 0).all()
+        if ref is None:
+            ref = out
+            continue
+        for key in ["oa", "od", "ox", "oy", "ov", "oyaw", "xref", "cost", "status", "iters", "target_ind", "record"]:
+            assert np.array_equal(getattr(out, key), getattr(ref, key)), (mode, key)
+    assert mpc.launch_count - launches0 == 4             # (ordering kernel + step kernel) x 2 steps on the last engine
+    mpc.reset_schedule_hints()
+
+
 def test_fused_record_stores_reach_the_peer_tables(jm):
     """The kernel-epilogue all-gather on one GPU: two 'peer' tables that both live on this device."""
     import torch
