@@ -901,8 +901,9 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, doub
 // (measured on config 2: 1.27 ms in index order, 0.90 ms longest-first).  The queue therefore hands instances out
 // by descending key: the iteration count of the same instance in the previous step when the caller runs a closed
 // loop (work_hint; the active set, and with it the iteration count, changes slowly from step to step), otherwise
-// an a-priori key: the number of horizon stages on which the speed cap can bind at full throttle
-// (v0 close to the cap => many active, nearly degenerate speed rows => more iterations; correlation 0.5).
+// an a-priori key: the number of horizon stages on which the speed cap can bind at full throttle (v0 close to the
+// cap => many active, nearly degenerate speed rows) plus the stages on which the acceleration box binds while a slow
+// ego catches up with the reference points (correlation 0.56 with the iteration count on config 2).
 // One block; counting sort on 64 key values; the order inside a key class is not deterministic (it only affects timing).
 constexpr int kSchedKeys = 64;
 __global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int* __restrict__ hint,
@@ -919,8 +920,13 @@ __global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int*
     } else {
       const double* pv = params ? params + (size_t)b * JMPC_NPARAM : defaults.v;
       const double v0 = state[(size_t)b * 4 + 2];
-      const double stages_to_cap = (pv[JMPC_P_SPEED] - v0) / fmax(pv[JMPC_P_MAX_ACCEL] * pv[JMPC_P_DT], 1e-9);
-      key = (int)fmin(fmax((double)T - stages_to_cap, 0.0), (double)T) * 2;
+      const double dv_stage = fmax(pv[JMPC_P_MAX_ACCEL] * pv[JMPC_P_DT], 1e-9);        // speed gained per stage at full throttle
+      // stages on which the speed cap can bind
+      const double cap_stages = fmin(fmax((double)T - (pv[JMPC_P_SPEED] - v0) / dv_stage, 0.0), (double)T);
+      // stages at full throttle to reach the speed the reference points advance with (mpc.py:98: max(v, 10/3.6)); the
+      // acceleration box binds on those and, to close the gap opened meanwhile, on about as many again
+      const double acc_stages = fmin(fmax((pv[JMPC_P_V_REF_MIN] - v0) / dv_stage, 0.0), (double)T);
+      key = (int)(2.0 * (cap_stages + 2.0 * acc_stages));
     }
     return min(max(key, 0), kSchedKeys - 1);
   };

@@ -8,7 +8,9 @@ from junction_mpc.batched import BatchedMPC
 dev=torch.device('cuda',0)
 t=lambda a,dt: torch.as_tensor(np.ascontiguousarray(a),dtype=dt,device=dev)
 cfg=int(sys.argv[1]) if len(sys.argv)>1 else 2
-w=synth.make_workload(cfg) if cfg<10 else synth.make_workload(2,B=cfg); B,T=w["B"],w["T"]
+seed=int(sys.argv[2]) if len(sys.argv)>2 else 0
+cfgB=int(sys.argv[3]) if len(sys.argv)>3 else 0
+w=(synth.make_workload(cfg,B=cfgB or None,seed_offset=seed) if cfg<10 else synth.make_workload(2,B=cfg,seed_offset=seed)); B,T=w["B"],w["T"]
 mpc=BatchedMPC(w["courses"], dl=w["dl"], T=T, max_batch=B, schedule="index")
 def run(order, reps=10, reset=False):
     state,clen,tgt0,oa0,od0=t(w["state"][order],torch.float64),t(w["course_len"][order],torch.int32),t(w["target_ind"][order],torch.int32),t(w["oa"][order],torch.float64),t(w["od"][order],torch.float64)
