@@ -90,12 +90,14 @@ StepKernel step_kernel_for(int T) {
 }
 
 int step_geometry(jmpc_handle h, int B, int T, StepGeom* g) {
-  int wpb = 4;
-  if (const char* e = getenv("JMPC_WPB")) wpb = std::max(1, std::min(4, atoi(e)));
+  int wpb = JMPC_WPB;
+  if (const char* e = getenv("JMPC_WPB")) wpb = std::max(1, std::min(JMPC_WPB, atoi(e)));
   const size_t smem = jmpc::step_block_smem_bytes(T, wpb);
   StepKernel k = step_kernel_for(T);
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int carve = cudaSharedmemCarveoutMaxShared;
+  if (const char* e = getenv("JMPC_CARVEOUT")) carve = atoi(e);          // percent of the unified L1 / shared memory given to shared
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, wpb * 32, smem));
   if (per_sm < 1) return fail("step kernel does not fit on an SM for this horizon");
@@ -765,7 +767,7 @@ int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const doubl
   CK(cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
   const int nb = jmpc::nblk(n);
-  const size_t smem = (jmpc::tiles_doubles(n) + 16 * nb + 8 * nb) * sizeof(double) + (size_t)jmpc::chol_lut_entries(nb + 1) * 2 + 16;
+  const size_t smem = (jmpc::tiles_doubles(n) + 8 * nb) * sizeof(double) + (size_t)jmpc::chol_lut_entries(nb + 1) * 2 + 16;
   jmpc::linalg_selftest_kernel<<<1, 32, smem, h->own_stream>>>(n, dA, db, dx, dsol, dprod, dok);
   CK(cudaGetLastError());
   h->launches++;

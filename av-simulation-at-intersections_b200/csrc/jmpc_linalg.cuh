@@ -108,15 +108,15 @@ __device__ inline void chol_lut_build(unsigned short* lut, int nb, int tid, int 
   }
 }
 
-// In-place Cholesky K = L L' on tiles.  Dinv receives the inverses of the diagonal blocks of L (nb x 16 doubles,
-// lower triangular), which turn the panel and the triangular solves into multiplications.
+// In-place Cholesky K = L L' on tiles.  The off-diagonal tiles receive L; each diagonal tile receives the INVERSE of
+// L's diagonal block (lower triangular), which turns the panel and the triangular solves into multiplications.
 // Returns false when some pivot was not positive and had to be replaced (all lanes agree); the factor is usable
 // either way.
 // When `rhs` is given (4 * nb doubles in shared memory) the forward substitution L y = rhs rides along: block J of y
 // is the inverted diagonal block times block J of rhs (every lane, registers), and the lane that has just computed a
 // row of the panel subtracts that row times y from its rhs entry -- no extra loads of L and no extra
 // synchronisation; rhs holds y afterwards (solve_backward_tiles completes the solve).
-__device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, const unsigned short* lut,
+__device__ inline bool chol_tiles(double* K, int nb, int lane, const unsigned short* lut,
                                   double* rhs = nullptr) {
   bool all_clean = true;
   JMPC_PRAGMA_J
@@ -136,17 +136,16 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
     // component of every solve; the outer iteration corrects the step.  `clean` reports whether it happened.
     bool clean = true;
     const double r0 = pivot_rsqrt(a00, clean);
-    const double l00 = a00 * r0, l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+    const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
     a11 = fma(-l10, l10, a11);
     const double r1 = pivot_rsqrt(a11, clean);
-    const double l11 = a11 * r1, l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
+    const double l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
     a22 = fma(-l21, l21, fma(-l20, l20, a22));
     const double r2 = pivot_rsqrt(a22, clean);
-    const double l22 = a22 * r2, l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
+    const double l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
     a33 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
     const double r3 = pivot_rsqrt(a33, clean);
     all_clean = all_clean && clean;
-    const double l33 = a33 * r3;
     // M = L^{-1} (lower triangular)
     const double m00 = r0, m11 = r1, m22 = r2, m33 = r3;
     const double m10 = -(l10 * m00) * r1;
@@ -179,11 +178,9 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
       }
     }
     if (lane == 0) {
-      double* Dw = K + tile_off(J, J);
-      st4(Dw, l00, 0.0, 0.0, 0.0); st4(Dw + 4, l10, l11, 0.0, 0.0);
-      st4(Dw + 8, l20, l21, l22, 0.0); st4(Dw + 12, l30, l31, l32, l33);
-    } else if (lane == 1) {
-      double* Mw = Dinv + (J << 4);
+      // the diagonal tile receives the inverse of the factor's diagonal block: nothing reads the block itself again
+      // (the panel, the trailing update and the triangular sweeps all work with the inverse)
+      double* Mw = K + tile_off(J, J);
       st4(Mw, m00, 0.0, 0.0, 0.0); st4(Mw + 4, m10, m11, 0.0, 0.0);
       st4(Mw + 8, m20, m21, m22, 0.0); st4(Mw + 12, m30, m31, m32, m33);
       if (rhs) st4(rhs + (J << 2), y0, y1, y2, y3);
@@ -223,11 +220,11 @@ __device__ inline bool chol_tiles(double* K, double* Dinv, int nb, int lane, con
 
 // Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).  The two sweeps are separate
 // functions: the forward one can also ride along with the factorisation (chol_tiles).
-__device__ inline void solve_forward_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
+__device__ inline void solve_forward_tiles(const double* K, double* b, int nb, int lane) {
   const int n4 = nb << 2;
   JMPC_PRAGMA_J
   for (int J = 0; J < nb; ++J) {                      // forward: L y = b
-    const double* Mw = Dinv + (J << 4);
+    const double* Mw = K + tile_off(J, J);
     double b0, b1, b2, b3;
     ld4(b + (J << 2), b0, b1, b2, b3);
     const double m00 = Mw[0];
@@ -248,10 +245,10 @@ __device__ inline void solve_forward_tiles(const double* K, const double* Dinv, 
     __syncwarp();
   }
 }
-__device__ inline void solve_backward_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
+__device__ inline void solve_backward_tiles(const double* K, double* b, int nb, int lane) {
   JMPC_PRAGMA_J
   for (int J = nb - 1; J >= 0; --J) {                 // backward: L' x = y
-    const double* Mw = Dinv + (J << 4);
+    const double* Mw = K + tile_off(J, J);
     double y0, y1, y2, y3;
     ld4(b + (J << 2), y0, y1, y2, y3);
     const double m00 = Mw[0];
@@ -309,9 +306,9 @@ __device__ inline void symv_tiles(const double* P, const double* x, int nb, int 
 // solve in the same layout -- block entries fetched by shuffle, no __syncwarp -- was measured too: 20 % shorter for
 // a warp that runs alone, but 2.3x the instructions and 3x the shared-memory wavefronts of solve_tiles, and 12 %
 // slower on a full batch; it was dropped.)
-__device__ inline void solve_tiles(const double* K, const double* Dinv, double* b, int nb, int lane) {
-  solve_forward_tiles(K, Dinv, b, nb, lane);
-  solve_backward_tiles(K, Dinv, b, nb, lane);
+__device__ inline void solve_tiles(const double* K, double* b, int nb, int lane) {
+  solve_forward_tiles(K, b, nb, lane);
+  solve_backward_tiles(K, b, nb, lane);
 }
 
 // y = P x for a symmetric P on tiles (diagonal tiles stored full), x in shared memory (4 * nb entries); lane k < T gets
@@ -351,8 +348,7 @@ __global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, cons
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, nb = nblk(n), n4 = nb << 2;
   double* K = sm;
-  double* Dinv = K + tiles_doubles(n);
-  double* rhs = Dinv + 16 * nb;
+  double* rhs = K + tiles_doubles(n);
   double* xv = rhs + n4;
   unsigned short* lut = reinterpret_cast<unsigned short*>(xv + n4);
   chol_lut_build(lut, nb, lane, 32);
@@ -371,8 +367,8 @@ __global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, cons
   if (lane < n) prod[lane] = y0;
   if (lane + 32 < n) prod[lane + 32] = y1;
   __syncwarp();
-  const bool good = chol_tiles(K, Dinv, nb, lane, lut);
-  solve_tiles(K, Dinv, rhs, nb, lane);
+  const bool good = chol_tiles(K, nb, lane, lut);
+  solve_tiles(K, rhs, nb, lane);
   __syncwarp();
   for (int i = lane; i < n; i += 32) sol[i] = rhs[i];
   if (lane == 0) *ok = good ? 1 : 0;

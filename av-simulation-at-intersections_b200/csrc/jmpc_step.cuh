@@ -85,7 +85,6 @@ __host__ __device__ inline int k_region_doubles(int T) {
 __host__ __device__ inline int warp_smem_doubles(int T) {
   const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
   return k_region_doubles(T)    // K / L on 4x4 tiles (and the condensing's moment tables)
-         + 16 * nblk(n)         // inverses of the factor's diagonal blocks
          + 4 * n4               // u, q, rhs, grad
          + 14 * T1e             // prefix sums ca, cb, cc, ck; stage weights W11, W12, W22, qv, qpsi; WeX, WeY, epsi; vb, th
          + 4 * Te               // per-iteration row weights wA, wD, wR, SW
@@ -213,7 +212,7 @@ __device__ inline int nearest_index(const double* __restrict__ cx, const double*
 
 // ---- per-warp shared-memory views --------------------------------------------------------------------
 struct WarpMem {
-  double *K, *Dinv, *u, *q, *rhs, *grad;
+  double *K, *u, *q, *rhs, *grad;
   double *ca, *cb, *cc, *ck;
   double *W11, *W12, *W22, *qv, *qpsi;
   double *WeX, *WeY, *epsi, *vb, *th;
@@ -224,7 +223,6 @@ struct WarpMem {
     const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
     double* p = base;
     K = p; p += k_region_doubles(T);
-    Dinv = p; p += 16 * nblk(n);
     u = p; p += n4; q = p; p += n4; rhs = p; p += n4; grad = p; p += n4;
     // grad .. epsi are dead while the solver runs: 4 (2T) + 7 (T + 1) >= 8T doubles, the solver's row stash
     ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
@@ -681,7 +679,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
       // the factorisation (one triangular sweep out of four per iteration saved).
       if (lane < T) { M.rhs[lane] = -g0 - ra_p; M.rhs[T + lane] = -g1 - rd_p; }
       __syncwarp();
-      const bool clean = chol_tiles(M.K, M.Dinv, nb, lane, lut, M.rhs);     // non-positive pivots are replaced, never fatal
+      const bool clean = chol_tiles(M.K, nb, lane, lut, M.rhs);     // non-positive pivots are replaced, never fatal
       JMPC_TOCK(ts_, 4);
       // Numerical breakdown of the factorisation (a pivot lost to roundoff, w ~ 1e13 by then) on an iterate that is
       // already two orders inside the reduced tolerances: stop here.  The step computed from the patched factor is
@@ -713,13 +711,13 @@ __device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, con
           if (lane < T) { M.rhs[lane] = -g0 - ra; M.rhs[T + lane] = -g1 - rd; }
           __syncwarp();
           JMPC_TOCK(ts_, 5);
-          solve_forward_tiles(M.K, M.Dinv, M.rhs, nb, lane);
+          solve_forward_tiles(M.K, M.rhs, nb, lane);
         } else {
 #pragma unroll
           for (int r = 0; r < 4; ++r) { dlh[r] = lh[r] * sh[r]; dll[r] = ll[r] * sl[r]; }
           JMPC_TOCK(ts_, 5);
         }
-        solve_backward_tiles(M.K, M.Dinv, M.rhs, nb, lane);
+        solve_backward_tiles(M.K, M.rhs, nb, lane);
         __syncwarp();
         if (phase == 1 && lane == 0 && it + 1 < A.max_iters) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
         const double du0 = (lane < T) ? M.rhs[lane] : 0.0, du1 = (lane < T) ? M.rhs[T + lane] : 0.0;
@@ -945,7 +943,11 @@ template <int TT>
 #ifndef JMPC_MINBLOCKS
 #define JMPC_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, JMPC_MINBLOCKS) mpc_step_kernel(const __grid_constant__ StepArgs A) {
+#ifndef JMPC_WPB
+#define JMPC_WPB 4                 // warps per block; JMPC_WPB x JMPC_MINBLOCKS resident warps per SM set the register budget
+#endif
+__global__ void __launch_bounds__(32 * JMPC_WPB, JMPC_MINBLOCKS) mpc_step_kernel(
+    const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
