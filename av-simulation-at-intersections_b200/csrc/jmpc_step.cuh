@@ -439,53 +439,64 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
       if (lane < n4 - n) pscr[elem_off(n + lane, n + lane)] = 1.0;
     }
     {
-      int i = 0, j = lane;
-      while (j > i) { j -= i + 1; ++i; }
-      for (int e = lane; e < n * (n + 1) / 2; e += 32) {
-        const bool id = i >= T, jd = j >= T;
-        const int ki = id ? i - T : i, kj = jd ? j - T : j;
-        const int t0 = max(ki, kj) + 1;
-        // S(W; F, G)(F0, G0) = sum_{t >= t0} W_t (F_t - F0)(G_t - G0) from the suffix moments
-        const double* mom = M.K + t0;
-        const int ms = even_up(T + 1);
-        auto S = [&](int mW, int mWF, int mWG, int mWFG, double F0, double G0) -> double {
-          return mom[mWFG * ms] - G0 * mom[mWF * ms] - F0 * mom[mWG * ms] + F0 * G0 * mom[mW * ms];
-        };
-        double acc;
-        if (!id) {                       // accel x accel: sX = dt (A - A0), sY = dt (C - C0), sV = dt
-          const double ai = M.ca[ki + 1], ci = M.cc[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-          acc = S(MOM_11, MOM_11_A, MOM_11_A, MOM_11_AA, ai, aj) + S(MOM_12, MOM_12_A, MOM_12_C, MOM_12_AC, ai, cj)
-              + S(MOM_12, MOM_12_C, MOM_12_A, MOM_12_AC, ci, aj) + S(MOM_22, MOM_22_C, MOM_22_C, MOM_22_CC, ci, cj)
-              + mom[MOM_QV * ms];
-          acc *= dt2;
-        } else if (!jd) {                // steer (row) x accel (col): sX_i = -g (B - B0), sY_i = g (K - K0)
-          const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-          acc = -S(MOM_11, MOM_11_B, MOM_11_A, MOM_11_AB, bi, aj) - S(MOM_12, MOM_12_B, MOM_12_C, MOM_12_BC, bi, cj)
-              + S(MOM_12, MOM_12_K, MOM_12_A, MOM_12_AK, kki, aj) + S(MOM_22, MOM_22_K, MOM_22_C, MOM_22_CK, kki, cj);
-          acc *= M.wA[ki] * dt;
-        } else {                         // steer x steer, plus the yaw weight
-          const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], bj = M.cb[kj + 1], kkj = M.ck[kj + 1];
-          acc = S(MOM_11, MOM_11_B, MOM_11_B, MOM_11_BB, bi, bj) - S(MOM_12, MOM_12_B, MOM_12_K, MOM_12_BK, bi, kkj)
-              - S(MOM_12, MOM_12_K, MOM_12_B, MOM_12_BK, kki, bj) + S(MOM_22, MOM_22_K, MOM_22_K, MOM_22_KK, kki, kkj)
-              + mom[MOM_QPSI * ms];
-          acc *= M.wA[ki] * M.wA[kj];
-        }
-        acc *= 2.0;
-        if (id == jd) {                  // input and input-rate weights (mpc.py:180-187)
-          const double rd_w = id ? Rdd : Rda;
-          if (ki == kj) {
-            const bool e_t = (end_mask >> ki) & 1u;
-            const double r = id ? (e_t ? Red : Rd_) : (e_t ? Rea : Ra);
-            const int nb = (T >= 2) ? ((ki == 0 || ki == T - 1) ? 1 : 2) : 0;
-            acc += 2.0 * r + 2.0 * rd_w * nb;
-          } else if (ki == kj + 1) {
-            acc -= 2.0 * rd_w;
-          }
-        }
+      // Three passes, one per block type (accel x accel, steer x accel, steer x steer): a single pass over the packed
+      // triangle mixed steer x accel and steer x steer entries in every group of 32, so the warp executed both paths.
+      const int ms = even_up(T + 1);
+      // S(W; F, G)(F0, G0) = sum_{t >= t0} W_t (F_t - F0)(G_t - G0) from the suffix moments
+      auto S = [&](const double* mom, int mW, int mWF, int mWG, int mWFG, double F0, double G0) -> double {
+        return mom[mWFG * ms] - G0 * mom[mWF * ms] - F0 * mom[mWG * ms] + F0 * G0 * mom[mW * ms];
+      };
+      auto store = [&](int i, int j, double acc) {
         pscr[elem_off(i, j)] = acc;
         if (i != j && (i >> 2) == (j >> 2)) pscr[elem_off(j, i)] = acc;      // diagonal tiles are stored full
-        j += 32;
-        while (j > i) { j -= i + 1; ++i; }
+      };
+      // input and input-rate weights on the (block-)diagonal and first sub-diagonal (mpc.py:180-187)
+      auto input_weights = [&](int ki, int kj, double r_run, double r_end, double rd_w) -> double {
+        if (ki == kj) {
+          const bool e_t = (end_mask >> ki) & 1u;
+          const int nbr = (T >= 2) ? ((ki == 0 || ki == T - 1) ? 1 : 2) : 0;
+          return 2.0 * (e_t ? r_end : r_run) + 2.0 * rd_w * nbr;
+        }
+        return (ki == kj + 1) ? -2.0 * rd_w : 0.0;
+      };
+      {                                  // accel x accel: sX = dt (A - A0), sY = dt (C - C0), sV = dt
+        int ki = 0, kj = lane;
+        while (kj > ki) { kj -= ki + 1; ++ki; }
+        for (int e = lane; e < tri(T); e += 32) {
+          const double* mom = M.K + ki + 1;                      // t0 = max(ki, kj) + 1 = ki + 1
+          const double ai = M.ca[ki + 1], ci = M.cc[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
+          double acc = S(mom, MOM_11, MOM_11_A, MOM_11_A, MOM_11_AA, ai, aj) + S(mom, MOM_12, MOM_12_A, MOM_12_C, MOM_12_AC, ai, cj)
+                     + S(mom, MOM_12, MOM_12_C, MOM_12_A, MOM_12_AC, ci, aj) + S(mom, MOM_22, MOM_22_C, MOM_22_C, MOM_22_CC, ci, cj)
+                     + mom[MOM_QV * ms];
+          acc = 2.0 * dt2 * acc + input_weights(ki, kj, Ra, Rea, Rda);
+          store(ki, kj, acc);
+          kj += 32;
+          while (kj > ki) { kj -= ki + 1; ++ki; }
+        }
+      }
+      for (int e = lane; e < T * T; e += 32) {                   // steer (row) x accel (col): sX_i = -g (B - B0), sY_i = g (K - K0)
+        const int ki = e / T, kj = e - ki * T;
+        const double* mom = M.K + max(ki, kj) + 1;
+        const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
+        double acc = -S(mom, MOM_11, MOM_11_B, MOM_11_A, MOM_11_AB, bi, aj) - S(mom, MOM_12, MOM_12_B, MOM_12_C, MOM_12_BC, bi, cj)
+                   + S(mom, MOM_12, MOM_12_K, MOM_12_A, MOM_12_AK, kki, aj) + S(mom, MOM_22, MOM_22_K, MOM_22_C, MOM_22_CK, kki, cj);
+        acc *= 2.0 * M.wA[ki] * dt;
+        store(T + ki, kj, acc);
+      }
+      {                                  // steer x steer, plus the yaw weight
+        int ki = 0, kj = lane;
+        while (kj > ki) { kj -= ki + 1; ++ki; }
+        for (int e = lane; e < tri(T); e += 32) {
+          const double* mom = M.K + ki + 1;
+          const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], bj = M.cb[kj + 1], kkj = M.ck[kj + 1];
+          double acc = S(mom, MOM_11, MOM_11_B, MOM_11_B, MOM_11_BB, bi, bj) - S(mom, MOM_12, MOM_12_B, MOM_12_K, MOM_12_BK, bi, kkj)
+                     - S(mom, MOM_12, MOM_12_K, MOM_12_B, MOM_12_BK, kki, bj) + S(mom, MOM_22, MOM_22_K, MOM_22_K, MOM_22_KK, kki, kkj)
+                     + mom[MOM_QPSI * ms];
+          acc = 2.0 * M.wA[ki] * M.wA[kj] * acc + input_weights(ki, kj, Rd_, Red, Rdd);
+          store(T + ki, T + kj, acc);
+          kj += 32;
+          while (kj > ki) { kj -= ki + 1; ++ki; }
+        }
       }
     }
     // linear term
