@@ -320,7 +320,7 @@ def main():
         pass
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1i_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1k_traffic.json")) as f:
             tr = json.load(f)
         if B == 4096 and T == 20:
             traffic = tr["dram_bytes_per_launch"]          # from the committed ncu --set full capture, per launch
@@ -356,7 +356,7 @@ def main():
                                        "so it is reported beside the headline, not as it"},
         "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
-                     "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1i_traffic.json)",
+                     "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1k_traffic.json)",
                      "peak_source": "jmpc_measure_fma_peak: register-resident FP64 FMA loop on all SMs, measured in this run "
                                     "(MEASURED_PEAKS.json holds no FP64 figure)",
                      "flops_per_solve": flops_per_solve(T, mean_iters), "kernel": "jmpc::mpc_step_kernel",
