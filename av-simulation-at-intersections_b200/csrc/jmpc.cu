@@ -338,8 +338,11 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
       CK(cudaMalloc(&h->d_hint, (size_t)h->max_B * sizeof(int)));
       CK(cudaMemsetAsync(h->d_hint, 0, (size_t)h->max_B * sizeof(int), s));
     }
-    // ordering only matters while the batch is a few waves of the resident warps deep
-    if (B > g.warps && B <= 16 * g.warps) {
+    // ordering only matters while the batch is a few waves of the resident warps deep (measured: no gain at 28 waves,
+    // where the one-block ordering kernel starts to cost as much as it saves)
+    long long sched_max_waves = 16;
+    if (const char* e = getenv("JMPC_SCHED_MAX_WAVES")) sched_max_waves = atoll(e);
+    if (B > g.warps && (long long)B <= sched_max_waves * (long long)g.warps) {
       const bool have_hint = h->schedule >= 2 && h->hint_B == B && h->hint_T == T;
       jmpc::ParamVec dv;
       memcpy(dv.v, h->defaults, sizeof dv.v);
