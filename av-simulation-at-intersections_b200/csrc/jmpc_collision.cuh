@@ -41,9 +41,11 @@ struct CollisionArgs {
   const int* skip;                                   // [B] or nullptr: skip[b] != 0 -> instance left untouched
 };
 
-// dynamic shared memory of one warp: arc[arc_cap] | ocx[n_obs][kMaxObsFrames][2] | ocy[...] | ego_idx[kMaxEgoFrames]
+// dynamic shared memory of one warp: arc[arc_cap] | ocx[n_obs][kMaxObsFrames][2] | ocy[...] | bbox[kMaxObstacles][4] |
+// ego_idx[kMaxEgoFrames]
 __host__ __device__ inline size_t collision_warp_smem_bytes(int arc_cap, int n_obs) {
-  return ((size_t)arc_cap + (size_t)4 * n_obs * kMaxObsFrames) * sizeof(double) + (size_t)kMaxEgoFrames * sizeof(short);
+  return ((size_t)arc_cap + (size_t)4 * n_obs * kMaxObsFrames + 4 * kMaxObstacles) * sizeof(double) +
+         (size_t)kMaxEgoFrames * sizeof(short);
 }
 
 // circle centres of a pose: same operation order as trajectories.py:27-34 with a zero lateral offset
@@ -80,12 +82,14 @@ struct CollisionSmem {
   double* arc;          // segment lengths, then running arc length
   double* ocx;          // obstacle circle centres [obstacle][frame][circle]
   double* ocy;
+  double* bbox;         // per obstacle: min x, max x, min y, max y of its predicted circle centres
   short* ego_idx;       // kept path points (relative to agent_idx)
   __device__ CollisionSmem(unsigned char* base, int arc_cap, int n_obs) {
     arc = reinterpret_cast<double*>(base);
     ocx = arc + arc_cap;
     ocy = ocx + (size_t)2 * n_obs * kMaxObsFrames;
-    ego_idx = reinterpret_cast<short*>(ocy + (size_t)2 * n_obs * kMaxObsFrames);
+    bbox = ocy + (size_t)2 * n_obs * kMaxObsFrames;
+    ego_idx = reinterpret_cast<short*>(bbox + 4 * kMaxObstacles);
   }
   __device__ __forceinline__ int oi(int ob, int frame, int circle) const { return (ob * kMaxObsFrames + frame) * 2 + circle; }
 };
@@ -185,8 +189,27 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
   }
   __syncwarp();
 
+  // Bounding box of every obstacle's predicted circle centres.  An ego circle further than the reach outside the box
+  // cannot touch any frame-shifted copy of that obstacle (the copies are clamped to the predicted frames), so the
+  // whole group of 2 * span pair tests is skipped -- a conservative test, the decisions stay bit-exact.
+  for (int ob = 0; ob < A.n_obs; ++ob) {
+    double x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+    for (int j = lane; j < 2 * n_of; j += 32) {
+      const double ox = S.ocx[S.oi(ob, j >> 1, j & 1)], oy = S.ocy[S.oi(ob, j >> 1, j & 1)];
+      x0 = fmin(x0, ox); x1 = fmax(x1, ox); y0 = fmin(y0, oy); y1 = fmax(y1, oy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x0 = fmin(x0, __shfl_xor_sync(full, x0, o)); x1 = fmax(x1, __shfl_xor_sync(full, x1, o));
+      y0 = fmin(y0, __shfl_xor_sync(full, y0, o)); y1 = fmax(y1, __shfl_xor_sync(full, y1, o));
+    }
+    if (lane == 0) { S.bbox[4 * ob] = x0; S.bbox[4 * ob + 1] = x1; S.bbox[4 * ob + 2] = y0; S.bbox[4 * ob + 3] = y1; }
+  }
+  __syncwarp();
+
   // ---- C. first touching pair in the reference's row order ------------------------------------------
   const double reach = 2.0 * A.radius;
+  const double pad = reach * (1.0 + 1e-9);
   const double reach2 = reach * reach, reach2_lo = reach2 * (1.0 - 1e-12), reach2_hi = reach2 * (1.0 + 1e-12);
   const int span = 2 * A.frame_window + 1;
   const int copies = A.n_obs * span;
@@ -202,6 +225,9 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
     for (int ac = 0; ac < 2 && best == 0x7fffffff; ++ac) {
       const double ax = ac ? rx[ei] : fx[ei], ay = ac ? ry[ei] : fy[ei];
       for (int ob = 0; ob < A.n_obs && best == 0x7fffffff; ++ob) {
+        if (ax < S.bbox[4 * ob] - pad || ax > S.bbox[4 * ob + 1] + pad || ay < S.bbox[4 * ob + 2] - pad ||
+            ay > S.bbox[4 * ob + 3] + pad)
+          continue;
         const int pbase = ac * 2 * copies + ob * span * 2;
         for (int q = lane; q < 2 * span; q += 32) {
           const int oc = q & 1, off = (q >> 1) - A.frame_window;
