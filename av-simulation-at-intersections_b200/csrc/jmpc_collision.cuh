@@ -170,19 +170,41 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
   }
 
   // ---- B. obstacle predictions (moving_obstacles_prediction.py:21-47) ------------------------------
-  const int n_of = min((int)ceil(A.horizon_s / dt), kMaxObsFrames);
+  // The yaw / speed recurrences need no trigonometry, so they are walked first (one lane per obstacle); then all lanes
+  // evaluate sin / cos of the n_of + 1 distinct headings in parallel; then the positions are accumulated in sequence.
+  // Each value is produced by the same operations in the same order as in the reference's loop, which evaluates
+  // sin / cos of every heading twice (2 x 35 sequential sincos per obstacle on 2-4 active lanes before).
+  const int n_of = min((int)ceil(A.horizon_s / dt), kMaxObsFrames - 1);
   if (lane < A.n_obs) {
     const double* o = A.obstacles + ((size_t)b * A.n_obs + lane) * 6;
-    double x = o[0], y = o[1], vo = o[2], yaw = o[3];
+    double vo = o[2], yaw = o[3];
     const double acc = o[4], tn = tan(o[5]);
+    S.ocy[S.oi(lane, 0, 0)] = yaw;                   // scratch: heading k in ocy[ob][k][0]
     for (int k = 0; k < n_of; ++k) {
-      double s, c;
-      sincos(yaw, &s, &c);
+      vo = __dadd_rn(vo, __dmul_rn(acc, dt));
+      yaw = __dadd_rn(yaw, __dmul_rn(__dmul_rn(vo / L, tn), dt));
+      S.ocy[S.oi(lane, k + 1, 0)] = yaw;
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < A.n_obs * (n_of + 1); j += 32) {
+    const int ob = j / (n_of + 1), k = j - ob * (n_of + 1);
+    double s, c;
+    sincos(S.ocy[S.oi(ob, k, 0)], &s, &c);
+    S.ocx[S.oi(ob, k, 0)] = c; S.ocx[S.oi(ob, k, 1)] = s;      // scratch: cos / sin of heading k in ocx[ob][k][0 / 1]
+  }
+  __syncwarp();
+  if (lane < A.n_obs) {
+    const double* o = A.obstacles + ((size_t)b * A.n_obs + lane) * 6;
+    double x = o[0], y = o[1], vo = o[2];
+    const double acc = o[4];
+    double c = S.ocx[S.oi(lane, 0, 0)], s = S.ocx[S.oi(lane, 0, 1)];
+    for (int k = 0; k < n_of; ++k) {
       x = __dadd_rn(x, __dmul_rn(__dmul_rn(vo, c), dt));
       y = __dadd_rn(y, __dmul_rn(__dmul_rn(vo, s), dt));
       vo = __dadd_rn(vo, __dmul_rn(acc, dt));
-      yaw = __dadd_rn(yaw, __dmul_rn(__dmul_rn(vo / L, tn), dt));
-      sincos(yaw, &s, &c);
+      c = S.ocx[S.oi(lane, k + 1, 0)]; s = S.ocx[S.oi(lane, k + 1, 1)];       // heading after the step
+      // slot k is overwritten with the circle centres only now that its cos / sin have been consumed
       circle_centre(x, y, c, s, A.off_front, S.ocx[S.oi(lane, k, 0)], S.ocy[S.oi(lane, k, 0)]);
       circle_centre(x, y, c, s, A.off_rear, S.ocx[S.oi(lane, k, 1)], S.ocy[S.oi(lane, k, 1)]);
     }
