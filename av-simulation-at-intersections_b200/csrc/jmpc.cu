@@ -738,6 +738,36 @@ int32_t jmpc_episode_post(jmpc_handle h, int32_t B, double* state, const int32_t
   return 0;
 }
 
+int32_t jmpc_episode_post_dev(jmpc_handle h, int32_t B, double* state, const int32_t* course_id, const double* record,
+                              const double* params, int32_t* target_ind, int32_t* steps, int32_t* done, double* di,
+                              int32_t* warm, double* history_base, int32_t history_rows, int32_t* flags_base,
+                              const int32_t* flag, const int32_t* iter_dev, double dt_loop, void* stream) {
+  if (!h) return fail("jmpc_episode_post_dev: NULL handle");
+  if (B < 0 || B > h->max_B) return fail("jmpc_episode_post_dev: B out of range");
+  if (!state || !record || !target_ind || !steps || !done || !di || !iter_dev) return fail("jmpc_episode_post_dev: NULL array");
+  if (B == 0) return 0;
+  CK(cudaSetDevice(h->device));
+  jmpc::EpisodeArgs a;
+  fill_episode_args(h, a, B, course_id, params);
+  a.state = state; a.record = record; a.target_ind = target_ind; a.steps = steps; a.done = done; a.di = di;
+  a.warm = warm; a.history = nullptr; a.t_now = 0.0;
+  a.iter_dev = iter_dev; a.history_base = history_base; a.history_rows = history_rows; a.flags_base = flags_base;
+  a.flag = flag; a.dt_loop = dt_loop;
+  jmpc::episode_post_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int32_t jmpc_counter_add(jmpc_handle h, int32_t* counter, int32_t delta, void* stream) {
+  if (!h || !counter) return fail("jmpc_counter_add: NULL argument");
+  CK(cudaSetDevice(h->device));
+  jmpc::counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
 int32_t jmpc_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, double* obstacles, const int32_t* done,
                            double dt, void* stream) {
   if (!h) return fail("jmpc_obstacle_step: NULL handle");

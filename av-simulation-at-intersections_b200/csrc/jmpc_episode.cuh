@@ -39,6 +39,14 @@ struct EpisodeArgs {
   const double* record;     // [B][JMPC_RECORD_LEN] from the step kernel
   double* history;          // [B][8] slice for this step: x, y, yaw, v, t, delta, a, xref_deviation; or nullptr
   double t_now;
+  // device-indexed variant (jmpc_episode_post_dev): the loop iteration is read from device memory, so that a
+  // captured CUDA graph of the loop body can be replayed without per-iteration host arguments
+  const int* iter_dev;      // nullptr -> use history / t_now above
+  double* history_base;     // [rows][B][8] or nullptr
+  int* flags_base;          // [rows][B] or nullptr: per-iteration copy of the collision flags
+  const int* flag;          // [B]
+  int history_rows;
+  double dt_loop;
 };
 
 // One warp per episode: goal test, then the ego's index on the full course.
@@ -82,6 +90,15 @@ __global__ void __launch_bounds__(128) episode_pre_kernel(const EpisodeArgs A) {
 __global__ void episode_post_kernel(const EpisodeArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
+  double* history = A.history;
+  double t_now = A.t_now;
+  if (A.iter_dev) {
+    const int it = *A.iter_dev;
+    const bool in_rows = it < A.history_rows;
+    history = (A.history_base && in_rows) ? A.history_base + (size_t)it * A.B * 8 : nullptr;
+    t_now = (double)(it + 1) * A.dt_loop;
+    if (A.flags_base && A.flag && in_rows) A.flags_base[(size_t)it * A.B + b] = A.flag[b];     // all episodes, as the host copy did
+  }
   if (A.done[b]) return;
   const double* prm = A.params ? A.params + (size_t)b * JMPC_NPARAM : A.defaults.v;
   const double* rec = A.record + (size_t)b * JMPC_RECORD_LEN;
@@ -115,12 +132,14 @@ __global__ void episode_post_kernel(const EpisodeArgs A) {
   v = fmax(fmin(v, prm[JMPC_P_SIM_MAX_SPEED]), prm[JMPC_P_MIN_SPEED]);
   A.state[4 * b] = x; A.state[4 * b + 1] = y; A.state[4 * b + 2] = v; A.state[4 * b + 3] = yaw;
   A.steps[b] += 1;
-  if (A.history) {
-    double* hrow = A.history + (size_t)b * 8;        // History.store (simulation.py:76-84), raw delta as stored there
-    hrow[0] = x; hrow[1] = y; hrow[2] = yaw; hrow[3] = v; hrow[4] = A.t_now + dt; hrow[5] = delta; hrow[6] = acc;
+  if (history) {
+    double* hrow = history + (size_t)b * 8;          // History.store (simulation.py:76-84), raw delta as stored there
+    hrow[0] = x; hrow[1] = y; hrow[2] = yaw; hrow[3] = v; hrow[4] = t_now + dt; hrow[5] = delta; hrow[6] = acc;
     hrow[7] = dev;
   }
 }
+
+__global__ void counter_add_kernel(int* counter, int delta) { *counter += delta; }
 
 // Constant-input obstacle motion, one thread per obstacle: obstacles [B][n_obs][6] = x, y, v, yaw, a, steer.
 __global__ void obstacle_step_kernel(int count, double* __restrict__ obs, const int* __restrict__ done, int n_obs,

@@ -51,6 +51,9 @@ SIGNATURES = {
                                     C.c_void_p]),
     "jmpc_episode_pre": (C.c_int32, [C.c_void_p, C.c_int32] + [C.c_void_p] * 7 + [C.c_double, C.c_double, C.c_void_p]),
     "jmpc_episode_post": (C.c_int32, [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_double, C.c_void_p]),
+    "jmpc_episode_post_dev": (C.c_int32, [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_double, C.c_void_p]),
+    "jmpc_counter_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "jmpc_obstacle_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "jmpc_launch_count": (C.c_int64, [C.c_void_p]),
     "jmpc_measure_fma_peak": (C.c_int32, [C.c_void_p, c_f64p, c_f64p]),

@@ -51,6 +51,7 @@ class BatchedEpisodes:
         self.history = torch.full((self.max_steps, B, 8), float("nan"), dtype=f64, device=self.dev) if record_history else None
         self.flags = torch.zeros(self.max_steps, B, dtype=i32, device=self.dev) if record_history else None
         self.iteration = 0
+        self.iter_dev = torch.zeros(1, dtype=i32, device=self.dev)     # the same counter on the device (graph replay)
         engine.set_skip_mask(self.done)          # finished episodes cost nothing in the step / collision kernels
 
     def _p(self, ten):
@@ -71,24 +72,56 @@ class BatchedEpisodes:
             self.v.copy_(self.state[:, 2])
             e.collision(self.agent_idx, self.v, obs, self.frame_window, self.margin, self.flag, self.course_len,
                         course_id=self.course_id, params=self.params, horizon_s=self.horizon_s)
-            if self.flags is not None and i < self.max_steps:
-                self.flags[i].copy_(self.flag)
+            has_flags = True
+        else:
+            has_flags = False
         e.step(self.state, self.target_ind, self.oa, self.od, self.out, course_id=self.course_id,
                course_len=self.course_len, warm=self.warm, params=self.params)
-        hist = self.history[i] if (self.history is not None and i < self.max_steps) else None
-        _cabi.check(lib.jmpc_episode_post(e._h, self.B, self._p(self.state), self._p(self.course_id), self._p(self.out.record),
-                                          self._p(self.params), self._p(self.target_ind), self._p(self.steps),
-                                          self._p(self.done), self._p(self.di), self._p(self.warm), self._p(hist),
-                                          float((i + 1) * e.dt), stream), "jmpc_episode_post")
+        # history row, flag copy and time stamp are indexed by the device-side iteration counter: nothing in the loop
+        # body depends on a host value that changes from one iteration to the next (except a script's frame)
+        _cabi.check(lib.jmpc_episode_post_dev(
+            e._h, self.B, self._p(self.state), self._p(self.course_id), self._p(self.out.record), self._p(self.params),
+            self._p(self.target_ind), self._p(self.steps), self._p(self.done), self._p(self.di), self._p(self.warm),
+            self._p(self.history), self.max_steps, self._p(self.flags) if has_flags else None, self._p(self.flag),
+            self._p(self.iter_dev), float(e.dt), stream), "jmpc_episode_post_dev")
         if self.obstacles is not None and self.obstacles.shape[1] > 0:
             _cabi.check(lib.jmpc_obstacle_step(e._h, self.B, int(self.obstacles.shape[1]), self._p(self.obstacles),
                                                self._p(self.done), float(e.dt), stream), "jmpc_obstacle_step")
+        _cabi.check(lib.jmpc_counter_add(e._h, self._p(self.iter_dev), 1, stream), "jmpc_counter_add")
         self.iteration += 1
 
-    def run(self, max_steps: Optional[int] = None, check_every: int = 8):
-        """Iterate until every episode reached its goal (or max_steps).  Returns a dict of numpy results."""
+    def run(self, max_steps: Optional[int] = None, check_every: int = 8, use_graph: bool = False):
+        """Iterate until every episode reached its goal (or max_steps).  Returns a dict of numpy results.
+
+        With constant-input obstacles the loop body takes no per-iteration host argument, so with `use_graph`
+        `check_every` iterations are captured once as a CUDA graph and replayed (one launch per 8 iterations instead
+        of ~50 driver calls).  Measured on 4096 episodes (T = 13, ~290 iterations, 0.164 s): the capture costs more
+        than the replays save (0.167-0.183 s), the loop is not launch bound at this size, so it is off by default;
+        it pays for long runs of small batches."""
+        torch = self.torch
         max_steps = int(max_steps or self.max_steps)
+        graph = None
+        if use_graph and self.script is None and max_steps - self.iteration > 2 * check_every:
+            self.iterate()                                    # eager once: scratch allocations, kernel attributes
+            torch.cuda.synchronize(self.e.device)
+            it0 = self.iteration
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="relaxed"):
+                    for _ in range(check_every):
+                        self.iterate()
+                self.iteration = it0                          # capturing executed nothing
+            except Exception:                                 # capture refused: plain launches
+                graph = None
+                self.iteration = it0
+                torch.cuda.synchronize(self.e.device)
         while self.iteration < max_steps:
+            if graph is not None and max_steps - self.iteration >= check_every:
+                graph.replay()
+                self.iteration += check_every
+                if bool((self.done != 0).all().item()):
+                    break
+                continue
             self.iterate()
             if self.iteration % check_every == 0 and bool((self.done != 0).all().item()):
                 break

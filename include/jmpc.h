@@ -212,6 +212,11 @@ int32_t jmpc_plant_step(jmpc_handle h, int32_t B, double* state, const double* a
  *                      mpc.py:298-301), stores target_ind, sets warm (0 after a failed solve: the next step starts
  *                      from zeros, mpc.py:225-227), increments steps and, if history != NULL, writes one
  *                      History row [B][8] = x, y, yaw, v, t, delta, a, xref_deviation (simulation.py:76-84).
+ *   jmpc_episode_post_dev: the same with the loop iteration i read from device memory (iter_dev): the History row goes
+ *                      to history_base[i] ([rows][B][8], skipped once i >= rows), the collision flags are copied to
+ *                      flags_base[i] ([rows][B]), t = (i + 1) * dt_loop.  With jmpc_counter_add (*counter += delta,
+ *                      one thread) closing the iteration, the whole loop body has no per-iteration host argument and
+ *                      can be captured once as a CUDA graph and replayed.
  *   jmpc_obstacle_step: constant-input motion of obstacles [B][n_obs][6] (moving_obstacles_prediction.py:21-29). */
 int32_t jmpc_episode_pre(jmpc_handle h, int32_t B, const double* state, const int32_t* course_id,
                          const int32_t* course_len, const int32_t* target_ind, const int32_t* steps,
@@ -219,6 +224,11 @@ int32_t jmpc_episode_pre(jmpc_handle h, int32_t B, const double* state, const in
 int32_t jmpc_episode_post(jmpc_handle h, int32_t B, double* state, const int32_t* course_id, const double* record,
                           const double* params, int32_t* target_ind, int32_t* steps, int32_t* done, double* di,
                           int32_t* warm, double* history, double t_now, void* stream);
+int32_t jmpc_episode_post_dev(jmpc_handle h, int32_t B, double* state, const int32_t* course_id, const double* record,
+                              const double* params, int32_t* target_ind, int32_t* steps, int32_t* done, double* di,
+                              int32_t* warm, double* history_base, int32_t history_rows, int32_t* flags_base,
+                              const int32_t* flag, const int32_t* iter_dev, double dt_loop, void* stream);
+int32_t jmpc_counter_add(jmpc_handle h, int32_t* counter, int32_t delta, void* stream);
 int32_t jmpc_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, double* obstacles, const int32_t* done,
                            double dt, void* stream);
 
