@@ -46,7 +46,7 @@ def bytes_per_solve(T: int) -> float:
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
