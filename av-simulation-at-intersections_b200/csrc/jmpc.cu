@@ -43,6 +43,7 @@ struct jmpc_handle_s {
   // courses
   double *d_cx = nullptr, *d_cy = nullptr, *d_cyaw = nullptr;
   double *d_ccfx = nullptr, *d_ccfy = nullptr, *d_ccrx = nullptr, *d_ccry = nullptr;   // collision-circle tables
+  double* d_arc = nullptr; long long* d_arc_off = nullptr;                                // arc-length tables (collision kernel)
   double off_front = 2.86 / 2 + (3.5 / 2 - 1.0), off_rear = 2.86 / 2 - (3.5 / 2 - 1.0), radius = 2.0 / 1.4142135623730951;
   int* d_course_n = nullptr;
   int n_courses = 0, course_stride = 0;
@@ -173,6 +174,34 @@ int refresh_circle_tables(jmpc_handle h) {
   return 0;
 }
 
+// Arc-length tables of the uploaded courses (jmpc_collision.cuh: arc_table_kernel), N (N + 1) / 2 doubles per course;
+// courses are left without a table (the kernel then sums on the fly) once 256 MB are used.
+int refresh_arc_tables(jmpc_handle h) {
+  CK(cudaSetDevice(h->device));
+  if (h->d_arc) { cudaFree(h->d_arc); h->d_arc = nullptr; }
+  if (!h->d_arc_off) CK(cudaMalloc(&h->d_arc_off, (size_t)h->max_courses * sizeof(long long)));
+  std::vector<long long> off(h->n_courses, -1);
+  long long total = 0;
+  const long long cap = (256ll << 20) / (long long)sizeof(double);
+  for (int c = 0; c < h->n_courses; ++c) {
+    const long long n = h->course_n[c], need = n * (n + 1) / 2;
+    if (total + need > cap) continue;
+    off[c] = total; total += need;
+  }
+  if (total > 0) CK(cudaMalloc(&h->d_arc, (size_t)total * sizeof(double)));
+  for (int c = 0; c < h->n_courses; ++c) {
+    if (off[c] < 0) continue;
+    const size_t coff = (size_t)c * h->course_stride;
+    const int n = h->course_n[c];
+    jmpc::arc_table_kernel<<<(n + 63) / 64, 64, 0, h->own_stream>>>(n, h->d_cx + coff, h->d_cy + coff, h->d_arc + off[c]);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
+  CK(cudaMemcpyAsync(h->d_arc_off, off.data(), (size_t)h->n_courses * sizeof(long long), cudaMemcpyHostToDevice, h->own_stream));
+  CK(cudaStreamSynchronize(h->own_stream));
+  return 0;
+}
+
 template <typename F>
 __global__ void fma_peak_kernel(F* out, int iters) {
   F a0 = (F)threadIdx.x * (F)1e-3, a1 = a0 + (F)1, a2 = a0 + (F)2, a3 = a0 + (F)3;
@@ -264,7 +293,7 @@ int32_t jmpc_destroy(jmpc_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaFree(h->d_cx); cudaFree(h->d_cy); cudaFree(h->d_cyaw); cudaFree(h->d_course_n);
-  cudaFree(h->d_ccfx); cudaFree(h->d_ccfy); cudaFree(h->d_ccrx); cudaFree(h->d_ccry);
+  cudaFree(h->d_ccfx); cudaFree(h->d_ccfy); cudaFree(h->d_ccrx); cudaFree(h->d_ccry); cudaFree(h->d_arc); cudaFree(h->d_arc_off);
   cudaFree(h->d_pscratch); cudaFree(h->d_counter); cudaFree(h->d_stage); cudaFree(h->d_order); cudaFree(h->d_hint);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -293,6 +322,7 @@ int32_t jmpc_set_courses(jmpc_handle h, int32_t n_courses, int32_t stride, const
   }
   CK(cudaMemcpy(h->d_course_n, len, n_courses * sizeof(int), cudaMemcpyHostToDevice));
   h->n_courses = n_courses;
+  if (refresh_arc_tables(h)) return -1;
   return refresh_circle_tables(h);
 }
 
@@ -619,6 +649,7 @@ int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const
   jmpc::CollisionArgs a;
   a.B = B; a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
   a.ccfx = h->d_ccfx; a.ccfy = h->d_ccfy; a.ccrx = h->d_ccrx; a.ccry = h->d_ccry;
+  a.arc_tab = getenv("JMPC_NO_ARC_TABLE") ? nullptr : h->d_arc; a.arc_off = h->d_arc_off;
   a.off_front = h->off_front; a.off_rear = h->off_rear; a.radius = h->radius; a.arc_cap = h->max_N;
   a.course_stride = h->course_stride; a.course_id = course_id; a.agent_idx = agent_idx; a.v = v;
   a.obstacles = obstacles; a.n_obs = n_obs; a.frame_window = frame_window; a.margin = margin;

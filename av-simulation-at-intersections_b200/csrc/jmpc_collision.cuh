@@ -38,6 +38,9 @@ struct CollisionArgs {
   const double* params; ParamBlock defaults;
   int* flag; int* course_len_out;
   int arc_cap;                                       // course points the arc-length scan can hold (handle max_N)
+  // Optional per-course table of the running arc lengths from every start index (arc_table_kernel): row a0 of course c
+  // starts at arc_tab + arc_off[c] + a0 * N - a0 (a0 - 1) / 2 and has N - a0 entries; arc_off[c] < 0 = no table
+  const double* arc_tab; const long long* arc_off;
   const int* skip;                                   // [B] or nullptr: skip[b] != 0 -> instance left untouched
 };
 
@@ -65,6 +68,27 @@ __global__ void circle_table_kernel(int n, const double* __restrict__ cx, const 
   sincos(cyaw[i], &s, &c);
   circle_centre(cx[i], cy[i], c, s, off_front, fx[i], fy[i]);
   circle_centre(cx[i], cy[i], c, s, off_rear, rx[i], ry[i]);
+}
+
+// Running arc length of trajectory_full[a0:] for every start index a0 of a course: np.cumsum of the segment lengths,
+// i.e. strictly sequential float64 adds starting at a0 (the partial sums depend on a0 through rounding, so every row
+// is summed on its own; one thread per row).  Built once per course; the collision kernel then reads the row
+// instead of letting one lane re-do up to N sequential adds per instance.
+__host__ __device__ inline long long arc_row_offset(int a0, int N) { return (long long)a0 * N - ((long long)a0 * (a0 - 1)) / 2; }
+__global__ void arc_table_kernel(int N, const double* __restrict__ cx, const double* __restrict__ cy, double* __restrict__ tab) {
+  const int a0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a0 >= N) return;
+  double* row = tab + arc_row_offset(a0, N);
+  double acc = 0.0;
+  for (int i = 0; i < N - a0; ++i) {
+    double seg = 0.0;
+    if (i > 0) {
+      const double dx = cx[a0 + i] - cx[a0 + i - 1], dy = cy[a0 + i] - cy[a0 + i - 1];
+      seg = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    }
+    acc = __dadd_rn(acc, seg);
+    row[i] = acc;
+  }
 }
 
 // dist(a, b) <= reach with numpy's sqrt(dx*dx + dy*dy); the square root is only evaluated when the squared
@@ -122,6 +146,9 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
   }
 
   // ---- A. ego prediction: resample_curve(path, dl_i) ------------------------------------------------
+  const bool have_tab = A.arc_tab && A.arc_off[cid] >= 0 && M == N - a0;
+  const double* arc = have_tab ? A.arc_tab + A.arc_off[cid] + arc_row_offset(a0, N) : S.arc;
+  if (!have_tab) {
   for (int i = lane; i < M; i += 32) {
     double seg = 0.0;
     if (i > 0) {
@@ -136,6 +163,7 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
     for (int i = 0; i < M; ++i) { acc = __dadd_rn(acc, S.arc[i]); S.arc[i] = acc; }
   }
   __syncwarp();
+  }
   int n_ego = 0;
   {
     const bool ramp = v < max_speed;                 // mpc_intersection.py:114
@@ -155,7 +183,7 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
             else for (int q = 0; q <= k; ++q) cs = __dadd_rn(cs, max_accel);
             dl = __dmul_rn(dt, fmin(__dadd_rn(cs, v), max_speed));
           }
-          return floor(S.arc[k] / dl);
+          return floor(arc[k] / dl);
         };
         keep = (i == 0) || (i == M - 1) || (bucket(i) - bucket(i - 1) >= 1.0);
       }

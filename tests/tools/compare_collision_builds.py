@@ -13,8 +13,10 @@ if len(sys.argv) > 1:
         res[f"flag{cfg}"] = flag; res[f"clen{cfg}"] = clen
     np.savez(sys.argv[1], **res)
 else:
-    for lib, out in (("/root/repo/build/variants/libjmpc_head.so", "/tmp/coll_old.npz"), ("", "/tmp/coll_new.npz")):
-        env = dict(os.environ)
+    # default: arc-length table off vs on; with an argument "head": previous build vs this one
+    pairs = (("", "/tmp/coll_old.npz", {"JMPC_NO_ARC_TABLE": "1"}), ("", "/tmp/coll_new.npz", {}))
+    for lib, out, extra in pairs:
+        env = dict(os.environ); env.update(extra)
         if lib: env["JMPC_LIB"] = lib
         subprocess.check_call([sys.executable, __file__, out], env=env)
     a, b = np.load("/tmp/coll_old.npz"), np.load("/tmp/coll_new.npz")
