@@ -376,7 +376,9 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
       const bool have_hint = h->schedule >= 2 && h->hint_B == B && h->hint_T == T;
       jmpc::ParamVec dv;
       memcpy(dv.v, h->defaults, sizeof dv.v);
-      jmpc::schedule_kernel<<<1, 1024, 0, s>>>(B, T, have_hint ? h->d_hint : nullptr, state, params, dv, h->d_order);
+      double acc_weight = 2.0;                         // weight of the acceleration-saturation stages in the a-priori key
+      if (const char* e = getenv("JMPC_KEY_ACC_WEIGHT")) acc_weight = atof(e);
+      jmpc::schedule_kernel<<<1, 1024, 0, s>>>(B, T, have_hint ? h->d_hint : nullptr, state, params, dv, h->d_order, acc_weight);
       CK(cudaGetLastError());
       h->launches++;
       a.order = h->d_order;

@@ -917,7 +917,7 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, doub
 constexpr int kSchedKeys = 64;
 __global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int* __restrict__ hint,
                                                         const double* __restrict__ state, const double* __restrict__ params,
-                                                        ParamVec defaults, int* __restrict__ order) {
+                                                        ParamVec defaults, int* __restrict__ order, double acc_weight) {
   __shared__ int count[kSchedKeys];
   __shared__ int start[kSchedKeys];
   for (int k = threadIdx.x; k < kSchedKeys; k += blockDim.x) count[k] = 0;
@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int*
       // stages at full throttle to reach the speed the reference points advance with (mpc.py:98: max(v, 10/3.6)); the
       // acceleration box binds on those and, to close the gap opened meanwhile, on about as many again
       const double acc_stages = fmin(fmax((pv[JMPC_P_V_REF_MIN] - v0) / dv_stage, 0.0), (double)T);
-      key = (int)(2.0 * (cap_stages + 2.0 * acc_stages));
+      key = (int)(2.0 * (cap_stages + acc_weight * acc_stages));
     }
     return min(max(key, 0), kSchedKeys - 1);
   };
