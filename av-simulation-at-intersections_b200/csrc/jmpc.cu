@@ -44,6 +44,7 @@ struct jmpc_handle_s {
   double *d_cx = nullptr, *d_cy = nullptr, *d_cyaw = nullptr;
   double *d_ccfx = nullptr, *d_ccfy = nullptr, *d_ccrx = nullptr, *d_ccry = nullptr;   // collision-circle tables
   double* d_arc = nullptr; long long* d_arc_off = nullptr;                                // arc-length tables (collision kernel)
+  bool arc_all = false;                                                                   // every uploaded course has a table
   double off_front = 2.86 / 2 + (3.5 / 2 - 1.0), off_rear = 2.86 / 2 - (3.5 / 2 - 1.0), radius = 2.0 / 1.4142135623730951;
   int* d_course_n = nullptr;
   int n_courses = 0, course_stride = 0;
@@ -182,10 +183,11 @@ int refresh_arc_tables(jmpc_handle h) {
   if (!h->d_arc_off) CK(cudaMalloc(&h->d_arc_off, (size_t)h->max_courses * sizeof(long long)));
   std::vector<long long> off(h->n_courses, -1);
   long long total = 0;
+  h->arc_all = true;
   const long long cap = (256ll << 20) / (long long)sizeof(double);
   for (int c = 0; c < h->n_courses; ++c) {
     const long long n = h->course_n[c], need = n * (n + 1) / 2;
-    if (total + need > cap) continue;
+    if (total + need > cap) { h->arc_all = false; continue; }
     off[c] = total; total += need;
   }
   if (total > 0) CK(cudaMalloc(&h->d_arc, (size_t)total * sizeof(double)));
@@ -660,7 +662,10 @@ int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const
   a.flag = flag; a.course_len_out = course_len_out; a.skip = h->skip;
   const int wpb = 4;
   const int blocks = (B + wpb - 1) / wpb;
-  const size_t smem = wpb * jmpc::collision_warp_smem_bytes(h->max_N, n_obs);
+  // with a table for every course the kernel needs no shared memory for the arc scan: 5 KB per warp instead of 12.6 KB
+  // at max_N = 960 and two obstacles, i.e. more than twice the resident warps of this latency-bound kernel
+  a.arc_smem = (a.arc_tab && h->arc_all) ? 0 : h->max_N;
+  const size_t smem = wpb * jmpc::collision_warp_smem_bytes(a.arc_smem, n_obs);
   if (!h->collision_attr_set) {             // per handle: function attributes are per device
     CK(cudaFuncSetAttribute(jmpc::collision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     h->collision_attr_set = true;

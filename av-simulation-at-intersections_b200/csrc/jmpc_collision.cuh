@@ -37,7 +37,9 @@ struct CollisionArgs {
   double off_front, off_rear, radius;
   const double* params; ParamBlock defaults;
   int* flag; int* course_len_out;
-  int arc_cap;                                       // course points the arc-length scan can hold (handle max_N)
+  int arc_cap;                                       // longest course (handle max_N)
+  int arc_smem;                                      // doubles of shared memory per warp for the on-the-fly arc scan: arc_cap,
+                                                     // or 0 when every course has a table (twice the resident warps then)
   // Optional per-course table of the running arc lengths from every start index (arc_table_kernel): row a0 of course c
   // starts at arc_tab + arc_off[c] + a0 * N - a0 (a0 - 1) / 2 and has N - a0 entries; arc_off[c] < 0 = no table
   const double* arc_tab; const long long* arc_off;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
   const int b = blockIdx.x * (blockDim.x >> 5) + wib;
   if (b >= A.B) return;
   if (A.skip && A.skip[b] != 0) return;
-  CollisionSmem S(smem_raw + (size_t)wib * collision_warp_smem_bytes(A.arc_cap, A.n_obs), A.arc_cap, A.n_obs);
+  CollisionSmem S(smem_raw + (size_t)wib * collision_warp_smem_bytes(A.arc_smem, A.n_obs), A.arc_smem, A.n_obs);
   const unsigned full = 0xffffffffu;
 
   const double* prm = A.params ? A.params + (size_t)b * JMPC_NPARAM : A.defaults.v;
