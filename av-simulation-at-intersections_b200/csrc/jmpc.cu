@@ -42,6 +42,7 @@ struct jmpc_handle_s {
   double defaults[JMPC_NPARAM];
   // courses
   double *d_cx = nullptr, *d_cy = nullptr, *d_cyaw = nullptr;
+  double* d_cv = nullptr; bool have_cv = false;                                          // reference speed profile (jmpc_set_course_speed)
   double *d_ccfx = nullptr, *d_ccfy = nullptr, *d_ccrx = nullptr, *d_ccry = nullptr;   // collision-circle tables
   double* d_arc = nullptr; long long* d_arc_off = nullptr;                                // arc-length tables (collision kernel)
   bool arc_all = false;                                                                   // every uploaded course has a table
@@ -65,52 +66,76 @@ struct jmpc_handle_s {
   bool collision_attr_set = false;
   const int* skip = nullptr;           // jmpc_set_skip_mask
   // longest-first scheduling (jmpc_set_schedule)
+  int host_transfer = 1;               // jmpc_set_host_transfer
   int schedule = 0;                     // 0 index order, 1 a-priori key, 2 previous step's iteration counts (+ 1 as fallback)
   int* d_order = nullptr; int* d_hint = nullptr;
   int hint_B = 0, hint_T = 0;           // batch the hints were recorded for (0 = none)
   struct HostBlock { char* base; size_t bytes; char* dev; };
   std::vector<HostBlock> host_blocks;   // page-locked blocks from jmpc_host_alloc (+ h_stage) with their device mapping
+  // launch geometry of the step kernel per horizon, resolved once (function attributes, occupancy)
+  struct Geom { bool ready = false; void (*kernel)(const jmpc::StepArgs) = nullptr; int groups = 1, wpb = 0, per_sm = 0; size_t smem = 0; };
+  Geom geom[JMPC_MAX_T + 1];
 };
 
 namespace {
 
 // launch geometry of the step kernel for horizon T
-struct StepGeom { int blocks, threads; size_t smem; int warps; };
+struct StepGeom { int blocks, threads; size_t smem; int groups_total; };
 
 using StepKernel = void (*)(const jmpc::StepArgs);
 
-// horizons with a compile-time specialisation; anything else runs the generic kernel
-StepKernel step_kernel_for(int T) {
-  if (getenv("JMPC_GENERIC")) return jmpc::mpc_step_kernel<0>;
+// Horizons with a compile-time specialisation; anything else runs a generic kernel.  Horizons up to 15 (T + 1 <= 16
+// horizon points) run two instances per warp, one per half (jmpc_step.cuh).
+StepKernel step_kernel_for(int T, int* groups) {
+  *groups = 32 / jmpc::group_lanes_for(T);
+#ifdef JMPC_EXPERIMENT
+  if (getenv("JMPC_GENERIC")) return *groups == 2 ? jmpc::mpc_step_kernel<0, 16> : jmpc::mpc_step_kernel<0, 32>;
+#endif
   switch (T) {
-    case 8: return jmpc::mpc_step_kernel<8>;
-    case 13: return jmpc::mpc_step_kernel<13>;
-    case 20: return jmpc::mpc_step_kernel<20>;
-    case 25: return jmpc::mpc_step_kernel<25>;
-    default: return jmpc::mpc_step_kernel<0>;
+    case 8: return jmpc::mpc_step_kernel<8, 16>;
+    case 13: return jmpc::mpc_step_kernel<13, 16>;
+    case 20: return jmpc::mpc_step_kernel<20, 32>;
+    case 25: return jmpc::mpc_step_kernel<25, 32>;
+    default: return *groups == 2 ? jmpc::mpc_step_kernel<0, 16> : jmpc::mpc_step_kernel<0, 32>;
   }
 }
 
-int step_geometry(jmpc_handle h, int B, int T, StepGeom* g) {
-  int wpb = JMPC_WPB;
-  if (const char* e = getenv("JMPC_WPB")) wpb = std::max(1, std::min(JMPC_WPB, atoi(e)));
-  const size_t smem = jmpc::step_block_smem_bytes(T, wpb);
-  StepKernel k = step_kernel_for(T);
-  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  int carve = cudaSharedmemCarveoutMaxShared;
-  if (const char* e = getenv("JMPC_CARVEOUT")) carve = atoi(e);          // percent of the unified L1 / shared memory given to shared
-  CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, wpb * 32, smem));
-  if (per_sm < 1) return fail("step kernel does not fit on an SM for this horizon");
-  int cap = h->opt.warps_per_sm;
-  if (const char* e = getenv("JMPC_WARPS_PER_SM")) cap = atoi(e);
-  if (cap > 0) per_sm = std::max(1, std::min(per_sm, cap / wpb));
-  int blocks = h->sm_count * per_sm;
-  const int need = (B + wpb - 1) / wpb;
+// Function attributes and occupancy are resolved once per (handle, T): the single-ego call runs this path every
+// time step.  (Experiment builds, -DJMPC_EXPERIMENT, re-read their environment knobs on every call instead.)
+int step_geometry(jmpc_handle h, int B, int T, StepGeom* g, StepKernel* kernel) {
+  jmpc_handle_s::Geom& c = h->geom[T];
+#ifdef JMPC_EXPERIMENT
+  c.ready = false;
+#endif
+  if (!c.ready) {
+    int wpb = JMPC_WPB;
+    int carve = cudaSharedmemCarveoutMaxShared;
+    int cap = h->opt.warps_per_sm;
+#ifdef JMPC_EXPERIMENT
+    if (const char* e = getenv("JMPC_WPB")) wpb = std::max(1, std::min(JMPC_WPB, atoi(e)));
+    if (const char* e = getenv("JMPC_CARVEOUT")) carve = atoi(e);          // percent of the unified L1 / shared memory given to shared
+    if (const char* e = getenv("JMPC_WARPS_PER_SM")) cap = atoi(e);
+#endif
+    int groups = 1;
+    StepKernel k = step_kernel_for(T, &groups);
+    const size_t smem = jmpc::step_block_smem_bytes(T, wpb, groups);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, wpb * 32, smem));
+    if (per_sm < 1) return fail("step kernel does not fit on an SM for this horizon");
+    if (cap > 0) per_sm = std::max(1, std::min(per_sm, cap / wpb));
+    c.kernel = k; c.groups = groups; c.wpb = wpb; c.per_sm = per_sm; c.smem = smem; c.ready = true;
+    if (getenv("JMPC_DEBUG"))
+      fprintf(stderr, "[jmpc] step geometry: T=%d %d instance(s) per warp, %d blocks per SM x %d warps, smem/block=%zu\n", T,
+              groups, per_sm, wpb, smem);
+  }
+  int blocks = h->sm_count * c.per_sm;
+  const int per_block = c.wpb * c.groups;
+  const int need = (B + per_block - 1) / per_block;
   if (blocks > need) blocks = need;
-  g->blocks = blocks; g->threads = wpb * 32; g->smem = smem; g->warps = blocks * wpb;
-  if (getenv("JMPC_DEBUG")) fprintf(stderr, "[jmpc] step geometry: T=%d B=%d blocks=%d (%d per SM) smem/block=%zu\n", T, B, blocks, per_sm, smem);
+  g->blocks = blocks; g->threads = c.wpb * 32; g->smem = c.smem; g->groups_total = blocks * per_block;
+  *kernel = c.kernel;
   return 0;
 }
 
@@ -255,6 +280,7 @@ int32_t jmpc_create(int32_t device, int32_t max_B, int32_t max_T, int32_t max_N,
   *out = nullptr;
   if (max_T < 2 || max_T > JMPC_MAX_T) return fail("jmpc_create: max_T must be in [2, JMPC_MAX_T]");
   if (max_B < 1 || max_N < 1 || max_courses < 1) return fail("jmpc_create: sizes must be positive");
+  if (max_N > 32767) return fail("jmpc_create: max_N must be <= 32767 (16-bit path indices in the collision kernel)");
   if (!default_params) return fail("jmpc_create: default_params is NULL");
   int count = 0;
   CK(cudaGetDeviceCount(&count));
@@ -264,7 +290,9 @@ int32_t jmpc_create(int32_t device, int32_t max_B, int32_t max_T, int32_t max_N,
   if (!h) return fail("jmpc_create: out of host memory");
   h->device = device; h->max_B = max_B; h->max_T = max_T; h->max_N = max_N; h->max_courses = max_courses;
   h->opt.max_solver_iters = 40; h->opt.linearisation_iters = 1; h->opt.mu_tol = 1e-13; h->opt.warps_per_sm = 0;
+  h->opt.du_th = 0.0;
   if (options) {
+    if (options->du_th > 0) h->opt.du_th = options->du_th;
     if (options->max_solver_iters > 0) h->opt.max_solver_iters = options->max_solver_iters;
     if (options->linearisation_iters > 0) h->opt.linearisation_iters = options->linearisation_iters;
     if (options->mu_tol > 0) h->opt.mu_tol = options->mu_tol;
@@ -278,7 +306,8 @@ int32_t jmpc_create(int32_t device, int32_t max_B, int32_t max_T, int32_t max_N,
   h->course_stride = max_N;
   const size_t cbytes = (size_t)max_courses * max_N * sizeof(double);
   if ((e = cudaMalloc(&h->d_cx, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_cy, cbytes)) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_cyaw, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_ccfx, cbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_cyaw, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_cv, cbytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_ccfx, cbytes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_ccfy, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_ccrx, cbytes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_ccry, cbytes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_course_n, max_courses * sizeof(int))) != cudaSuccess ||
@@ -294,7 +323,7 @@ int32_t jmpc_create(int32_t device, int32_t max_B, int32_t max_T, int32_t max_N,
 int32_t jmpc_destroy(jmpc_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->d_cx); cudaFree(h->d_cy); cudaFree(h->d_cyaw); cudaFree(h->d_course_n);
+  cudaFree(h->d_cx); cudaFree(h->d_cy); cudaFree(h->d_cyaw); cudaFree(h->d_cv); cudaFree(h->d_course_n);
   cudaFree(h->d_ccfx); cudaFree(h->d_ccfy); cudaFree(h->d_ccrx); cudaFree(h->d_ccry); cudaFree(h->d_arc); cudaFree(h->d_arc_off);
   cudaFree(h->d_pscratch); cudaFree(h->d_counter); cudaFree(h->d_stage); cudaFree(h->d_order); cudaFree(h->d_hint);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -313,19 +342,49 @@ int32_t jmpc_set_courses(jmpc_handle h, int32_t n_courses, int32_t stride, const
                          const double* cy, const double* cyaw) {
   if (!h || !len || !cx || !cy || !cyaw) return fail("jmpc_set_courses: NULL argument");
   if (n_courses < 1 || n_courses > h->max_courses) return fail("jmpc_set_courses: n_courses out of range");
-  CK(cudaSetDevice(h->device));
-  h->course_n.assign(len, len + n_courses);
-  for (int c = 0; c < n_courses; ++c) {
+  for (int c = 0; c < n_courses; ++c)             // validate everything before the handle's state is touched
     if (len[c] < 1 || len[c] > h->max_N || len[c] > stride) return fail("jmpc_set_courses: course length out of range");
+  CK(cudaSetDevice(h->device));
+  // Uploads go through the handle's pinned block on its own stream, the stream the table kernels below run on: a
+  // pageable cudaMemcpy on the legacy stream has no ordering against a non-blocking stream.
+  const size_t row = (size_t)h->max_N * sizeof(double);
+  if (ensure_stage(h, 3 * row + (size_t)n_courses * sizeof(int))) return -1;
+  cudaStream_t st = h->own_stream;
+  for (int c = 0; c < n_courses; ++c) {
     const size_t off = (size_t)c * h->course_stride, src = (size_t)c * stride, nb = (size_t)len[c] * sizeof(double);
-    CK(cudaMemcpy(h->d_cx + off, cx + src, nb, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_cy + off, cy + src, nb, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_cyaw + off, cyaw + src, nb, cudaMemcpyHostToDevice));
+    memcpy(h->h_stage, cx + src, nb); memcpy(h->h_stage + row, cy + src, nb); memcpy(h->h_stage + 2 * row, cyaw + src, nb);
+    CK(cudaMemcpyAsync(h->d_cx + off, h->h_stage, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_cy + off, h->h_stage + row, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_cyaw + off, h->h_stage + 2 * row, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                  // the staging rows are reused by the next course
   }
-  CK(cudaMemcpy(h->d_course_n, len, n_courses * sizeof(int), cudaMemcpyHostToDevice));
+  memcpy(h->h_stage, len, (size_t)n_courses * sizeof(int));
+  CK(cudaMemcpyAsync(h->d_course_n, h->h_stage, (size_t)n_courses * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  h->course_n.assign(len, len + n_courses);
   h->n_courses = n_courses;
+  h->have_cv = false;                               // a speed profile belongs to the courses it was uploaded for
   if (refresh_arc_tables(h)) return -1;
   return refresh_circle_tables(h);
+}
+
+int32_t jmpc_set_course_speed(jmpc_handle h, int32_t n_courses, int32_t stride, const double* cv) {
+  if (!h) return fail("jmpc_set_course_speed: NULL handle");
+  if (!cv) { h->have_cv = false; return 0; }
+  if (n_courses != h->n_courses) return fail("jmpc_set_course_speed: n_courses differs from the uploaded courses");
+  for (int c = 0; c < n_courses; ++c)
+    if (h->course_n[c] > stride) return fail("jmpc_set_course_speed: stride shorter than a course");
+  CK(cudaSetDevice(h->device));
+  if (ensure_stage(h, (size_t)h->max_N * sizeof(double))) return -1;
+  cudaStream_t st = h->own_stream;
+  for (int c = 0; c < n_courses; ++c) {
+    const size_t nb = (size_t)h->course_n[c] * sizeof(double);
+    memcpy(h->h_stage, cv + (size_t)c * stride, nb);
+    CK(cudaMemcpyAsync(h->d_cv + (size_t)c * h->course_stride, h->h_stage, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  h->have_cv = true;
+  return 0;
 }
 
 int32_t jmpc_set_car_geometry(jmpc_handle h, double front_offset, double rear_offset, double radius) {
@@ -343,16 +402,19 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
                 double* oa_out, double* od_out, const double* params, double* ox, double* oy, double* ov,
                 double* oyaw, double* xref, double* cost, int* status, int* iters, double* record, cudaStream_t s) {
   StepGeom g;
-  if (step_geometry(h, B, T, &g)) return -1;
+  StepKernel kernel = nullptr;
+  if (step_geometry(h, B, T, &g, &kernel)) return -1;
   const int n = 2 * T;
-  if (ensure_scratch(h, (size_t)g.warps * jmpc::tiles_doubles(n))) return -1;
+  if (ensure_scratch(h, (size_t)g.groups_total * jmpc::tiles_doubles(n))) return -1;
   jmpc::StepArgs a;
   a.B = B; a.T = T; a.lin_iters = h->opt.linearisation_iters; a.max_iters = h->opt.max_solver_iters;
-  a.mu_tol = h->opt.mu_tol;
+  a.mu_tol = h->opt.mu_tol; a.du_th = h->opt.du_th;
   a.tol_res = 1e-9; a.init_mu = 0.0;
+#ifdef JMPC_EXPERIMENT
   if (const char* e = getenv("JMPC_TOL_RES")) a.tol_res = atof(e);          // solver experiments (tests/tools/tune_solver.py)
   if (const char* e = getenv("JMPC_INIT_MU")) a.init_mu = atof(e);
-  a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
+#endif
+  a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.cv = h->have_cv ? h->d_cv : nullptr; a.course_n = h->d_course_n;
   a.course_stride = h->course_stride; a.n_courses = h->n_courses;
   a.state = state; a.course_id = course_id; a.course_len = course_len; a.warm = warm; a.params = params;
   memcpy(a.defaults, h->defaults, sizeof a.defaults);
@@ -370,16 +432,18 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
       CK(cudaMalloc(&h->d_hint, (size_t)h->max_B * sizeof(int)));
       CK(cudaMemsetAsync(h->d_hint, 0, (size_t)h->max_B * sizeof(int), s));
     }
-    // ordering only matters while the batch is a few waves of the resident warps deep (measured: no gain at 28 waves,
-    // where the one-block ordering kernel starts to cost as much as it saves)
+    // ordering only matters while the batch is a few waves of the resident instance slots deep (measured: no gain
+    // at 28 waves, where the one-block ordering kernel starts to cost as much as it saves)
     long long sched_max_waves = 16;
+    double acc_weight = 2.0;                         // weight of the acceleration-saturation stages in the a-priori key
+#ifdef JMPC_EXPERIMENT
     if (const char* e = getenv("JMPC_SCHED_MAX_WAVES")) sched_max_waves = atoll(e);
-    if (B > g.warps && (long long)B <= sched_max_waves * (long long)g.warps) {
+    if (const char* e = getenv("JMPC_KEY_ACC_WEIGHT")) acc_weight = atof(e);
+#endif
+    if (B > g.groups_total && (long long)B <= sched_max_waves * (long long)g.groups_total) {
       const bool have_hint = h->schedule >= 2 && h->hint_B == B && h->hint_T == T;
       jmpc::ParamVec dv;
       memcpy(dv.v, h->defaults, sizeof dv.v);
-      double acc_weight = 2.0;                         // weight of the acceleration-saturation stages in the a-priori key
-      if (const char* e = getenv("JMPC_KEY_ACC_WEIGHT")) acc_weight = atof(e);
       jmpc::schedule_kernel<<<1, 1024, 0, s>>>(B, T, have_hint ? h->d_hint : nullptr, state, params, dv, h->d_order, acc_weight);
       CK(cudaGetLastError());
       h->launches++;
@@ -388,7 +452,7 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
     if (h->schedule >= 2) { a.work_hint = h->d_hint; h->hint_B = B; h->hint_T = T; }
   }
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), s));
-  step_kernel_for(T)<<<g.blocks, g.threads, g.smem, s>>>(a);
+  kernel<<<g.blocks, g.threads, g.smem, s>>>(a);
   CK(cudaGetLastError());
   h->launches++;
   return 0;
@@ -473,6 +537,13 @@ int32_t jmpc_reset_schedule_hints(jmpc_handle h) {
   return 0;
 }
 
+int32_t jmpc_set_host_transfer(jmpc_handle h, int32_t mode) {
+  if (!h) return fail("jmpc_set_host_transfer: NULL handle");
+  if (mode < 0 || mode > 2) return fail("jmpc_set_host_transfer: mode must be 0, 1 or 2");
+  h->host_transfer = mode;
+  return 0;
+}
+
 int32_t jmpc_set_skip_mask(jmpc_handle h, const int32_t* skip) {
   if (!h) return fail("jmpc_set_skip_mask: NULL handle");
   h->skip = skip;
@@ -509,11 +580,12 @@ int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* sta
       !xref || !cost || !status)
     return fail("jmpc_step_host: NULL array");
   if (h->n_courses < 1) return fail("jmpc_step_host: no courses uploaded (jmpc_set_courses)");
+  if (h->skip) return fail("jmpc_step_host: a skip mask is set (jmpc_set_skip_mask is for the device entry points)");
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   const size_t T1 = T + 1, b = (size_t)B;
   // Staging block layout [inputs | outputs], the same offsets on the device (d_stage) and in the handle's
-  // page-locked host block (h_stage).  Transfer modes (JMPC_ZEROCOPY, default 2):
+  // page-locked host block (h_stage).  Transfer modes (jmpc_set_host_transfer):
   //   1  (default) inputs by cudaMemcpyAsync into d_stage; the kernel stores its results directly into page-locked
   //      host memory through the device mapping (unified addressing): the caller's own array where that is
   //      page-locked (jmpc_host_alloc, cudaHostAlloc, torch pin_memory), the h_stage slot otherwise (one host
@@ -529,11 +601,14 @@ int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* sta
   size_t off = 0;
   Seg segs[20];
   int ns = 0;
+#ifdef JMPC_EXPERIMENT
   const bool timing = getenv("JMPC_TIMING") != nullptr;                 // host-side breakdown on stderr
+#else
+  const bool timing = false;
+#endif
   auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = timing ? now() : 0.0;
-  const char* mode_env = getenv("JMPC_ZEROCOPY");       // read per call: tests switch it
-  const int mode = mode_env ? atoi(mode_env) : 1;
+  const int mode = h->host_transfer;
   auto seg = [&](size_t bytes, const void* host) -> Seg& {
     Seg& s = segs[ns++];
     s.off = off; s.bytes = host ? bytes : 0; s.host = const_cast<void*>(host);
@@ -653,7 +728,10 @@ int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const
   jmpc::CollisionArgs a;
   a.B = B; a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
   a.ccfx = h->d_ccfx; a.ccfy = h->d_ccfy; a.ccrx = h->d_ccrx; a.ccry = h->d_ccry;
-  a.arc_tab = getenv("JMPC_NO_ARC_TABLE") ? nullptr : h->d_arc; a.arc_off = h->d_arc_off;
+  a.arc_tab = h->d_arc; a.arc_off = h->d_arc_off;
+#ifdef JMPC_EXPERIMENT
+  if (getenv("JMPC_NO_ARC_TABLE")) a.arc_tab = nullptr;
+#endif
   a.off_front = h->off_front; a.off_rear = h->off_rear; a.radius = h->radius; a.arc_cap = h->max_N;
   a.course_stride = h->course_stride; a.course_id = course_id; a.agent_idx = agent_idx; a.v = v;
   a.obstacles = obstacles; a.n_obs = n_obs; a.frame_window = frame_window; a.margin = margin;
@@ -684,33 +762,66 @@ int32_t jmpc_collision_host(jmpc_handle h, int32_t B, const int32_t* course_id, 
   if (!h) return fail("jmpc_collision_host: NULL handle");
   if (B < 0 || B > h->max_B) return fail("jmpc_collision_host: B out of range");
   if (!agent_idx || !v || !flag || !course_len_out) return fail("jmpc_collision_host: NULL array");
+  if (n_obs < 0 || n_obs > jmpc::kMaxObstacles) return fail("jmpc_collision_host: n_obs out of range");
+  if (n_obs > 0 && !obstacles) return fail("jmpc_collision_host: obstacles is NULL");
+  if (h->skip) return fail("jmpc_collision_host: a skip mask is set (jmpc_set_skip_mask is for the device entry points)");
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   const size_t b = (size_t)B;
+  // Inputs: page-locked caller arrays (jmpc_host_alloc) are copied to the device straight from where they are, others
+  // through the handle's pinned block.  Results: the kernel stores flag / course_len_out into page-locked host memory
+  // through its device mapping (the caller's arrays when they are page-locked, the pinned block + one memcpy otherwise),
+  // as the step's host entry point does: no device->host copy pass.
+  struct Seg { size_t off, bytes; const void* host; bool pinned; void* mapped; };
+  Seg segs[7];
+  int ns = 0;
   size_t off = 0;
-  auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
-  const size_t o_v = seg(b * 8), o_obs = seg(b * n_obs * 6 * 8), o_prm = seg(params ? b * JMPC_NPARAM * 8 : 0);
-  const size_t o_cid = seg(course_id ? b * 4 : 0), o_idx = seg(b * 4);
-  const size_t in_end = off;
-  const size_t o_flag = seg(b * 4), o_len = seg(b * 4);
+  auto seg = [&](size_t bytes, const void* host) -> Seg& {
+    Seg& s = segs[ns++];
+    s.off = off; s.bytes = host ? bytes : 0; s.host = host; s.mapped = nullptr;
+    s.pinned = (host && s.bytes) ? is_pinned(h, host, &s.mapped) : false;
+    off += (s.bytes + 15) & ~size_t(15);
+    return s;
+  };
+  const Seg& s_v = seg(b * 8, v);
+  const Seg& s_obs = seg(b * n_obs * 6 * 8, n_obs ? obstacles : nullptr);
+  const Seg& s_prm = seg(b * JMPC_NPARAM * 8, params);
+  const Seg& s_cid = seg(b * 4, course_id);
+  const Seg& s_idx = seg(b * 4, agent_idx);
+  const int first_out = ns;
+  Seg& s_flag = seg(b * 4, flag);
+  Seg& s_len = seg(b * 4, course_len_out);
   if (ensure_stage(h, off)) return -1;
   char* hs = h->h_stage; char* ds = h->d_stage;
-  memcpy(hs + o_v, v, b * 8);
-  if (n_obs) memcpy(hs + o_obs, obstacles, b * n_obs * 6 * 8);
-  if (params) memcpy(hs + o_prm, params, b * JMPC_NPARAM * 8);
-  if (course_id) memcpy(hs + o_cid, course_id, b * 4);
-  memcpy(hs + o_idx, agent_idx, b * 4);
   cudaStream_t st = h->own_stream;
-  CK(cudaMemcpyAsync(ds, hs, in_end, cudaMemcpyHostToDevice, st));
-  int rc = jmpc_collision(h, B, course_id ? (const int*)(ds + o_cid) : nullptr, (const int*)(ds + o_idx),
-                          (const double*)(ds + o_v), (const double*)(ds + o_obs), n_obs, frame_window, margin,
-                          horizon_s, params ? (const double*)(ds + o_prm) : nullptr, (int*)(ds + o_flag),
-                          (int*)(ds + o_len), (void*)st);
+  for (int k = 0; k < first_out; ++k) {
+    const Seg& s = segs[k];
+    if (!s.bytes) continue;
+    const void* src = s.host;
+    if (!s.pinned) { memcpy(hs + s.off, s.host, s.bytes); src = hs + s.off; }
+    CK(cudaMemcpyAsync(ds + s.off, src, s.bytes, cudaMemcpyHostToDevice, st));
+  }
+  char* hs_dev = nullptr;
+  bool zc_out = h->host_transfer >= 1;
+  if (zc_out && cudaHostGetDevicePointer((void**)&hs_dev, hs, 0) != cudaSuccess) { cudaGetLastError(); zc_out = false; }
+  for (int k = first_out; k < ns && zc_out; ++k) {
+    Seg& s = segs[k];
+    if (s.pinned) { if (!s.mapped) zc_out = false; }
+    else s.mapped = hs_dev + s.off;
+  }
+  auto rp = [&](const Seg& s) -> const char* { return s.bytes ? ds + s.off : nullptr; };
+  auto wp = [&](const Seg& s) -> char* { return zc_out ? (char*)s.mapped : ds + s.off; };
+  int rc = jmpc_collision(h, B, (const int*)rp(s_cid), (const int*)rp(s_idx), (const double*)rp(s_v),
+                          (const double*)rp(s_obs), n_obs, frame_window, margin, horizon_s, (const double*)rp(s_prm),
+                          (int*)wp(s_flag), (int*)wp(s_len), (void*)st);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(hs + o_flag, ds + o_flag, off - o_flag, cudaMemcpyDeviceToHost, st));
+  if (!zc_out)
+    for (int k = first_out; k < ns; ++k)
+      CK(cudaMemcpyAsync(segs[k].pinned ? const_cast<void*>(segs[k].host) : (void*)(hs + segs[k].off), ds + segs[k].off,
+                         segs[k].bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  memcpy(flag, hs + o_flag, b * 4);
-  memcpy(course_len_out, hs + o_len, b * 4);
+  for (int k = first_out; k < ns; ++k)
+    if (!segs[k].pinned) memcpy(const_cast<void*>(segs[k].host), hs + segs[k].off, segs[k].bytes);
   return 0;
 }
 
@@ -825,29 +936,43 @@ int64_t jmpc_launch_count(jmpc_handle h) { return h ? h->launches : 0; }
 
 int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const double* b, const double* x, double* sol,
                           double* prod) {
+  return jmpc_debug_linalg_g(h, n, 32, 0, A, b, x, sol, prod);
+}
+
+int32_t jmpc_debug_linalg_g(jmpc_handle h, int32_t n, int32_t group_lanes, int32_t which, const double* A,
+                            const double* b, const double* x, double* sol, double* prod) {
   if (!h || !A || !b || !x || !sol || !prod) return fail("jmpc_debug_linalg: NULL argument");
   if (n < 1 || n > 2 * JMPC_MAX_T) return fail("jmpc_debug_linalg: n out of range");
+  if (group_lanes != 16 && group_lanes != 32) return fail("jmpc_debug_linalg: group_lanes must be 16 or 32");
+  const int groups = 32 / group_lanes;
+  if (which < 0 || which >= groups) return fail("jmpc_debug_linalg: no such lane group");
   CK(cudaSetDevice(h->device));
   const size_t nn = (size_t)n * n;
-  if (ensure_stage(h, (nn + 6 * (size_t)n + 2) * sizeof(double))) return -1;
+  const size_t in_doubles = nn + 2 * (size_t)n, out_doubles = 4 * (size_t)n + 2;
+  if (ensure_stage(h, (in_doubles + out_doubles) * sizeof(double))) return -1;
+  // everything on the handle's own stream, through its pinned block
+  double* hs = (double*)h->h_stage;
   double* d = (double*)h->d_stage;
+  memcpy(hs, A, nn * sizeof(double)); memcpy(hs + nn, b, n * sizeof(double)); memcpy(hs + nn + n, x, n * sizeof(double));
   double *dA = d, *db = dA + nn, *dx = db + n, *dsol = dx + n, *dprod = dsol + 2 * n;
   int* dok = (int*)(dprod + 2 * n);
-  CK(cudaMemset(dsol, 0xff, 4 * (size_t)n * sizeof(double)));          // NaN where the kernel writes nothing
-  CK(cudaMemcpy(dA, A, nn * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+  cudaStream_t st = h->own_stream;
+  CK(cudaMemcpyAsync(d, hs, in_doubles * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(dsol, 0xff, out_doubles * sizeof(double), st));          // NaN where the kernel writes nothing
   const int nb = jmpc::nblk(n);
-  const size_t smem = (jmpc::tiles_doubles(n) + 8 * nb) * sizeof(double) + (size_t)jmpc::chol_lut_entries(nb + 1) * 2 + 16;
-  jmpc::linalg_selftest_kernel<<<1, 32, smem, h->own_stream>>>(n, dA, db, dx, dsol, dprod, dok);
+  const size_t smem = (size_t)groups * (jmpc::tiles_doubles(n) + 8 * nb) * sizeof(double) +
+                      (size_t)jmpc::chol_lut_entries(nb + 1) * 2 + 16;
+  if (group_lanes == 32) jmpc::linalg_selftest_kernel<32><<<1, 32, smem, st>>>(n, which, dA, db, dx, dsol, dprod, dok);
+  else jmpc::linalg_selftest_kernel<16><<<1, 32, smem, st>>>(n, which, dA, db, dx, dsol, dprod, dok);
   CK(cudaGetLastError());
   h->launches++;
-  CK(cudaStreamSynchronize(h->own_stream));
+  CK(cudaMemcpyAsync(hs + in_doubles, dsol, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(sol, hs + in_doubles, 2 * (size_t)n * sizeof(double));
+  memcpy(prod, hs + in_doubles + 2 * n, 2 * (size_t)n * sizeof(double));
   int ok = 0;
-  CK(cudaMemcpy(sol, dsol, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(prod, dprod, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost));
-  return ok ? 0 : 1;
+  memcpy(&ok, hs + in_doubles + 4 * n, sizeof(int));
+  return ok == 1 ? 0 : 1;
 }
 
 int32_t jmpc_measure_fma_peak(jmpc_handle h, double* fp64_tflops, double* fp32_tflops) {

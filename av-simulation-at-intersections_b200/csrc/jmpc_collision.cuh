@@ -196,7 +196,13 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
       }
       n_ego += __popc(m);
     }
-    n_ego = min(n_ego, kMaxEgoFrames);
+  }
+  // Limits of the per-warp shared-memory tables: an instance whose ego prediction keeps more than kMaxEgoFrames points
+  // or whose obstacle prediction needs more than kMaxObsFrames - 1 steps cannot be decided here; it is reported
+  // (flag = -1, full course length) instead of being silently truncated.  The reference's scenes need 49 / 35.
+  if (n_ego > kMaxEgoFrames || (int)ceil(A.horizon_s / dt) > kMaxObsFrames - 1) {
+    if (lane == 0) { A.flag[b] = -1; A.course_len_out[b] = N; }
+    return;
   }
 
   // ---- B. obstacle predictions (moving_obstacles_prediction.py:21-47) ------------------------------

@@ -16,11 +16,9 @@
 
 #include "../../include/jmpc.h"
 #include "jmpc_collision.cuh"
+#include "jmpc_step.cuh"              // nearest_index
 
 namespace jmpc {
-
-__device__ inline int nearest_index(const double* __restrict__ cx, const double* __restrict__ cy, int n_course,
-                                    int start, double x, double y, int lane);   // jmpc_step.cuh
 
 struct EpisodeArgs {
   int B, T;
@@ -79,7 +77,7 @@ __global__ void __launch_bounds__(128) episode_pre_kernel(const EpisodeArgs A) {
     update = (cx[at] != cx[last]) || (cy[at] != cy[last]) || (cyaw[at] != cyaw[last]);
   }
   if (update) {
-    const int near = nearest_index(cx, cy, N, a0, x, y, lane);
+    const int near = nearest_index<32>(cx, cy, N, a0, x, y, lane, 0xffffffffu);
     if (near < 0) { if (lane == 0) A.done[b] = 2; return; }     // reference raises (trajectories.py:120)
     a0 = near;
   }
@@ -111,7 +109,9 @@ __global__ void episode_post_kernel(const EpisodeArgs A) {
   A.target_ind[b] = target;
   double delta = A.di[b], acc = prm[JMPC_P_MAX_DECEL];
   double dev = nan("");
-  if (status == JMPC_OPTIMAL || status == JMPC_MAX_ITER) {
+  // any status but OPTIMAL is a failed solve: the previous steer is kept and the ego brakes with MAX_DECEL
+  // (mpc.py:298-301); that includes JMPC_MAX_ITER, whose record carries no controls
+  if (status == JMPC_OPTIMAL) {
     delta = rec[0]; acc = rec[1];
     // get_current_xref_deviation (mpc.py:305-312); ox[0], oy[0] are the current position
     const double ang = A.cyaw[coff + target] + M_PI / 2;
@@ -120,7 +120,7 @@ __global__ void episode_post_kernel(const EpisodeArgs A) {
     dev = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
   }
   A.di[b] = delta;
-  if (A.warm) A.warm[b] = (status == JMPC_OPTIMAL || status == JMPC_MAX_ITER) ? 1 : 0;
+  if (A.warm) A.warm[b] = (status == JMPC_OPTIMAL) ? 1 : 0;
   // Simulation.step (simulation.py:35-47)
   const double dt = prm[JMPC_P_DT], L = prm[JMPC_P_L], ms = prm[JMPC_P_MAX_STEER];
   const double dcl = fmax(fmin(delta, ms), -ms);

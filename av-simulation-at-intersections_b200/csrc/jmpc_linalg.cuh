@@ -13,6 +13,11 @@
 //
 // Compared with a column-at-a-time factorisation on a packed triangle this does 64 FMAs per 32 shared-memory
 // instructions in the trailing update instead of 1 per 2, and synchronises the warp 3 times per 4 columns.
+//
+// Lane groups: every routine is a template on G, the number of lanes that cooperate on one matrix (32 = the whole
+// warp, 16 = two independent matrices per warp, one per half).  `gl` is the lane's index inside its group, `gm` the
+// group's lane mask; synchronisation and shuffles are group-scoped, so the halves of a warp never depend on each
+// other's control flow (they run in lock step whenever their control flow agrees, which is the common case).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -116,7 +121,8 @@ __device__ inline void chol_lut_build(unsigned short* lut, int nb, int tid, int 
 // is the inverted diagonal block times block J of rhs (every lane, registers), and the lane that has just computed a
 // row of the panel subtracts that row times y from its rhs entry -- no extra loads of L and no extra
 // synchronisation; rhs holds y afterwards (solve_backward_tiles completes the solve).
-__device__ inline bool chol_tiles(double* K, int nb, int lane, const unsigned short* lut,
+template <int G>
+__device__ inline bool chol_tiles(double* K, int nb, int gl, unsigned gm, const unsigned short* lut,
                                   double* rhs = nullptr) {
   bool all_clean = true;
   JMPC_PRAGMA_J
@@ -161,11 +167,11 @@ __device__ inline bool chol_tiles(double* K, int nb, int lane, const unsigned sh
       y0 = m00 * b0; y1 = fma(m11, b1, m10 * b0); y2 = fma(m22, b2, fma(m21, b1, m20 * b0));
       y3 = fma(m31, b1, m30 * b0) + fma(m33, b3, m32 * b2);
     }
-    __syncwarp();                                    // every lane has read the block before it is overwritten
+    __syncwarp(gm);                                  // every lane has read the block before it is overwritten
     JMPC_TOCK(tc_, 13);
     // ---- panel below the block: X = A L^{-T}, one matrix row per lane
     const int prow = (nb - J - 1) << 2;
-    for (int r = lane; r < prow; r += 32) {
+    for (int r = gl; r < prow; r += G) {
       double* row = K + tile_off(J + 1 + (r >> 2), J) + ((r & 3) << 2);
       double a0, a1, a2, a3;
       ld4(row, a0, a1, a2, a3);
@@ -177,7 +183,7 @@ __device__ inline bool chol_tiles(double* K, int nb, int lane, const unsigned sh
         *bi -= fma(x1, y1, x0 * y0) + fma(x3, y3, x2 * y2);
       }
     }
-    if (lane == 0) {
+    if (gl == 0) {
       // the diagonal tile receives the inverse of the factor's diagonal block: nothing reads the block itself again
       // (the panel, the trailing update and the triangular sweeps all work with the inverse)
       double* Mw = K + tile_off(J, J);
@@ -185,13 +191,13 @@ __device__ inline bool chol_tiles(double* K, int nb, int lane, const unsigned sh
       st4(Mw + 8, m20, m21, m22, 0.0); st4(Mw + 12, m30, m31, m32, m33);
       if (rhs) st4(rhs + (J << 2), y0, y1, y2, y3);
     }
-    __syncwarp();
+    __syncwarp(gm);
     JMPC_TOCK(tc_, 14);
     // ---- trailing update: C(I, Kc) -= L(I, J) L(Kc, J)'; a task is half a tile (two rows), so the 45 / 36 / 28 ...
     // tiles of the first block columns fill the 32 lanes better than whole tiles would
     const int m = nb - J - 1, ntasks = m * (m + 1);
     const unsigned short* tasks = lut + chol_lut_offset(m);
-    for (int q = lane; q < ntasks; q += 32) {
+    for (int q = gl; q < ntasks; q += G) {
       const unsigned e = tasks[q];
       const int I = J + 1 + (int)(e & 15u), Kc = J + 1 + (int)((e >> 4) & 15u), h = (int)((e >> 8) & 1u) << 1;
       const double* LI = K + tile_off(I, J) + 4 * h;
@@ -212,7 +218,7 @@ __device__ inline bool chol_tiles(double* K, int nb, int lane, const unsigned sh
         st4(C + 4 * r, c0, c1, c2, c3);
       }
     }
-    __syncwarp();
+    __syncwarp(gm);
     JMPC_TOCK(tc_, 15);
   }
   return all_clean;
@@ -220,7 +226,8 @@ __device__ inline bool chol_tiles(double* K, int nb, int lane, const unsigned sh
 
 // Solve L L' x = b in place; b has 4*nb entries in shared memory (16-byte aligned).  The two sweeps are separate
 // functions: the forward one can also ride along with the factorisation (chol_tiles).
-__device__ inline void solve_forward_tiles(const double* K, double* b, int nb, int lane) {
+template <int G>
+__device__ inline void solve_forward_tiles(const double* K, double* b, int nb, int gl, unsigned gm) {
   const int n4 = nb << 2;
   JMPC_PRAGMA_J
   for (int J = 0; J < nb; ++J) {                      // forward: L y = b
@@ -235,17 +242,18 @@ __device__ inline void solve_forward_tiles(const double* K, double* b, int nb, i
     (void)mpad;
     const double y0 = m00 * b0, y1 = fma(m11, b1, m10 * b0), y2 = fma(m22, b2, fma(m21, b1, m20 * b0));
     const double y3 = fma(m33, b3, fma(m32, b2, fma(m31, b1, m30 * b0)));
-    __syncwarp();
-    for (int i = ((J + 1) << 2) + lane; i < n4; i += 32) {
+    __syncwarp(gm);
+    for (int i = ((J + 1) << 2) + gl; i < n4; i += G) {
       double l0, l1, l2, l3;
       ld4(K + tile_off(i >> 2, J) + ((i & 3) << 2), l0, l1, l2, l3);
       b[i] = fma(-l3, y3, fma(-l2, y2, fma(-l1, y1, fma(-l0, y0, b[i]))));
     }
-    if (lane == 0) st4(b + (J << 2), y0, y1, y2, y3);
-    __syncwarp();
+    if (gl == 0) st4(b + (J << 2), y0, y1, y2, y3);
+    __syncwarp(gm);
   }
 }
-__device__ inline void solve_backward_tiles(const double* K, double* b, int nb, int lane) {
+template <int G>
+__device__ inline void solve_backward_tiles(const double* K, double* b, int nb, int gl, unsigned gm) {
   JMPC_PRAGMA_J
   for (int J = nb - 1; J >= 0; --J) {                 // backward: L' x = y
     const double* Mw = K + tile_off(J, J);
@@ -259,13 +267,13 @@ __device__ inline void solve_backward_tiles(const double* K, double* b, int nb, 
     (void)mpad;
     const double x3 = m33 * y3, x2 = fma(m32, y3, m22 * y2), x1 = fma(m31, y3, fma(m21, y2, m11 * y1));
     const double x0 = fma(m30, y3, fma(m20, y2, fma(m10, y1, m00 * y0)));
-    __syncwarp();
-    for (int i = lane; i < (J << 2); i += 32) {
+    __syncwarp(gm);
+    for (int i = gl; i < (J << 2); i += G) {
       const double* col = K + tile_off(J, i >> 2) + (i & 3);
       b[i] = fma(-col[12], x3, fma(-col[8], x2, fma(-col[4], x1, fma(-col[0], x0, b[i]))));
     }
-    if (lane == 0) st4(b + (J << 2), x0, x1, x2, x3);
-    __syncwarp();
+    if (gl == 0) st4(b + (J << 2), x0, x1, x2, x3);
+    __syncwarp(gm);
   }
 }
 
@@ -306,19 +314,20 @@ __device__ inline void symv_tiles(const double* P, const double* x, int nb, int 
 // solve in the same layout -- block entries fetched by shuffle, no __syncwarp -- was measured too: 20 % shorter for
 // a warp that runs alone, but 2.3x the instructions and 3x the shared-memory wavefronts of solve_tiles, and 12 %
 // slower on a full batch; it was dropped.)
-__device__ inline void solve_tiles(const double* K, double* b, int nb, int lane) {
-  solve_forward_tiles(K, b, nb, lane);
-  solve_backward_tiles(K, b, nb, lane);
+template <int G>
+__device__ inline void solve_tiles(const double* K, double* b, int nb, int gl, unsigned gm) {
+  solve_forward_tiles<G>(K, b, nb, gl, gm);
+  solve_backward_tiles<G>(K, b, nb, gl, gm);
 }
 
 // y = P x for a symmetric P on tiles (diagonal tiles stored full), x in shared memory (4 * nb entries); lane k < T gets
 // rows k (y0) and T + k (y1), four independent accumulators per row.
 template <int NB>
-__device__ __forceinline__ void symv_rows(const double* P, const double* x, int T, int nb_rt, int lane, double& y0,
+__device__ __forceinline__ void symv_rows(const double* P, const double* x, int T, int nb_rt, int gl, double& y0,
                                           double& y1) {
   const int nb = (NB > 0) ? NB : nb_rt;
-  const bool own = lane < T;
-  const int ia = own ? lane : 0, ib = own ? T + lane : 0;
+  const bool own = gl < T;
+  const int ia = own ? gl : 0, ib = own ? T + gl : 0;
   const int Ia = ia >> 2, Ib = ib >> 2;
   const double* rowa = P + tile_off(Ia, 0) + ((ia & 3) << 2);
   const double* rowb = P + tile_off(Ib, 0) + ((ib & 3) << 2);
@@ -341,55 +350,59 @@ __device__ __forceinline__ void symv_rows(const double* P, const double* x, int 
   y1 = own ? (b0 + b1) + (b2 + b3) : 0.0;
 }
 
-// Self-test kernel: one warp packs a dense symmetric matrix into tiles, multiplies, factors and solves.
-__global__ void linalg_selftest_kernel(int n, const double* __restrict__ A, const double* __restrict__ b,
+// Self-test kernel: one lane group packs a dense symmetric matrix into tiles, multiplies, factors and solves.  With
+// G < 32 every group of the warp works on its own copy in its own shared-memory region, and group `which` reports.
+template <int G>
+__global__ void linalg_selftest_kernel(int n, int which, const double* __restrict__ A, const double* __restrict__ b,
                                        const double* __restrict__ x, double* __restrict__ sol,
                                        double* __restrict__ prod, int* __restrict__ ok) {
   extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31, nb = nblk(n), n4 = nb << 2;
-  double* K = sm;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), sub = lane / G, nb = nblk(n), n4 = nb << 2;
+  const unsigned gm = (G == 32) ? kFullMask : (((1u << (G & 31)) - 1u) << (sub * G));
+  const int per_group = tiles_doubles(n) + 2 * n4;
+  double* K = sm + sub * per_group;
   double* rhs = K + tiles_doubles(n);
   double* xv = rhs + n4;
-  unsigned short* lut = reinterpret_cast<unsigned short*>(xv + n4);
+  unsigned short* lut = reinterpret_cast<unsigned short*>(sm + (32 / G) * per_group);
   chol_lut_build(lut, nb, lane, 32);
-  for (int e = lane; e < tiles_doubles(n); e += 32) K[e] = 0.0;
   __syncwarp();
-  for (int e = lane; e < n4 * n4; e += 32) {
-    const int i = e / n4, j = e % n4;
-    if (j > i && (i >> 2) != (j >> 2)) continue;
-    double v = (i < n && j < n) ? A[i * n + j] : ((i == j) ? 1.0 : 0.0);
-    K[elem_off(i, j)] = v;
-  }
-  for (int i = lane; i < n4; i += 32) { rhs[i] = (i < n) ? b[i] : 0.0; xv[i] = (i < n) ? x[i] : 0.0; }
-  __syncwarp();
-  double y0, y1;
-  symv_tiles(K, xv, nb, lane, y0, y1);
-  if (lane < n) prod[lane] = y0;
-  if (lane + 32 < n) prod[lane + 32] = y1;
-  __syncwarp();
-  const bool good = chol_tiles(K, nb, lane, lut);
-  solve_tiles(K, rhs, nb, lane);
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) sol[i] = rhs[i];
-  if (lane == 0) *ok = good ? 1 : 0;
-  // the matvec in the solver's layout (even n only: lane k owns rows k and n/2 + k); its result goes behind the
-  // other one: prod[n .. 2n)
-  if ((n & 1) == 0) {
-    const int T = n >> 1;
-    __syncwarp();
-    // symv needs the matrix again
-    __syncwarp();
-    for (int e = lane; e < tiles_doubles(n); e += 32) K[e] = 0.0;
-    __syncwarp();
-    for (int e = lane; e < n4 * n4; e += 32) {
+  const bool report = sub == which;
+  auto pack = [&]() {
+    for (int e = gl; e < tiles_doubles(n); e += G) K[e] = 0.0;
+    __syncwarp(gm);
+    for (int e = gl; e < n4 * n4; e += G) {
       const int i = e / n4, j = e % n4;
       if (j > i && (i >> 2) != (j >> 2)) continue;
       K[elem_off(i, j)] = (i < n && j < n) ? A[i * n + j] : ((i == j) ? 1.0 : 0.0);
     }
-    __syncwarp();
+    __syncwarp(gm);
+  };
+  pack();
+  for (int i = gl; i < n4; i += G) { rhs[i] = (i < n) ? b[i] : 0.0; xv[i] = (i < n) ? x[i] : 0.0; }
+  __syncwarp(gm);
+  if (G == 32) {                                    // the plain tiled matvec only exists for a whole warp
+    double y0, y1;
+    symv_tiles(K, xv, nb, lane, y0, y1);
+    if (lane < n) prod[lane] = y0;
+    if (lane + 32 < n) prod[lane + 32] = y1;
+    __syncwarp(gm);
+  }
+  const bool good = chol_tiles<G>(K, nb, gl, gm, lut);
+  solve_tiles<G>(K, rhs, nb, gl, gm);
+  __syncwarp(gm);
+  if (report) {
+    for (int i = gl; i < n; i += G) sol[i] = rhs[i];
+    if (gl == 0) *ok = good ? 1 : 0;
+  }
+  // the matvec in the solver's layout (even n, n / 2 <= G: lane k owns rows k and n/2 + k); its result goes behind
+  // the other one: prod[n .. 2n)
+  if ((n & 1) == 0 && (n >> 1) <= G) {
+    const int T = n >> 1;
+    __syncwarp(gm);
+    pack();                                         // symv needs the matrix again
     double q0, q1;
-    symv_rows<0>(K, xv, T, nb, lane, q0, q1);
-    if (lane < T) { prod[n + lane] = q0; prod[n + T + lane] = q1; }
+    symv_rows<0>(K, xv, T, nb, gl, q0, q1);
+    if (report && gl < T) { prod[n + gl] = q0; prod[n + T + gl] = q1; }
   }
 }
 

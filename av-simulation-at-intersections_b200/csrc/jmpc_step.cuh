@@ -1,4 +1,5 @@
-// jmpc_step.cuh -- the fused MPC-step kernel: one warp owns one instance.
+// jmpc_step.cuh -- the fused MPC-step kernel: one lane group (a whole warp, or half a warp for horizons T <= 15)
+// owns one instance.
 //
 // Pipeline per instance (reference lines relative to SaeedRahmani/AV-Simulation-at-Intersections):
 //   1. nearest forward index on the course        main/lib/trajectories.py:100-126
@@ -14,6 +15,15 @@
 // All arithmetic is float64: the index decisions (rint, 3-nearest rule) must match numpy bit for bit, and
 // the condensed Hessians have cond ~1e6..1e7, far outside what fp32 factors resolve
 // at the 1e-4 control tolerance.
+//
+// Lane groups.  Lane k of a group owns horizon stage k, so an instance needs T + 1 lanes: with the reference's
+// default horizon (T = 13) a warp-per-instance mapping leaves 18 of 32 lanes idle in all the row work and pays every
+// synchronisation, every redundant diagonal-block factorisation and every shuffle reduction for one instance only.
+// The kernel is therefore a template on G, the lanes per instance: G = 16 packs two independent instances into a
+// warp (one per half), G = 32 is the whole warp (T >= 16).  The groups of a warp run in lock step: every phase is
+// uniform control flow (a group that is finished, failed or has no instance left keeps executing on its own
+// shared-memory region with its commits switched off), but all shuffles and synchronisations are group-scoped,
+// so correctness never depends on the halves being converged.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,8 +46,10 @@ struct StepArgs {
   double mu_tol;
   double tol_res;           // primal / (scaled) dual residual tolerance of the strict exit
   double init_mu;           // > 0: centred start lambda = init_mu / s ; 0: lambda = 1
+  double du_th;             // > 0: leave the linearisation loop once sum|du| <= du_th (mpc.py:236-240, commented out there)
   // course tables
   const double* cx; const double* cy; const double* cyaw;
+  const double* cv;         // reference speed profile per course point (mpc_with_speed.py:104) or nullptr
   const int* course_n; int course_stride; int n_courses;
   // inputs
   const double* state; const int* course_id; const int* course_len; const int* warm;
@@ -59,7 +71,7 @@ struct StepArgs {
   int n_peers;
   long long rank_offset;
   // scratch
-  double* pscratch;         // [resident warps][tiles_doubles(n)] condensed Hessian on tiles, L2 resident
+  double* pscratch;         // [resident groups][tiles_doubles(n)] condensed Hessian on tiles, L2 resident
   unsigned int* counter;    // dynamic work queue
 };
 
@@ -75,65 +87,75 @@ enum MomentSlot {
   MOM_QV, MOM_QPSI, MOM_COUNT
 };
 
-// shared-memory doubles one warp needs for horizon T (every sub-array starts 16-byte aligned)
+// shared-memory doubles one instance needs for horizon T (every sub-array starts 16-byte aligned)
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
 // the K region also hosts the suffix moments during the condensing (short horizons need more room for those)
 __host__ __device__ inline int k_region_doubles(int T) {
   const int a = tiles_doubles(2 * T), b = MOM_COUNT * even_up(T + 1);
   return a > b ? a : b;
 }
-__host__ __device__ inline int warp_smem_doubles(int T) {
+__host__ __device__ inline int inst_smem_doubles(int T) {
   const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
   return k_region_doubles(T)    // K / L on 4x4 tiles (and the condensing's moment tables)
          + 4 * n4               // u, q, rhs, grad
-         + 14 * T1e             // prefix sums ca, cb, cc, ck; stage weights W11, W12, W22, qv, qpsi; WeX, WeY, epsi; vb, th
+         + 9 * T1e              // prefix sums ca, cb, cc, ck; WeX, WeY, epsi; vb, th
          + 4 * Te               // per-iteration row weights wA, wD, wR, SW
          + kParamSlots          // the instance's parameter vector + derived row bounds
          + 2;                   // mbarrier of the TMA Hessian copy (8 bytes, padded to 16)
 }
 
-// dynamic shared memory of a block of `wpb` warps: the warps' regions plus the block-shared Cholesky task table
-__host__ __device__ inline size_t step_block_smem_bytes(int T, int wpb) {
-  return (size_t)wpb * warp_smem_doubles(T) * sizeof(double) + (((size_t)chol_lut_entries(nblk(2 * T) + 1) * 2 + 15) & ~(size_t)15);
+// lanes per instance for horizon T: lane k owns stage k and horizon point k (T + 1 points)
+__host__ __device__ inline int group_lanes_for(int T) { return (T + 1 <= 16) ? 16 : 32; }
+
+// dynamic shared memory of a block of `wpb` warps with `groups` instances each: the instances' regions plus the
+// block-shared Cholesky task table
+__host__ __device__ inline size_t step_block_smem_bytes(int T, int wpb, int groups) {
+  return (size_t)wpb * groups * inst_smem_doubles(T) * sizeof(double) +
+         (((size_t)chol_lut_entries(nblk(2 * T) + 1) * 2 + 15) & ~(size_t)15);
 }
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
-__device__ __forceinline__ double warp_sum(double v) {
+// ---- group-scoped collectives: G lanes, `gm` = the group's lane mask, `gl` = lane index inside the group ----------
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  if constexpr (G == 32) return kFull;
+  else return ((1u << G) - 1u) << (lane & ~(G - 1));
+}
+template <int G>
+__device__ __forceinline__ double grp_sum(double v, unsigned gm) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o);
   return v;
 }
-__device__ __forceinline__ double warp_min(double v) {
+template <int G>
+__device__ __forceinline__ double grp_max(double v, unsigned gm) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o));
   return v;
 }
-__device__ __forceinline__ double warp_max(double v) {
+// inclusive prefix sum over the group's lanes
+template <int G>
+__device__ __forceinline__ double grp_scan(double v, int gl, unsigned gm) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-  return v;
-}
-// inclusive prefix sum over lanes 0..31
-__device__ __forceinline__ double warp_scan(double v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_up_sync(kFull, v, o);
-    if (lane >= o) v += t;
+  for (int o = 1; o < G; o <<= 1) {
+    double t = __shfl_up_sync(gm, v, o, G);
+    if (gl >= o) v += t;
   }
   return v;
 }
-// inclusive suffix sum: out[lane] = sum_{l >= lane} v[l]
-__device__ __forceinline__ double warp_rscan(double v, int lane) {
+// inclusive suffix sum: out[gl] = sum_{l >= gl} v[l]
+template <int G>
+__device__ __forceinline__ double grp_rscan(double v, int gl, unsigned gm) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_down_sync(kFull, v, o);
-    if (lane + o < 32) v += t;
+  for (int o = 1; o < G; o <<= 1) {
+    double t = __shfl_down_sync(gm, v, o, G);
+    if (gl + o < G) v += t;
   }
   return v;
 }
 
-// Lane 0 writes the instance's result record locally and, when peers are set, into every peer's gathered table
+// One lane writes the instance's result record locally and, when peers are set, into every peer's gathered table
 // (one 64-byte store each; with NVSwitch every peer is one hop away, and the stores are the only communication of
 // the whole step -- the all-gather is fused into the solve kernel's epilogue).
 __device__ __forceinline__ void write_record(const StepArgs& A, int b, double r0, double r1, double r2, double r3,
@@ -150,10 +172,10 @@ __device__ __forceinline__ void write_record(const StepArgs& A, int b, double r0
 
 // An instance that is not solved keeps its in-out values: when the write side is a different array (host entry
 // points) they are carried over here.
-__device__ __forceinline__ void carry_inout(const StepArgs& A, int b, int T, int lane) {
-  if (A.oa_out != A.oa && lane < T) A.oa_out[(size_t)b * T + lane] = A.oa[(size_t)b * T + lane];
-  if (A.od_out != A.od && lane < T) A.od_out[(size_t)b * T + lane] = A.od[(size_t)b * T + lane];
-  if (A.target_out != A.target_ind && lane == 0) A.target_out[b] = A.target_ind[b];
+__device__ __forceinline__ void carry_inout(const StepArgs& A, int b, int T, int gl) {
+  if (A.oa_out != A.oa && gl < T) A.oa_out[(size_t)b * T + gl] = A.oa[(size_t)b * T + gl];
+  if (A.od_out != A.od && gl < T) A.od_out[(size_t)b * T + gl] = A.od[(size_t)b * T + gl];
+  if (A.target_out != A.target_ind && gl == 0) A.target_out[b] = A.target_ind[b];
 }
 
 // ---- candidate list for the 3-nearest rule: ascending by (d2, index) --------------------------------
@@ -176,15 +198,16 @@ __device__ __forceinline__ void near3_insert(Near3& s, double d, int i) {
 // Nearest forward index (trajectories.py:100-126).  Returns -1 when the rule raises.
 // Distances are compared squared (monotone in the reference's sqrt); products are kept unfused so the
 // ordering matches numpy's dx*dx + dy*dy.  Ties break towards the lower index.
+template <int G>
 __device__ inline int nearest_index(const double* __restrict__ cx, const double* __restrict__ cy, int n_course,
-                                    int start, double x, double y, int lane) {
+                                    int start, double x, double y, int gl, unsigned gm) {
   const int m = n_course - start;
   if (m <= 1) return start;
   if (m == 2) return start + 1;
   Near3 s;
   s.d0 = s.d1 = s.d2 = INFINITY;
   s.i0 = s.i1 = s.i2 = 0x7fffffff;
-  for (int j = start + lane; j < n_course; j += 32) {
+  for (int j = start + gl; j < n_course; j += G) {
     const double ex = cx[j] - x, ey = cy[j] - y;
     const double d = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
     near3_insert(s, d, j - start);
@@ -195,9 +218,9 @@ __device__ inline int nearest_index(const double* __restrict__ cx, const double*
     // global best among the lanes' heads
     double bd = s.d0; int bi = s.i0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double od = __shfl_xor_sync(kFull, bd, o);
-      const int oi = __shfl_xor_sync(kFull, bi, o);
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(gm, bd, o);
+      const int oi = __shfl_xor_sync(gm, bi, o);
       if (closer(od, oi, bd, bi)) { bd = od; bi = oi; }
     }
     res[r] = bi;
@@ -210,11 +233,10 @@ __device__ inline int nearest_index(const double* __restrict__ cx, const double*
   return -1;
 }
 
-// ---- per-warp shared-memory views --------------------------------------------------------------------
+// ---- per-instance shared-memory views ------------------------------------------------------------------
 struct WarpMem {
   double *K, *u, *q, *rhs, *grad;
   double *ca, *cb, *cc, *ck;
-  double *W11, *W12, *W22, *qv, *qpsi;
   double *WeX, *WeY, *epsi, *vb, *th;
   double *wA, *wD, *wR, *SW;
   double *prm;
@@ -227,7 +249,6 @@ struct WarpMem {
     // grad .. epsi are dead while the solver runs: 4 (2T) + 7 (T + 1) >= 8T doubles, the solver's row stash
     ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
     WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e;
-    W11 = p; p += T1e; W12 = p; p += T1e; W22 = p; p += T1e; qv = p; p += T1e; qpsi = p; p += T1e;
     vb = p; p += T1e; th = p; p += T1e;
     wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; SW = p; p += Te;
     prm = p; p += kParamSlots;
@@ -258,32 +279,43 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 // z = A u for the stage rows (u in shared memory)
-__device__ __forceinline__ void rows_apply(const double* u, int T, int lane, double z[4]) {
-  const double a = (lane < T) ? u[lane] : 0.0;
-  const double d = (lane < T) ? u[T + lane] : 0.0;
-  const double dn = __shfl_down_sync(kFull, d, 1);
-  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = warp_scan(a, lane);
+template <int G>
+__device__ __forceinline__ void rows_apply(const double* u, int T, int gl, unsigned gm, double z[4]) {
+  const double a = (gl < T) ? u[gl] : 0.0;
+  const double d = (gl < T) ? u[T + gl] : 0.0;
+  const double dn = __shfl_down_sync(gm, d, 1, G);
+  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = grp_scan<G>(a, gl, gm);
 }
-// the same for a vector held in registers (a = entry lane, d = entry T + lane; 0 beyond the horizon)
-__device__ __forceinline__ void rows_apply_reg(double a, double d, int lane, double z[4]) {
-  const double dn = __shfl_down_sync(kFull, d, 1);
-  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = warp_scan(a, lane);
+// the same for a vector held in registers (a = entry gl, d = entry T + gl; 0 beyond the horizon)
+template <int G>
+__device__ __forceinline__ void rows_apply_reg(double a, double d, int gl, unsigned gm, double z[4]) {
+  const double dn = __shfl_down_sync(gm, d, 1, G);
+  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = grp_scan<G>(a, gl, gm);
 }
 // (A' t): this lane's entries for a_k (ra) and delta_k (rd); dead rows must carry t = 0
-__device__ __forceinline__ void rows_apply_T(const double t[4], int lane, double& ra, double& rd) {
-  ra = t[0] + warp_rscan(t[3], lane);
-  double up = __shfl_up_sync(kFull, t[2], 1);
-  if (lane == 0) up = 0.0;
+template <int G>
+__device__ __forceinline__ void rows_apply_T(const double t[4], int gl, unsigned gm, double& ra, double& rd) {
+  ra = t[0] + grp_rscan<G>(t[3], gl, gm);
+  double up = __shfl_up_sync(gm, t[2], 1, G);
+  if (gl == 0) up = 0.0;
   rd = t[1] - t[2] + up;
+}
+
+// reference speed of horizon point `idx` (xref[2]): 0 for lib.mpc (mpc.py:107); the speed profile of
+// mpc_with_speed.py:104 is either a per-course table or the two-level profile its set_trajectory_fromarray builds
+// (V_REF before the cut index, 0 from there on); a cut index also applies on top of a table
+__device__ __forceinline__ double ref_speed(const StepArgs& A, const double* prm, int cid, int idx) {
+  if (!((double)idx < prm[JMPC_P_V_REF_CUT])) return 0.0;
+  return A.cv ? A.cv[(size_t)cid * A.course_stride + idx] : prm[JMPC_P_V_REF];
 }
 
 // ---- phase A: index, reference sampling, rollout, linearisation, condensing --------------------------------
 // Leaves everything the later phases need in shared memory / the L2 scratch; returns a jmpc_status
-// (JMPC_OPTIMAL = go on and solve).
-template <int TT>
-__device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_base, double* pscr, int lane, int lin,
-                                      int total_iters, double oa_k, double od_k, double ov_k, int& target,
-                                      int& idx_out, unsigned& end_mask_out) {
+// (JMPC_OPTIMAL = go on and solve).  `active` = this group holds a real instance (its failures are reported).
+template <int TT, int G>
+__device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, double* smem_base, double* pscr, int gl,
+                                      unsigned gm, int lin, int total_iters, double oa_k, double od_k, double ov_k,
+                                      int& target, int& idx_out, unsigned& end_mask_out) {
   const int T = (TT > 0) ? TT : A.T;
   const int n = 2 * T, T1 = T + 1, nb = nblk(n), n4 = nb << 2;
   WarpMem M(smem_base, T);
@@ -299,503 +331,514 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, double* smem_bas
   const double dt = P(JMPC_P_DT), dl = P(JMPC_P_DL), Lw = P(JMPC_P_L), speed = P(JMPC_P_SPEED);
   const double min_speed = P(JMPC_P_MIN_SPEED);
   if (lin == 0) target = min(max(target, 0), n_course);      // numpy slicing clamps an out-of-range start
-  {
-    // ---------------- 1. nearest index --------------------------------------------------------------
-    const int near = nearest_index(cx, cy, n_course, target, x0, y0, lane);
-    if (near < 0) {
-      carry_inout(A, b, T, lane);
-      if (lane == 0) {
+  // ---------------- 1. nearest index --------------------------------------------------------------
+  const int near = nearest_index<G>(cx, cy, n_course, target, x0, y0, gl, gm);
+  if (near < 0) {                        // group-uniform; the rest of the phase only touches this group's memory
+    if (active) {
+      carry_inout(A, b, T, gl);
+      if (gl == 0) {
         A.status[b] = JMPC_INDEX_RULE; if (A.iters) A.iters[b] = total_iters;
         write_record(A, b, nan(""), nan(""), nan(""), JMPC_INDEX_RULE, A.target_ind[b], total_iters, nan(""), nan(""));
       }
-      return JMPC_INDEX_RULE;
     }
-    target = near;
-
-    // ---------------- 2. reference sampling ---------------------------------------------------------
-    // travel = cumsum(|ov| dt): sequential float64 adds, reproduced literally (lane k owns point k)
-    double sp_k;
-    if (lin == 0) sp_k = fabs(fmax(v0, P(JMPC_P_V_REF_MIN))) * dt; else sp_k = fabs(ov_k) * dt;
-    double travel = 0.0;
-    {
-      double acc = 0.0;
-      for (int j = 0; j <= T; ++j) {          // uniform trip count: every lane takes part in the shuffle
-        const double sj = __shfl_sync(kFull, sp_k, j);
-        if (j <= lane) acc = (j == 0) ? sj : __dadd_rn(acc, sj);
-      }
-      travel = acc;
-    }
-    int idx = 0;
-    bool at_end = false;
-    double xr = 0.0, yr = 0.0, psir = 0.0, vr = 0.0;
-    if (lane <= T) {
-      const long long hop = (long long)rint(travel / dl);
-      long long id = hop + (long long)target;
-      if (id > (long long)(n_course - 1)) id = n_course - 1;
-      if (id < 0) id = 0;
-      idx = (int)id;
-      at_end = (idx == n_course - 1);
-      xr = cx[idx]; yr = cy[idx]; psir = cyaw[idx];
-      vr = ((double)idx < P(JMPC_P_V_REF_CUT)) ? P(JMPC_P_V_REF) : 0.0;     // mpc_with_speed.py:104; 0 for lib.mpc
-    }
-    const unsigned end_mask = __ballot_sync(kFull, at_end);    // bit t = reaches_end[t]
-
-    // ---------------- 3. operating-point rollout ----------------------------------------------------
-    // theta and v recurrences need no trigonometry of the state, so every lane walks them redundantly,
-    // then lane t evaluates sin/cos(theta_t) once and the positions are accumulated in sequence.
-    const double max_steer = P(JMPC_P_MAX_STEER), vmax_sim = P(JMPC_P_SIM_MAX_SPEED);
-    const double tan_k = tan(fmax(fmin(od_k, max_steer), -max_steer));
-    double vb = v0, th = yaw0;          // lane t ends up holding vbar_t, phibar_t
-    {
-      double v = v0, ang = yaw0;
-      for (int t = 0; t < T; ++t) {
-        const double a_t = __shfl_sync(kFull, oa_k, t);
-        const double tn_t = __shfl_sync(kFull, tan_k, t);
-        const double yaw_dot = __dmul_rn(v / Lw, tn_t);
-        ang = __dadd_rn(ang, __dmul_rn(yaw_dot, dt));
-        v = __dadd_rn(v, __dmul_rn(a_t, dt));
-        v = fmax(fmin(v, vmax_sim), min_speed);
-        if (lane == t + 1) { vb = v; th = ang; }
-      }
-    }
-    double sn, cs;
-    sincos(th, &sn, &cs);
-    // (x, y) are only reported (xbar rows 0,1 do not enter the QP); the QP needs vbar, phibar.
-    // ---------------- 4. linearisation + condensing -------------------------------------------------
-    // per-stage coefficients (stage t = lane, t < T)
-    double al = 0.0, be = 0.0, ga = 0.0, ka = 0.0, gk = 0.0;
-    if (lane < T) {
-      al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw;
-    }
-    // exclusive prefix sums c*[t] = sum_{j<t} (.)  for t = 0..T  (lane t).  Only differences c[t] - c[k] are ever
-    // used, so each array is centred on its mid-horizon value: that halves the magnitudes entering the moment
-    // expansion of the Hessian below.
-    double ca_t = warp_scan(al, lane) - al, cb_t = warp_scan(be, lane) - be;
-    double cc_t = warp_scan(ga, lane) - ga, ck_t = warp_scan(ka, lane) - ka;
-    ca_t -= __shfl_sync(kFull, ca_t, T >> 1); cb_t -= __shfl_sync(kFull, cb_t, T >> 1);
-    cc_t -= __shfl_sync(kFull, cc_t, T >> 1); ck_t -= __shfl_sync(kFull, ck_t, T >> 1);
-    // free response (u = 0): v = v0, psi = yaw0
-    const double fx_term = (lane < T) ? (al * v0 - be * (yaw0 - th)) : 0.0;
-    const double fy_term = (lane < T) ? (ga * v0 + ka * (yaw0 - th)) : 0.0;
-    const double xf_t = x0 + (warp_scan(fx_term, lane) - fx_term);
-    const double yf_t = y0 + (warp_scan(fy_term, lane) - fy_term);
-    // stage weights (t = lane, meaningful for 1 <= t <= T)
-    double w11 = 0.0, w12 = 0.0, w22 = 0.0, wv = 0.0, wpsi = 0.0;
-    if (lane >= 1 && lane <= T) {
-      if (at_end) {
-        w11 = P(JMPC_P_QF_X); w22 = P(JMPC_P_QF_Y); wv = P(JMPC_P_QF_V); wpsi = P(JMPC_P_QF_YAW);
-      } else {
-        double s1, c1, s2, c2;
-        sincos(psir + 0.5 * M_PI, &s1, &c1);
-        sincos(psir, &s2, &c2);
-        const double wp = P(JMPC_P_W_PERP), wl = P(JMPC_P_W_PARA);
-        w11 = (c1 * c1) * wp + (c2 * c2) * wl;
-        w12 = (c1 * s1) * wp + (c2 * s2) * wl;
-        w22 = (s1 * s1) * wp + (s2 * s2) * wl;
-        wv = P(JMPC_P_Q_V); wpsi = P(JMPC_P_Q_YAW);
-      }
-    }
-    // Suffix moments  mom[m][t0] = sum_{t >= t0} W_t * (product of centred prefix values at t),  23 sequences, kept
-    // in the K region (free until the solver starts).  With them every Hessian entry is O(1):
-    //   sum_{t>=t0} W (F_t - F0)(G_t - G0) = M_WFG - G0 M_WF - F0 M_WG + F0 G0 M_W.
-    {
-      const bool vt = (lane >= 1 && lane <= T);
-      const double A_ = vt ? ca_t : 0.0, B_ = vt ? cb_t : 0.0, C_ = vt ? cc_t : 0.0, K_ = vt ? ck_t : 0.0;
-      double* mom = M.K;
-      const int ms = even_up(T + 1);
-      auto put = [&](int m, double v) { const double sfx = warp_rscan(v, lane); if (lane <= T) mom[m * ms + lane] = sfx; };
-      put(MOM_11, w11); put(MOM_11_A, w11 * A_); put(MOM_11_B, w11 * B_);
-      put(MOM_11_AA, w11 * A_ * A_); put(MOM_11_AB, w11 * A_ * B_); put(MOM_11_BB, w11 * B_ * B_);
-      put(MOM_12, w12); put(MOM_12_A, w12 * A_); put(MOM_12_B, w12 * B_); put(MOM_12_C, w12 * C_); put(MOM_12_K, w12 * K_);
-      put(MOM_12_AC, w12 * A_ * C_); put(MOM_12_AK, w12 * A_ * K_); put(MOM_12_BC, w12 * B_ * C_); put(MOM_12_BK, w12 * B_ * K_);
-      put(MOM_22, w22); put(MOM_22_C, w22 * C_); put(MOM_22_K, w22 * K_);
-      put(MOM_22_CC, w22 * C_ * C_); put(MOM_22_CK, w22 * C_ * K_); put(MOM_22_KK, w22 * K_ * K_);
-      put(MOM_QV, wv); put(MOM_QPSI, wpsi);
-    }
-    const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 - vr, eps = yaw0 - psir;
-    if (lane <= T) {
-      M.ca[lane] = ca_t; M.cb[lane] = cb_t; M.cc[lane] = cc_t; M.ck[lane] = ck_t;
-      M.W11[lane] = w11; M.W12[lane] = w12; M.W22[lane] = w22; M.qv[lane] = wv; M.qpsi[lane] = wpsi;
-      M.WeX[lane] = w11 * ex + w12 * ey; M.WeY[lane] = w12 * ex + w22 * ey; M.epsi[lane] = eps;
-      M.grad[lane] = ev;                 // speed error per stage (grad is free until the solver starts)
-    }
-    if (lane < T) M.wA[lane] = gk;      // borrow wA for g_k during condensing
-    if (lane <= T) { M.vb[lane] = vb; M.th[lane] = th; }       // operating point, reused by the epilogue
-    if (lane == 0) {                     // derived row bounds, read back by the solver
-      M.prm[kSlotHi3] = (speed - v0) / dt; M.prm[kSlotLo3] = (min_speed - v0) / dt;
-      M.prm[kSlotLim] = P(JMPC_P_MAX_DSTEER) * dt;
-    }
-    __syncwarp();
-
-    const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
-    const double Rea = P(JMPC_P_REND_A), Red = P(JMPC_P_REND_D);
-    const double dt2 = dt * dt;
-    // Hessian on 4x4 tiles (jmpc_linalg.cuh), variable order [a_0..a_{T-1}, delta_0..delta_{T-1}]; the last
-    // block row is cleared first so that the identity padding (n -> multiple of 4) is in place
-    {
-      const int last0 = tile_off(nb - 1, 0), last1 = tiles_doubles(n);
-      for (int e = last0 + lane; e < last1; e += 32) pscr[e] = 0.0;
-      __syncwarp();
-      if (lane < n4 - n) pscr[elem_off(n + lane, n + lane)] = 1.0;
-    }
-    {
-      // Three passes, one per block type (accel x accel, steer x accel, steer x steer): a single pass over the packed
-      // triangle mixed steer x accel and steer x steer entries in every group of 32, so the warp executed both paths.
-      const int ms = even_up(T + 1);
-      // S(W; F, G)(F0, G0) = sum_{t >= t0} W_t (F_t - F0)(G_t - G0) from the suffix moments
-      auto S = [&](const double* mom, int mW, int mWF, int mWG, int mWFG, double F0, double G0) -> double {
-        return mom[mWFG * ms] - G0 * mom[mWF * ms] - F0 * mom[mWG * ms] + F0 * G0 * mom[mW * ms];
-      };
-      auto store = [&](int i, int j, double acc) {
-        pscr[elem_off(i, j)] = acc;
-        if (i != j && (i >> 2) == (j >> 2)) pscr[elem_off(j, i)] = acc;      // diagonal tiles are stored full
-      };
-      // input and input-rate weights on the (block-)diagonal and first sub-diagonal (mpc.py:180-187)
-      auto input_weights = [&](int ki, int kj, double r_run, double r_end, double rd_w) -> double {
-        if (ki == kj) {
-          const bool e_t = (end_mask >> ki) & 1u;
-          const int nbr = (T >= 2) ? ((ki == 0 || ki == T - 1) ? 1 : 2) : 0;
-          return 2.0 * (e_t ? r_end : r_run) + 2.0 * rd_w * nbr;
-        }
-        return (ki == kj + 1) ? -2.0 * rd_w : 0.0;
-      };
-      {                                  // accel x accel: sX = dt (A - A0), sY = dt (C - C0), sV = dt
-        int ki = 0, kj = lane;
-        while (kj > ki) { kj -= ki + 1; ++ki; }
-        for (int e = lane; e < tri(T); e += 32) {
-          const double* mom = M.K + ki + 1;                      // t0 = max(ki, kj) + 1 = ki + 1
-          const double ai = M.ca[ki + 1], ci = M.cc[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-          double acc = S(mom, MOM_11, MOM_11_A, MOM_11_A, MOM_11_AA, ai, aj) + S(mom, MOM_12, MOM_12_A, MOM_12_C, MOM_12_AC, ai, cj)
-                     + S(mom, MOM_12, MOM_12_C, MOM_12_A, MOM_12_AC, ci, aj) + S(mom, MOM_22, MOM_22_C, MOM_22_C, MOM_22_CC, ci, cj)
-                     + mom[MOM_QV * ms];
-          acc = 2.0 * dt2 * acc + input_weights(ki, kj, Ra, Rea, Rda);
-          store(ki, kj, acc);
-          kj += 32;
-          while (kj > ki) { kj -= ki + 1; ++ki; }
-        }
-      }
-      for (int e = lane; e < T * T; e += 32) {                   // steer (row) x accel (col): sX_i = -g (B - B0), sY_i = g (K - K0)
-        const int ki = e / T, kj = e - ki * T;
-        const double* mom = M.K + max(ki, kj) + 1;
-        const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-        double acc = -S(mom, MOM_11, MOM_11_B, MOM_11_A, MOM_11_AB, bi, aj) - S(mom, MOM_12, MOM_12_B, MOM_12_C, MOM_12_BC, bi, cj)
-                   + S(mom, MOM_12, MOM_12_K, MOM_12_A, MOM_12_AK, kki, aj) + S(mom, MOM_22, MOM_22_K, MOM_22_C, MOM_22_CK, kki, cj);
-        acc *= 2.0 * M.wA[ki] * dt;
-        store(T + ki, kj, acc);
-      }
-      {                                  // steer x steer, plus the yaw weight
-        int ki = 0, kj = lane;
-        while (kj > ki) { kj -= ki + 1; ++ki; }
-        for (int e = lane; e < tri(T); e += 32) {
-          const double* mom = M.K + ki + 1;
-          const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], bj = M.cb[kj + 1], kkj = M.ck[kj + 1];
-          double acc = S(mom, MOM_11, MOM_11_B, MOM_11_B, MOM_11_BB, bi, bj) - S(mom, MOM_12, MOM_12_B, MOM_12_K, MOM_12_BK, bi, kkj)
-                     - S(mom, MOM_12, MOM_12_K, MOM_12_B, MOM_12_BK, kki, bj) + S(mom, MOM_22, MOM_22_K, MOM_22_K, MOM_22_KK, kki, kkj)
-                     + mom[MOM_QPSI * ms];
-          acc = 2.0 * M.wA[ki] * M.wA[kj] * acc + input_weights(ki, kj, Rd_, Red, Rdd);
-          store(T + ki, T + kj, acc);
-          kj += 32;
-          while (kj > ki) { kj -= ki + 1; ++ki; }
-        }
-      }
-    }
-    // linear term
-    if (lane < T) {
-      const int k = lane;
-      const double ai = M.ca[k + 1], ci = M.cc[k + 1], bi = M.cb[k + 1], kki = M.ck[k + 1];
-      double qa = 0.0, qd = 0.0;
-      for (int t = k + 1; t <= T; ++t) {
-        qa += dt * ((M.ca[t] - ai) * M.WeX[t] + (M.cc[t] - ci) * M.WeY[t]) + dt * M.qv[t] * M.grad[t];
-        qd += gk * (-(M.cb[t] - bi) * M.WeX[t] + (M.ck[t] - kki) * M.WeY[t]) + gk * M.qpsi[t] * M.epsi[t];
-      }
-      M.q[k] = 2.0 * qa; M.q[T + k] = 2.0 * qd;
-      M.u[k] = 0.0; M.u[T + k] = 0.0;
-    }
-    if (lane < n4 - n) { M.q[n + lane] = 0.0; M.u[n + lane] = 0.0; M.rhs[n + lane] = 0.0; M.grad[n + lane] = 0.0; }
-    __threadfence();                     // the Hessian scratch is read back by TMA (async proxy) in the solver
-    __syncwarp();
-
-    // feasibility predicate: the t = 0 speed rows act on the fixed v0
-    if (!(min_speed <= v0 && v0 <= speed)) {
-      const int status = JMPC_INFEASIBLE;
-      carry_inout(A, b, T, lane);
-      // xref / target are still reported, as the reference assigns them before the solve result
-      if (lane <= T) {
-        double* xo = A.xref + (size_t)b * 4 * T1;
-        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = vr; xo[3 * T1 + lane] = psir;
-      }
-      if (lane == 0) {
-        A.status[b] = status; A.target_out[b] = target; if (A.iters) A.iters[b] = total_iters;
-        A.cost[b] = nan("");
-        write_record(A, b, nan(""), P(JMPC_P_MAX_DECEL), nan(""), status, target, total_iters, nan(""), nan(""));
-      }
-      return JMPC_INFEASIBLE;
-    }
-    idx_out = idx; end_mask_out = end_mask;
-    return JMPC_OPTIMAL;
-
-
+    return JMPC_INDEX_RULE;
   }
+  target = near;
+
+  // ---------------- 2. reference sampling ---------------------------------------------------------
+  // travel = cumsum(|ov| dt): sequential float64 adds, reproduced literally (lane k owns point k)
+  double sp_k;
+  if (lin == 0) sp_k = fabs(fmax(v0, P(JMPC_P_V_REF_MIN))) * dt; else sp_k = fabs(ov_k) * dt;
+  double travel = 0.0;
+  {
+    double acc = 0.0;
+    for (int j = 0; j <= T; ++j) {          // uniform trip count: every lane takes part in the shuffle
+      const double sj = __shfl_sync(gm, sp_k, j, G);
+      if (j <= gl) acc = (j == 0) ? sj : __dadd_rn(acc, sj);
+    }
+    travel = acc;
+  }
+  int idx = 0;
+  bool at_end = false;
+  double xr = 0.0, yr = 0.0, psir = 0.0, vr = 0.0;
+  if (gl <= T) {
+    const long long hop = (long long)rint(travel / dl);
+    long long id = hop + (long long)target;
+    if (id > (long long)(n_course - 1)) id = n_course - 1;
+    if (id < 0) id = 0;
+    idx = (int)id;
+    at_end = (idx == n_course - 1);
+    xr = cx[idx]; yr = cy[idx]; psir = cyaw[idx];
+    vr = ref_speed(A, M.prm, cid, idx);     // mpc_with_speed.py:104; 0 for lib.mpc
+  }
+  // bit t = reaches_end[t]
+  const unsigned end_mask = (__ballot_sync(gm, at_end) >> ((threadIdx.x & 31) & ~(G - 1))) & (unsigned)((1ull << G) - 1ull);
+
+  // ---------------- 3. operating-point rollout ----------------------------------------------------
+  // theta and v recurrences need no trigonometry of the state, so every lane walks them redundantly,
+  // then lane t evaluates sin/cos(theta_t) once and the positions are accumulated in sequence.
+  const double max_steer = P(JMPC_P_MAX_STEER), vmax_sim = P(JMPC_P_SIM_MAX_SPEED);
+  const double tan_k = tan(fmax(fmin(od_k, max_steer), -max_steer));
+  double vb = v0, th = yaw0;          // lane t ends up holding vbar_t, phibar_t
+  {
+    double v = v0, ang = yaw0;
+    for (int t = 0; t < T; ++t) {
+      const double a_t = __shfl_sync(gm, oa_k, t, G);
+      const double tn_t = __shfl_sync(gm, tan_k, t, G);
+      const double yaw_dot = __dmul_rn(v / Lw, tn_t);
+      ang = __dadd_rn(ang, __dmul_rn(yaw_dot, dt));
+      v = __dadd_rn(v, __dmul_rn(a_t, dt));
+      v = fmax(fmin(v, vmax_sim), min_speed);
+      if (gl == t + 1) { vb = v; th = ang; }
+    }
+  }
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  // (x, y) are only reported (xbar rows 0,1 do not enter the QP); the QP needs vbar, phibar.
+  // ---------------- 4. linearisation + condensing -------------------------------------------------
+  // per-stage coefficients (stage t = lane, t < T)
+  double al = 0.0, be = 0.0, ga = 0.0, ka = 0.0, gk = 0.0;
+  if (gl < T) {
+    al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw;
+  }
+  // exclusive prefix sums c*[t] = sum_{j<t} (.)  for t = 0..T  (lane t).  Only differences c[t] - c[k] are ever
+  // used, so each array is centred on its mid-horizon value: that halves the magnitudes entering the moment
+  // expansion of the Hessian below.
+  double ca_t = grp_scan<G>(al, gl, gm) - al, cb_t = grp_scan<G>(be, gl, gm) - be;
+  double cc_t = grp_scan<G>(ga, gl, gm) - ga, ck_t = grp_scan<G>(ka, gl, gm) - ka;
+  ca_t -= __shfl_sync(gm, ca_t, T >> 1, G); cb_t -= __shfl_sync(gm, cb_t, T >> 1, G);
+  cc_t -= __shfl_sync(gm, cc_t, T >> 1, G); ck_t -= __shfl_sync(gm, ck_t, T >> 1, G);
+  // free response (u = 0): v = v0, psi = yaw0
+  const double fx_term = (gl < T) ? (al * v0 - be * (yaw0 - th)) : 0.0;
+  const double fy_term = (gl < T) ? (ga * v0 + ka * (yaw0 - th)) : 0.0;
+  const double xf_t = x0 + (grp_scan<G>(fx_term, gl, gm) - fx_term);
+  const double yf_t = y0 + (grp_scan<G>(fy_term, gl, gm) - fy_term);
+  // stage weights (t = lane, meaningful for 1 <= t <= T)
+  double w11 = 0.0, w12 = 0.0, w22 = 0.0, wv = 0.0, wpsi = 0.0;
+  if (gl >= 1 && gl <= T) {
+    if (at_end) {
+      w11 = P(JMPC_P_QF_X); w22 = P(JMPC_P_QF_Y); wv = P(JMPC_P_QF_V); wpsi = P(JMPC_P_QF_YAW);
+    } else {
+      double s1, c1, s2, c2;
+      sincos(psir + 0.5 * M_PI, &s1, &c1);
+      sincos(psir, &s2, &c2);
+      const double wp = P(JMPC_P_W_PERP), wl = P(JMPC_P_W_PARA);
+      w11 = (c1 * c1) * wp + (c2 * c2) * wl;
+      w12 = (c1 * s1) * wp + (c2 * s2) * wl;
+      w22 = (s1 * s1) * wp + (s2 * s2) * wl;
+      wv = P(JMPC_P_Q_V); wpsi = P(JMPC_P_Q_YAW);
+    }
+  }
+  // Suffix moments  mom[m][t0] = sum_{t >= t0} W_t * (product of centred prefix values at t),  23 sequences, kept
+  // in the K region (free until the solver starts).  With them every Hessian entry is O(1):
+  //   sum_{t>=t0} W (F_t - F0)(G_t - G0) = M_WFG - G0 M_WF - F0 M_WG + F0 G0 M_W.
+  {
+    const bool vt = (gl >= 1 && gl <= T);
+    const double A_ = vt ? ca_t : 0.0, B_ = vt ? cb_t : 0.0, C_ = vt ? cc_t : 0.0, K_ = vt ? ck_t : 0.0;
+    double* mom = M.K;
+    const int ms = even_up(T + 1);
+    auto put = [&](int m, double v) { const double sfx = grp_rscan<G>(v, gl, gm); if (gl <= T) mom[m * ms + gl] = sfx; };
+    put(MOM_11, w11); put(MOM_11_A, w11 * A_); put(MOM_11_B, w11 * B_);
+    put(MOM_11_AA, w11 * A_ * A_); put(MOM_11_AB, w11 * A_ * B_); put(MOM_11_BB, w11 * B_ * B_);
+    put(MOM_12, w12); put(MOM_12_A, w12 * A_); put(MOM_12_B, w12 * B_); put(MOM_12_C, w12 * C_); put(MOM_12_K, w12 * K_);
+    put(MOM_12_AC, w12 * A_ * C_); put(MOM_12_AK, w12 * A_ * K_); put(MOM_12_BC, w12 * B_ * C_); put(MOM_12_BK, w12 * B_ * K_);
+    put(MOM_22, w22); put(MOM_22_C, w22 * C_); put(MOM_22_K, w22 * K_);
+    put(MOM_22_CC, w22 * C_ * C_); put(MOM_22_CK, w22 * C_ * K_); put(MOM_22_KK, w22 * K_ * K_);
+    put(MOM_QV, wv); put(MOM_QPSI, wpsi);
+  }
+  const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 - vr, eps = yaw0 - psir;
+  if (gl <= T) {
+    M.ca[gl] = ca_t; M.cb[gl] = cb_t; M.cc[gl] = cc_t; M.ck[gl] = ck_t;
+    M.WeX[gl] = w11 * ex + w12 * ey; M.WeY[gl] = w12 * ex + w22 * ey;
+    M.epsi[gl] = wpsi * eps;          // weighted yaw error per stage
+    M.grad[gl] = wv * ev;             // weighted speed error per stage (grad is free until the solver starts)
+  }
+  if (gl < T) M.wA[gl] = gk;          // borrow wA for g_k during condensing
+  if (gl <= T) { M.vb[gl] = vb; M.th[gl] = th; }       // operating point, reused by the epilogue
+  if (gl == 0) {                      // derived row bounds, read back by the solver
+    M.prm[kSlotHi3] = (speed - v0) / dt; M.prm[kSlotLo3] = (min_speed - v0) / dt;
+    M.prm[kSlotLim] = P(JMPC_P_MAX_DSTEER) * dt;
+  }
+  __syncwarp(gm);
+
+  const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
+  const double Rea = P(JMPC_P_REND_A), Red = P(JMPC_P_REND_D);
+  const double dt2 = dt * dt;
+  // Hessian on 4x4 tiles (jmpc_linalg.cuh), variable order [a_0..a_{T-1}, delta_0..delta_{T-1}]; the last
+  // block row is cleared first so that the identity padding (n -> multiple of 4) is in place
+  {
+    const int last0 = tile_off(nb - 1, 0), last1 = tiles_doubles(n);
+    for (int e = last0 + gl; e < last1; e += G) pscr[e] = 0.0;
+    __syncwarp(gm);
+    if (gl < n4 - n) pscr[elem_off(n + gl, n + gl)] = 1.0;
+  }
+  {
+    // Three passes, one per block type (accel x accel, steer x accel, steer x steer): a single pass over the packed
+    // triangle mixed steer x accel and steer x steer entries in every group of lanes, so the warp executed both paths.
+    const int ms = even_up(T + 1);
+    // S(W; F, G)(F0, G0) = sum_{t >= t0} W_t (F_t - F0)(G_t - G0) from the suffix moments
+    auto S = [&](const double* mom, int mW, int mWF, int mWG, int mWFG, double F0, double G0) -> double {
+      return mom[mWFG * ms] - G0 * mom[mWF * ms] - F0 * mom[mWG * ms] + F0 * G0 * mom[mW * ms];
+    };
+    auto store = [&](int i, int j, double acc) {
+      pscr[elem_off(i, j)] = acc;
+      if (i != j && (i >> 2) == (j >> 2)) pscr[elem_off(j, i)] = acc;      // diagonal tiles are stored full
+    };
+    // input and input-rate weights on the (block-)diagonal and first sub-diagonal (mpc.py:180-187)
+    auto input_weights = [&](int ki, int kj, double r_run, double r_end, double rd_w) -> double {
+      if (ki == kj) {
+        const bool e_t = (end_mask >> ki) & 1u;
+        const int nbr = (T >= 2) ? ((ki == 0 || ki == T - 1) ? 1 : 2) : 0;
+        return 2.0 * (e_t ? r_end : r_run) + 2.0 * rd_w * nbr;
+      }
+      return (ki == kj + 1) ? -2.0 * rd_w : 0.0;
+    };
+    {                                  // accel x accel: sX = dt (A - A0), sY = dt (C - C0), sV = dt
+      int ki = 0, kj = gl;
+      while (kj > ki) { kj -= ki + 1; ++ki; }
+      for (int e = gl; e < tri(T); e += G) {
+        const double* mom = M.K + ki + 1;                      // t0 = max(ki, kj) + 1 = ki + 1
+        const double ai = M.ca[ki + 1], ci = M.cc[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
+        double acc = S(mom, MOM_11, MOM_11_A, MOM_11_A, MOM_11_AA, ai, aj) + S(mom, MOM_12, MOM_12_A, MOM_12_C, MOM_12_AC, ai, cj)
+                   + S(mom, MOM_12, MOM_12_C, MOM_12_A, MOM_12_AC, ci, aj) + S(mom, MOM_22, MOM_22_C, MOM_22_C, MOM_22_CC, ci, cj)
+                   + mom[MOM_QV * ms];
+        acc = 2.0 * dt2 * acc + input_weights(ki, kj, Ra, Rea, Rda);
+        store(ki, kj, acc);
+        kj += G;
+        while (kj > ki) { kj -= ki + 1; ++ki; }
+      }
+    }
+    for (int e = gl; e < T * T; e += G) {                      // steer (row) x accel (col): sX_i = -g (B - B0), sY_i = g (K - K0)
+      const int ki = e / T, kj = e - ki * T;
+      const double* mom = M.K + max(ki, kj) + 1;
+      const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
+      double acc = -S(mom, MOM_11, MOM_11_B, MOM_11_A, MOM_11_AB, bi, aj) - S(mom, MOM_12, MOM_12_B, MOM_12_C, MOM_12_BC, bi, cj)
+                 + S(mom, MOM_12, MOM_12_K, MOM_12_A, MOM_12_AK, kki, aj) + S(mom, MOM_22, MOM_22_K, MOM_22_C, MOM_22_CK, kki, cj);
+      acc *= 2.0 * M.wA[ki] * dt;
+      store(T + ki, kj, acc);
+    }
+    {                                  // steer x steer, plus the yaw weight
+      int ki = 0, kj = gl;
+      while (kj > ki) { kj -= ki + 1; ++ki; }
+      for (int e = gl; e < tri(T); e += G) {
+        const double* mom = M.K + ki + 1;
+        const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], bj = M.cb[kj + 1], kkj = M.ck[kj + 1];
+        double acc = S(mom, MOM_11, MOM_11_B, MOM_11_B, MOM_11_BB, bi, bj) - S(mom, MOM_12, MOM_12_B, MOM_12_K, MOM_12_BK, bi, kkj)
+                   - S(mom, MOM_12, MOM_12_K, MOM_12_B, MOM_12_BK, kki, bj) + S(mom, MOM_22, MOM_22_K, MOM_22_K, MOM_22_KK, kki, kkj)
+                   + mom[MOM_QPSI * ms];
+        acc = 2.0 * M.wA[ki] * M.wA[kj] * acc + input_weights(ki, kj, Rd_, Red, Rdd);
+        store(T + ki, T + kj, acc);
+        kj += G;
+        while (kj > ki) { kj -= ki + 1; ++ki; }
+      }
+    }
+  }
+  // linear term
+  if (gl < T) {
+    const int k = gl;
+    const double ai = M.ca[k + 1], ci = M.cc[k + 1], bi = M.cb[k + 1], kki = M.ck[k + 1];
+    double qa = 0.0, qd = 0.0;
+    for (int t = k + 1; t <= T; ++t) {
+      qa += dt * ((M.ca[t] - ai) * M.WeX[t] + (M.cc[t] - ci) * M.WeY[t]) + dt * M.grad[t];
+      qd += gk * (-(M.cb[t] - bi) * M.WeX[t] + (M.ck[t] - kki) * M.WeY[t]) + gk * M.epsi[t];
+    }
+    M.q[k] = 2.0 * qa; M.q[T + k] = 2.0 * qd;
+    M.u[k] = 0.0; M.u[T + k] = 0.0;
+  }
+  if (gl < n4 - n) { M.q[n + gl] = 0.0; M.u[n + gl] = 0.0; M.rhs[n + gl] = 0.0; M.grad[n + gl] = 0.0; }
+  __threadfence();                     // the Hessian scratch is read back by TMA (async proxy) in the solver
+  __syncwarp(gm);
+
+  // feasibility predicate: the t = 0 speed rows act on the fixed v0
+  if (!(min_speed <= v0 && v0 <= speed)) {
+    if (active) {
+      carry_inout(A, b, T, gl);
+      // xref / target are still reported, as the reference assigns them before the solve result
+      if (gl <= T) {
+        double* xo = A.xref + (size_t)b * 4 * T1;
+        xo[gl] = xr; xo[T1 + gl] = yr; xo[2 * T1 + gl] = vr; xo[3 * T1 + gl] = psir;
+      }
+      if (gl == 0) {
+        A.status[b] = JMPC_INFEASIBLE; A.target_out[b] = target; if (A.iters) A.iters[b] = total_iters;
+        A.cost[b] = nan("");
+        write_record(A, b, nan(""), P(JMPC_P_MAX_DECEL), nan(""), JMPC_INFEASIBLE, target, total_iters, nan(""), nan(""));
+      }
+    }
+    return JMPC_INFEASIBLE;
+  }
+  idx_out = idx; end_mask_out = end_mask;
+  return JMPC_OPTIMAL;
 }
 
 // ---- phase B: Mehrotra predictor-corrector on the condensed QP -----------------------------------------------
-// Returns the iteration count; `converged` says whether the KKT tolerances were met.
-template <int TT>
-__device__ __noinline__ int step_solve(const StepArgs& A, double* smem_base, const double* pscr, int lane,
-                                       bool& converged_out, unsigned& tma_parity, const unsigned short* lut) {
+// Returns the group's iteration count; `converged_out` says whether its KKT tolerances were met.  The groups of a
+// warp iterate in lock step until all of them are done; a group that is done (or never active) keeps executing on
+// its own data with its commits switched off, so the iterate it reports is the one it was done with.
+template <int TT, int G>
+__device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* smem_base, const double* pscr, int gl,
+                                       unsigned gm, bool& converged_out, unsigned& tma_parity, const unsigned short* lut) {
   const int T = (TT > 0) ? TT : A.T;
   const int n = 2 * T, nb = nblk(n);
   WarpMem M(smem_base, T);
   auto P = [&](int k) -> double { return M.prm[k]; };
-    // ---------------- 5. interior-point solve -------------------------------------------------------
-    // Stage k = lane owns four two-sided rows: r = 0 accel box, 1 steer box, 2 steer rate k -> k+1, 3 speed
-    // (running sum of a up to k).  Only slacks and multipliers stay in registers across the factorisation;
-    // bounds are rebuilt from the parameter block when needed.
-    double sh[4], sl[4], lh[4], ll[4];
-    const bool live013 = lane < T, live2 = lane < T - 1;
-    auto is_live = [&](int r) -> bool { return r == 2 ? live2 : live013; };
-    auto bound_hi = [&](int r) -> double {
-      return r == 0 ? P(JMPC_P_MAX_ACCEL) : r == 1 ? P(JMPC_P_MAX_STEER) : r == 2 ? P(kSlotLim) : P(kSlotHi3);
-    };
-    auto bound_lo = [&](int r) -> double {
-      return r == 0 ? P(JMPC_P_MAX_DECEL) : r == 1 ? -P(JMPC_P_MAX_STEER) : r == 2 ? -P(kSlotLim) : P(kSlotLo3);
-    };
+  // ---------------- 5. interior-point solve -------------------------------------------------------
+  // Stage k = lane owns four two-sided rows: r = 0 accel box, 1 steer box, 2 steer rate k -> k+1, 3 speed
+  // (running sum of a up to k).  Only slacks and multipliers stay in registers across the factorisation;
+  // bounds are rebuilt from the parameter block when needed.
+  double sh[4], sl[4], lh[4], ll[4];
+  const bool live013 = gl < T, live2 = gl < T - 1;
+  auto is_live = [&](int r) -> bool { return r == 2 ? live2 : live013; };
+  auto bound_hi = [&](int r) -> double {
+    return r == 0 ? P(JMPC_P_MAX_ACCEL) : r == 1 ? P(JMPC_P_MAX_STEER) : r == 2 ? P(kSlotLim) : P(kSlotHi3);
+  };
+  auto bound_lo = [&](int r) -> double {
+    return r == 0 ? P(JMPC_P_MAX_DECEL) : r == 1 ? -P(JMPC_P_MAX_STEER) : r == 2 ? -P(kSlotLim) : P(kSlotLo3);
+  };
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      sh[r] = fmax(bound_hi(r), 1e-2); sl[r] = fmax(-bound_lo(r), 1e-2);      // u = 0 -> A u = 0
-      if (A.init_mu > 0.0) { lh[r] = is_live(r) ? A.init_mu / sh[r] : 0.0; ll[r] = is_live(r) ? A.init_mu / sl[r] : 0.0; }
-      else { lh[r] = is_live(r) ? 1.0 : 0.0; ll[r] = lh[r]; }
-    }
-    const double inv_rows = 1.0 / (double)(2 * (4 * T - 1));
-    double gscale = 0.0;
-    if (lane < T) gscale = fmax(fabs(M.q[lane]), fabs(M.q[T + lane]));
-    gscale = 1.0 + warp_max(gscale);
-    const int ntd = tiles_doubles(n);
-    bool converged = false;
-    bool acceptable = false;          // last evaluated iterate meets the reduced tolerances (see below)
+  for (int r = 0; r < 4; ++r) {
+    sh[r] = fmax(bound_hi(r), 1e-2); sl[r] = fmax(-bound_lo(r), 1e-2);      // u = 0 -> A u = 0
+    if (A.init_mu > 0.0) { lh[r] = is_live(r) ? A.init_mu / sh[r] : 0.0; ll[r] = is_live(r) ? A.init_mu / sl[r] : 0.0; }
+    else { lh[r] = is_live(r) ? 1.0 : 0.0; ll[r] = lh[r]; }
+  }
+  const double inv_rows = 1.0 / (double)(2 * (4 * T - 1));
+  double gscale = 0.0;
+  if (gl < T) gscale = fmax(fabs(M.q[gl]), fabs(M.q[T + gl]));
+  gscale = 1.0 + grp_max<G>(gscale, gm);
+  const int ntd = tiles_doubles(n);
+  bool converged = false;
+  bool acceptable = false;          // last evaluated iterate meets the reduced tolerances (see below)
+  bool done = !active;              // this group's solve is over (its state is frozen from then on)
+  int my_iters = 0;
 #ifdef JMPC_DEBUG_RESID
-    double dbg_mu = 0, dbg_rp = 0, dbg_rd = 0;
+  double dbg_mu = 0, dbg_rp = 0, dbg_rd = 0;
 #endif
-    int it = 0;
-    // P -> shared with one TMA bulk copy per iteration (the scratch copy is L2 resident).  The copy for iteration
-    // it + 1 is issued as soon as the corrector's triangular solves have read the factor for the last time, so it
-    // runs under the direction recovery, the step and the next iteration's row work.  Every exit of the loop lies
-    // behind the wait for the copy in flight (and none is issued for an iteration that will not run), so the
-    // barrier's phase stays in step and nothing lands in K after the solver has left.  The last reads of K are
-    // behind a __syncwarp; the fence inside tma_load_1d orders them (generic proxy) before the copy (async proxy).
-    if (lane == 0 && A.max_iters > 0) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
-    for (it = 0; it < A.max_iters; ++it) {
-      JMPC_TICK(ts_);
-      // The primal row residuals rph / rpl are needed again in both direction phases.  They are parked in shared memory
-      // (the rhs / grad / prefix-sum arrays are dead during the solve) instead of being held across the factorisation
-      // and the triangular solves: with them in registers the compiler spilled 0.5 KB per thread to local memory,
-      // which misses the small L1 left beside 222 KB of shared memory and waits on L2.
-      double* stash = M.grad;                         // [8][T]: rph[0..3], rpl[0..3] of stage = lane
-      double z[4], ish[4], isl[4], t4[4];
-      rows_apply(M.u, T, lane, z);
-      double mu = 0.0, rpmax = 0.0;
-      double w2, w3;
-      {
-        double w[4];
+  int it = 0;
+  // P -> shared with one TMA bulk copy per iteration (the scratch copy is L2 resident).  The copy for iteration
+  // it + 1 is issued as soon as the corrector's triangular solves have read the factor for the last time, so it
+  // runs under the direction recovery, the step and the next iteration's row work.  Every exit of the loop lies
+  // behind the wait for the copy in flight (and none is issued for an iteration that will not run), so the
+  // barrier's phase stays in step and nothing lands in K after the solver has left.  The last reads of K are
+  // behind a group __syncwarp; the fence inside tma_load_1d orders them (generic proxy) before the copy (async proxy).
+  if (gl == 0 && A.max_iters > 0) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
+  for (it = 0; it < A.max_iters; ++it) {
+    JMPC_TICK(ts_);
+    // The primal row residuals rph / rpl are needed again in both direction phases.  They are parked in shared memory
+    // (the rhs / grad / prefix-sum arrays are dead during the solve) instead of being held across the factorisation
+    // and the triangular solves: with them in registers the compiler spilled 0.5 KB per thread to local memory,
+    // which misses the small L1 left beside 222 KB of shared memory and waits on L2.
+    double* stash = M.grad;                         // [8][T]: rph[0..3], rpl[0..3] of stage = lane
+    double z[4], ish[4], isl[4], t4[4];
+    rows_apply<G>(M.u, T, gl, gm, z);
+    double mu = 0.0, rpmax = 0.0;
+    double w2, w3;
+    {
+      double w[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const bool lv = is_live(r);
-          ish[r] = rcp_pos(sh[r]); isl[r] = rcp_pos(sl[r]);
-          const double rph_r = lv ? (z[r] + sh[r] - bound_hi(r)) : 0.0;
-          const double rpl_r = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
-          if (lane < T) { stash[r * T + lane] = rph_r; stash[(4 + r) * T + lane] = rpl_r; }
-          // predictor (affine) complementarity target rc = lambda s:  (lambda rp - rc) / s = lambda (rp - s) / s
-          t4[r] = lv ? (fma(lh[r], rph_r, -lh[r] * sh[r]) * ish[r] - fma(ll[r], rpl_r, -ll[r] * sl[r]) * isl[r]) : 0.0;
-          w[r] = lv ? fma(lh[r], ish[r], ll[r] * isl[r]) : 0.0;
-          mu += lh[r] * sh[r] + ll[r] * sl[r];
-          rpmax = fmax(rpmax, fmax(fabs(rph_r), fabs(rpl_r)));
-        }
-        w2 = w[2]; w3 = w[3];
-        double wup = __shfl_up_sync(kFull, w2, 1);
-        if (lane == 0) wup = 0.0;
-        const double sw = warp_rscan(w3, lane);
-        if (lane < T) { M.wA[lane] = w[0]; M.wD[lane] = w[1] + w2 + wup; M.wR[lane] = w2; M.SW[lane] = sw; }
+      for (int r = 0; r < 4; ++r) {
+        const bool lv = is_live(r);
+        ish[r] = rcp_pos(sh[r]); isl[r] = rcp_pos(sl[r]);
+        const double rph_r = lv ? (z[r] + sh[r] - bound_hi(r)) : 0.0;
+        const double rpl_r = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
+        if (gl < T) { stash[r * T + gl] = rph_r; stash[(4 + r) * T + gl] = rpl_r; }
+        // predictor (affine) complementarity target rc = lambda s:  (lambda rp - rc) / s = lambda (rp - s) / s
+        t4[r] = lv ? (fma(lh[r], rph_r, -lh[r] * sh[r]) * ish[r] - fma(ll[r], rpl_r, -ll[r] * sl[r]) * isl[r]) : 0.0;
+        w[r] = lv ? fma(lh[r], ish[r], ll[r] * isl[r]) : 0.0;
+        mu += lh[r] * sh[r] + ll[r] * sl[r];
+        rpmax = fmax(rpmax, fmax(fabs(rph_r), fabs(rpl_r)));
       }
-      mu = warp_sum(mu) * inv_rows;
-      rpmax = warp_max(rpmax);
-      double ra_p, rd_p;                              // A' (predictor row terms)
-      rows_apply_T(t4, lane, ra_p, rd_p);
-      // P u is formed from the clean Hessian: folding the barrier weights in first and subtracting them again
-      // would cancel catastrophically once w ~ 1e12
-      JMPC_TOCK(ts_, 0);
-      mbar_wait(M.mbar, tma_parity);
-      tma_parity ^= 1u;
-      __syncwarp();
-      JMPC_TOCK(ts_, 1);
-      double pu0, pu1;                              // rows lane and T + lane of P u
-      symv_rows<(TT > 0) ? ((2 * TT + 3) >> 2) : 0>(M.K, M.u, T, nb, lane, pu0, pu1);
+      w2 = w[2]; w3 = w[3];
+      double wup = __shfl_up_sync(gm, w2, 1, G);
+      if (gl == 0) wup = 0.0;
+      const double sw = grp_rscan<G>(w3, gl, gm);
+      if (gl < T) { M.wA[gl] = w[0]; M.wD[gl] = w[1] + w2 + wup; M.wR[gl] = w2; M.SW[gl] = sw; }
+    }
+    mu = grp_sum<G>(mu, gm) * inv_rows;
+    rpmax = grp_max<G>(rpmax, gm);
+    double ra_p, rd_p;                              // A' (predictor row terms)
+    rows_apply_T<G>(t4, gl, gm, ra_p, rd_p);
+    // P u is formed from the clean Hessian: folding the barrier weights in first and subtracting them again
+    // would cancel catastrophically once w ~ 1e12
+    JMPC_TOCK(ts_, 0);
+    mbar_wait(M.mbar, tma_parity);
+    tma_parity ^= 1u;
+    __syncwarp(gm);
+    JMPC_TOCK(ts_, 1);
+    double pu0, pu1;                              // rows gl and T + gl of P u
+    symv_rows<(TT > 0) ? ((2 * TT + 3) >> 2) : 0>(M.K, M.u, T, nb, gl, pu0, pu1);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) t4[r] = is_live(r) ? (lh[r] - ll[r]) : 0.0;
-      double ra, rd;
-      rows_apply_T(t4, lane, ra, rd);
-      // gradient of the Lagrangian (dual residual), kept in registers: g0 for a_lane, g1 for delta_lane
-      const double g0 = (lane < T) ? pu0 + M.q[lane] + ra : 0.0, g1 = (lane < T) ? pu1 + M.q[T + lane] + rd : 0.0;
-      __syncwarp();                                 // every lane is done reading P before K is assembled in place
-      JMPC_TOCK(ts_, 2);
-      // K = P + A' diag(w) A: only the accel block and the steer tridiagonal change
-      {
-        // accel x accel block: + SW[max(i, j)] (+ wA on the diagonal), done by half tiles; the task table of the
-        // Cholesky update for m = ceil(T / 4) block rows enumerates exactly these tiles
-        const int ma = (T + 3) >> 2, ntasks = ma * (ma + 1);
-        const unsigned short* tasks = lut + chol_lut_offset(ma);
-        for (int q = lane; q < ntasks; q += 32) {
-          const unsigned e = tasks[q];
-          const int I = (int)(e & 15u), Jc = (int)((e >> 4) & 15u), h = (int)((e >> 8) & 1u) << 1;
-          double* tile = M.K + tile_off(I, Jc) + 4 * h;
+    for (int r = 0; r < 4; ++r) t4[r] = is_live(r) ? (lh[r] - ll[r]) : 0.0;
+    double ra, rd;
+    rows_apply_T<G>(t4, gl, gm, ra, rd);
+    // gradient of the Lagrangian (dual residual), kept in registers: g0 for a_gl, g1 for delta_gl
+    const double g0 = (gl < T) ? pu0 + M.q[gl] + ra : 0.0, g1 = (gl < T) ? pu1 + M.q[T + gl] + rd : 0.0;
+    __syncwarp(gm);                               // every lane is done reading P before K is assembled in place
+    JMPC_TOCK(ts_, 2);
+    // K = P + A' diag(w) A: only the accel block and the steer tridiagonal change
+    {
+      // accel x accel block: + SW[max(i, j)] (+ wA on the diagonal), done by half tiles; the task table of the
+      // Cholesky update for m = ceil(T / 4) block rows enumerates exactly these tiles
+      const int ma = (T + 3) >> 2, ntasks = ma * (ma + 1);
+      const unsigned short* tasks = lut + chol_lut_offset(ma);
+      for (int q = gl; q < ntasks; q += G) {
+        const unsigned e = tasks[q];
+        const int I = (int)(e & 15u), Jc = (int)((e >> 4) & 15u), h = (int)((e >> 8) & 1u) << 1;
+        double* tile = M.K + tile_off(I, Jc) + 4 * h;
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const int i = (I << 2) + h + r, j0 = Jc << 2;
-            if (i < T) {
-              const double sw = M.SW[i], wa = M.wA[i];
-              double c0, c1, c2, c3;
-              ld4(tile + 4 * r, c0, c1, c2, c3);
-              c0 += (j0 <= i) ? sw + ((j0 == i) ? wa : 0.0) : 0.0;
-              c1 += (j0 + 1 <= i) ? sw + ((j0 + 1 == i) ? wa : 0.0) : 0.0;
-              c2 += (j0 + 2 <= i) ? sw + ((j0 + 2 == i) ? wa : 0.0) : 0.0;
-              c3 += (j0 + 3 <= i) ? sw + ((j0 + 3 == i) ? wa : 0.0) : 0.0;
-              st4(tile + 4 * r, c0, c1, c2, c3);
-            }
+        for (int r = 0; r < 2; ++r) {
+          const int i = (I << 2) + h + r, j0 = Jc << 2;
+          if (i < T) {
+            const double sw = M.SW[i], wa = M.wA[i];
+            double c0, c1, c2, c3;
+            ld4(tile + 4 * r, c0, c1, c2, c3);
+            c0 += (j0 <= i) ? sw + ((j0 == i) ? wa : 0.0) : 0.0;
+            c1 += (j0 + 1 <= i) ? sw + ((j0 + 1 == i) ? wa : 0.0) : 0.0;
+            c2 += (j0 + 2 <= i) ? sw + ((j0 + 2 == i) ? wa : 0.0) : 0.0;
+            c3 += (j0 + 3 <= i) ? sw + ((j0 + 3 == i) ? wa : 0.0) : 0.0;
+            st4(tile + 4 * r, c0, c1, c2, c3);
           }
         }
       }
-      if (lane < T) {
-        const int i = T + lane;
-        M.K[elem_off(i, i)] += M.wD[lane];
-        if (lane >= 1) M.K[elem_off(i, i - 1)] -= M.wR[lane - 1];
-      }
-      double rdmax = fmax(fabs(g0), fabs(g1));
-      rdmax = warp_max(rdmax);
-      __syncwarp();
-      if (mu <= A.mu_tol && rpmax <= A.tol_res && rdmax <= A.tol_res * gscale) { converged = true; break; }
+    }
+    if (gl < T) {
+      const int i = T + gl;
+      M.K[elem_off(i, i)] += M.wD[gl];
+      if (gl >= 1) M.K[elem_off(i, i - 1)] -= M.wR[gl - 1];
+    }
+    double rdmax = fmax(fabs(g0), fabs(g1));
+    rdmax = grp_max<G>(rdmax, gm);
+    __syncwarp(gm);
+    if (!done) {
+      if (mu <= A.mu_tol && rpmax <= A.tol_res && rdmax <= A.tol_res * gscale) { converged = true; done = true; }
       // Complementarity three orders below its target with the primal rows satisfied: the iterate has converged;
       // what is left in the dual residual is multiplier noise on the active rows (w ~ 1e16 by now, their slacks are
       // at roundoff), which lies in the span of the active normals and does not move u.  Iterating further only
       // amplifies it.  Measured on 200k instances: controls at such exits are within 1e-8 of the oracle.
-      if (mu <= 1e-3 * A.mu_tol && rpmax <= A.tol_res) { converged = true; break; }
+      else if (mu <= 1e-3 * A.mu_tol && rpmax <= A.tol_res) { converged = true; done = true; }
       // Reduced tolerances, the analogue of the OPTIMAL_INACCURATE status the reference accepts (mpc.py:199): used
       // when the factorisation breaks down numerically a step or two before the strict target (w ~ 1e13 by then),
       // or the iteration cap is hit.  Measured: such iterates are still 5-6x inside the control tolerance.
-      acceptable = (mu <= 1e-9 && rpmax <= 1e-7 && rdmax <= 1e-7 * gscale);
+      else acceptable = (mu <= 1e-9 && rpmax <= 1e-7 && rdmax <= 1e-7 * gscale);
+      if (done) my_iters = it;
 #ifdef JMPC_DEBUG_RESID
       dbg_mu = mu; dbg_rp = rpmax; dbg_rd = rdmax / gscale;
 #endif
-
-      JMPC_TOCK(ts_, 3);
-      // The predictor's right-hand side needs nothing from the factor, so its forward substitution rides along with
-      // the factorisation (one triangular sweep out of four per iteration saved).
-      if (lane < T) { M.rhs[lane] = -g0 - ra_p; M.rhs[T + lane] = -g1 - rd_p; }
-      __syncwarp();
-      const bool clean = chol_tiles(M.K, nb, lane, lut, M.rhs);     // non-positive pivots are replaced, never fatal
-      JMPC_TOCK(ts_, 4);
-      // Numerical breakdown of the factorisation (a pivot lost to roundoff, w ~ 1e13 by then) on an iterate that is
-      // already two orders inside the reduced tolerances: stop here.  The step computed from the patched factor is
-      // usually harmless, but on a few instances in 10^5 (weakly active speed rows, T = 25) it threw the iterate far
-      // enough out that the iteration cap was reached; which instances depended on the build.
-      if (!clean && mu <= 1e-11 && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) { acceptable = true; break; }
-
-      double dsh[4], dsl[4], dlh[4], dll[4];
-      double sigma_mu = 0.0, aff_step = 0.0;
-#pragma unroll 1
-      for (int phase = 0; phase < 2; ++phase) {
-        // complementarity targets: predictor rc = l s ; corrector rc = l s + ds_aff dl_aff - sigma mu
-        double rph[4], rpl[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          rph[r] = (lane < T) ? stash[r * T + lane] : 0.0; rpl[r] = (lane < T) ? stash[(4 + r) * T + lane] : 0.0;
-        }
-        if (phase == 1) {
-          double th[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const double rch = fma(lh[r], sh[r], dsh[r] * dlh[r] - sigma_mu), rcl = fma(ll[r], sl[r], dsl[r] * dll[r] - sigma_mu);
-            const double a_h = fma(lh[r], rph[r], -rch) * ish[r];
-            const double a_l = fma(ll[r], rpl[r], -rcl) * isl[r];
-            th[r] = is_live(r) ? (a_h - a_l) : 0.0;
-            dlh[r] = rch; dll[r] = rcl;               // stash rc for the direction recovery below
-          }
-          rows_apply_T(th, lane, ra, rd);
-          if (lane < T) { M.rhs[lane] = -g0 - ra; M.rhs[T + lane] = -g1 - rd; }
-          __syncwarp();
-          JMPC_TOCK(ts_, 5);
-          solve_forward_tiles(M.K, M.rhs, nb, lane);
-        } else {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) { dlh[r] = lh[r] * sh[r]; dll[r] = ll[r] * sl[r]; }
-          JMPC_TOCK(ts_, 5);
-        }
-        solve_backward_tiles(M.K, M.rhs, nb, lane);
-        __syncwarp();
-        if (phase == 1 && lane == 0 && it + 1 < A.max_iters) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
-        const double du0 = (lane < T) ? M.rhs[lane] : 0.0, du1 = (lane < T) ? M.rhs[T + lane] : 0.0;
-        JMPC_TOCK(ts_, 6);
-        double dz[4];
-        rows_apply_reg(du0, du1, lane, dz);
-        // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l).  The maximum ratio is tracked as a
-        // (numerator, denominator) pair compared by cross-multiplication, so the 16 candidates per lane cost no
-        // division (fp64 division is ~20 instructions); one division remains after the warp reduction.
-        double wn = 0.0, wd = 1.0;
-        auto cand = [&](double num, double den) { if (num * wd > wn * den) { wn = num; wd = den; } };
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const bool lv = is_live(r);
-          const double rch = dlh[r], rcl = dll[r];
-          dsh[r] = lv ? (-rph[r] - dz[r]) : 0.0;
-          dsl[r] = lv ? (-rpl[r] + dz[r]) : 0.0;
-          dlh[r] = lv ? (-(fma(lh[r], dsh[r], rch)) * ish[r]) : 0.0;
-          dll[r] = lv ? (-(fma(ll[r], dsl[r], rcl)) * isl[r]) : 0.0;
-          if (lv) { cand(-dsh[r], sh[r]); cand(-dsl[r], sl[r]); cand(-dlh[r], lh[r]); cand(-dll[r], ll[r]); }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double on = __shfl_xor_sync(kFull, wn, o), od = __shfl_xor_sync(kFull, wd, o);
-          if (on * wd > wn * od) { wn = on; wd = od; }
-        }
-        const double amax = (wn > 0.0) ? wd / wn : INFINITY;
-        if (phase == 0) {
-          const double aa = fmin(1.0, amax);
-          aff_step = aa;
-          double mu_aff = 0.0;
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            mu_aff += fma(aa, dlh[r], lh[r]) * fma(aa, dsh[r], sh[r]) + fma(aa, dll[r], ll[r]) * fma(aa, dsl[r], sl[r]);
-          mu_aff = warp_sum(mu_aff) * inv_rows;
-          const double ratio = mu_aff / mu;
-          sigma_mu = ratio * ratio * ratio * mu;
-        } else {
-          // Fraction to the boundary tied to the length aa of the affine (predictor) step: a long predictor step
-          // means the iterate is well centred and the corrector may go almost to the boundary (0.9999); a short
-          // one keeps the classical 0.99.  Saves ~13 % of the iterations; a rule driven by mu alone (1 - mu) made
-          // a few instances in 10^4 oscillate between a tiny predictor step and a pure centring step.
-          const double alpha = fmin(1.0, fmin(0.9999, fmax(0.99, 1.0 - 0.1 * (1.0 - aff_step) * (1.0 - aff_step))) * amax);
-          if (lane < T) { M.u[lane] = fma(alpha, du0, M.u[lane]); M.u[T + lane] = fma(alpha, du1, M.u[T + lane]); }
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            sh[r] = fma(alpha, dsh[r], sh[r]); sl[r] = fma(alpha, dsl[r], sl[r]);
-            lh[r] = fma(alpha, dlh[r], lh[r]); ll[r] = fma(alpha, dll[r], ll[r]);
-          }
-        }
-        __syncwarp();
-        JMPC_TOCK(ts_, 7);
-      }
     }
+    if (G == 32 ? done : __all_sync(kFull, done)) break;
+
+    JMPC_TOCK(ts_, 3);
+    // The predictor's right-hand side needs nothing from the factor, so its forward substitution rides along with
+    // the factorisation (one triangular sweep out of four per iteration saved).
+    if (gl < T) { M.rhs[gl] = -g0 - ra_p; M.rhs[T + gl] = -g1 - rd_p; }
+    __syncwarp(gm);
+    const bool clean = chol_tiles<G>(M.K, nb, gl, gm, lut, M.rhs);     // non-positive pivots are replaced, never fatal
+    JMPC_TOCK(ts_, 4);
+    // Numerical breakdown of the factorisation (a pivot lost to roundoff, w ~ 1e13 by then) on an iterate that is
+    // already two orders inside the reduced tolerances: stop here.  The step computed from the patched factor is
+    // usually harmless, but on a few instances in 10^5 (weakly active speed rows, T = 25) it threw the iterate far
+    // enough out that the iteration cap was reached; which instances depended on the build.
+    if (!done && !clean && mu <= 1e-11 && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) { acceptable = true; done = true; my_iters = it; }
+    if (G == 32 && done) break;
+
+    double dsh[4], dsl[4], dlh[4], dll[4];
+    double sigma_mu = 0.0, aff_step = 0.0;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      // complementarity targets: predictor rc = l s ; corrector rc = l s + ds_aff dl_aff - sigma mu
+      double rph[4], rpl[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        rph[r] = (gl < T) ? stash[r * T + gl] : 0.0; rpl[r] = (gl < T) ? stash[(4 + r) * T + gl] : 0.0;
+      }
+      if (phase == 1) {
+        double th[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double rch = fma(lh[r], sh[r], dsh[r] * dlh[r] - sigma_mu), rcl = fma(ll[r], sl[r], dsl[r] * dll[r] - sigma_mu);
+          const double a_h = fma(lh[r], rph[r], -rch) * ish[r];
+          const double a_l = fma(ll[r], rpl[r], -rcl) * isl[r];
+          th[r] = is_live(r) ? (a_h - a_l) : 0.0;
+          dlh[r] = rch; dll[r] = rcl;               // stash rc for the direction recovery below
+        }
+        rows_apply_T<G>(th, gl, gm, ra, rd);
+        if (gl < T) { M.rhs[gl] = -g0 - ra; M.rhs[T + gl] = -g1 - rd; }
+        __syncwarp(gm);
+        JMPC_TOCK(ts_, 5);
+        solve_forward_tiles<G>(M.K, M.rhs, nb, gl, gm);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { dlh[r] = lh[r] * sh[r]; dll[r] = ll[r] * sl[r]; }
+        JMPC_TOCK(ts_, 5);
+      }
+      solve_backward_tiles<G>(M.K, M.rhs, nb, gl, gm);
+      __syncwarp(gm);
+      if (phase == 1 && gl == 0 && it + 1 < A.max_iters) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
+      const double du0 = (gl < T) ? M.rhs[gl] : 0.0, du1 = (gl < T) ? M.rhs[T + gl] : 0.0;
+      JMPC_TOCK(ts_, 6);
+      double dz[4];
+      rows_apply_reg<G>(du0, du1, gl, gm, dz);
+      // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l).  The maximum ratio is tracked as a
+      // (numerator, denominator) pair compared by cross-multiplication, so the 16 candidates per lane cost no
+      // division (fp64 division is ~20 instructions); one division remains after the group reduction.
+      double wn = 0.0, wd = 1.0;
+      auto cand = [&](double num, double den) { if (num * wd > wn * den) { wn = num; wd = den; } };
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool lv = is_live(r);
+        const double rch = dlh[r], rcl = dll[r];
+        dsh[r] = lv ? (-rph[r] - dz[r]) : 0.0;
+        dsl[r] = lv ? (-rpl[r] + dz[r]) : 0.0;
+        dlh[r] = lv ? (-(fma(lh[r], dsh[r], rch)) * ish[r]) : 0.0;
+        dll[r] = lv ? (-(fma(ll[r], dsl[r], rcl)) * isl[r]) : 0.0;
+        if (lv) { cand(-dsh[r], sh[r]); cand(-dsl[r], sl[r]); cand(-dlh[r], lh[r]); cand(-dll[r], ll[r]); }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        const double on = __shfl_xor_sync(gm, wn, o), od = __shfl_xor_sync(gm, wd, o);
+        if (on * wd > wn * od) { wn = on; wd = od; }
+      }
+      const double amax = (wn > 0.0) ? wd / wn : INFINITY;
+      if (phase == 0) {
+        const double aa = fmin(1.0, amax);
+        aff_step = aa;
+        double mu_aff = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          mu_aff += fma(aa, dlh[r], lh[r]) * fma(aa, dsh[r], sh[r]) + fma(aa, dll[r], ll[r]) * fma(aa, dsl[r], sl[r]);
+        mu_aff = grp_sum<G>(mu_aff, gm) * inv_rows;
+        const double ratio = mu_aff / mu;
+        sigma_mu = ratio * ratio * ratio * mu;
+      } else if (!done) {
+        // Fraction to the boundary tied to the length aa of the affine (predictor) step: a long predictor step
+        // means the iterate is well centred and the corrector may go almost to the boundary (0.9999); a short
+        // one keeps the classical 0.99.  Saves ~13 % of the iterations; a rule driven by mu alone (1 - mu) made
+        // a few instances in 10^4 oscillate between a tiny predictor step and a pure centring step.
+        const double alpha = fmin(1.0, fmin(0.9999, fmax(0.99, 1.0 - 0.1 * (1.0 - aff_step) * (1.0 - aff_step))) * amax);
+        if (gl < T) { M.u[gl] = fma(alpha, du0, M.u[gl]); M.u[T + gl] = fma(alpha, du1, M.u[T + gl]); }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          sh[r] = fma(alpha, dsh[r], sh[r]); sl[r] = fma(alpha, dsl[r], sl[r]);
+          lh[r] = fma(alpha, dlh[r], lh[r]); ll[r] = fma(alpha, dll[r], ll[r]);
+        }
+      }
+      __syncwarp(gm);
+      JMPC_TOCK(ts_, 7);
+    }
+  }
+  if (!done) my_iters = it;
 #ifdef JMPC_DEBUG_RESID
-    if (lane == 0) { M.prm[29] = dbg_mu; M.prm[30] = dbg_rp; M.prm[31] = dbg_rd; }
-    __syncwarp();
+  if (gl == 0) { M.prm[29] = dbg_mu; M.prm[30] = dbg_rp; M.prm[31] = dbg_rd; }
+  __syncwarp(gm);
 #endif
-    converged_out = converged || acceptable;
-    return it;
+  converged_out = converged || acceptable;
+  return my_iters;
 }
 
 // ---- phase C: states of the linearised model for the solution, objective, outputs ---------------------------
-template <int TT>
-__device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_base, int lane, bool last, int status,
-                                         int target, int idx, unsigned end_mask, int total_iters, double& oa_k,
-                                         double& od_k, double& ov_k) {
+// Returns true when the group's results have been written (last linearisation pass, DU_TH exit, or failed solve).
+template <int TT, int G>
+__device__ __noinline__ bool step_output(const StepArgs& A, int b, bool active, double* smem_base, int gl, unsigned gm,
+                                         bool last, bool solved, int target, int idx, unsigned end_mask,
+                                         int total_iters, double& oa_k, double& od_k, double& ov_k) {
   const int T = (TT > 0) ? TT : A.T;
   const int T1 = T + 1;
   WarpMem M(smem_base, T);
@@ -803,103 +846,144 @@ __device__ __noinline__ void step_output(const StepArgs& A, int b, double* smem_
   const double x0 = A.state[(size_t)b * 4 + 0], y0 = A.state[(size_t)b * 4 + 1];
   const double v0 = A.state[(size_t)b * 4 + 2], yaw0 = A.state[(size_t)b * 4 + 3];
   const double dt = P(JMPC_P_DT), Lw = P(JMPC_P_L);
-  // per-lane data of phase A, re-read instead of being held in registers across the solve
+  // per-lane data of phase A, re-read or recomputed instead of being held in registers across the solve
   const int cid = A.course_id ? A.course_id[b] : 0;
-  double xr = 0.0, yr = 0.0, psir = 0.0, vr = 0.0, vb = 0.0, th = 0.0, w11 = 0.0, w12 = 0.0, w22 = 0.0, wv = 0.0, wpsi = 0.0;
-  if (lane <= T) {
+  double xr = 0.0, yr = 0.0, psir = 0.0, vr = 0.0, vb = 0.0, th = 0.0;
+  if (gl <= T) {
     const size_t off = (size_t)cid * A.course_stride + idx;
     xr = A.cx[off]; yr = A.cy[off]; psir = A.cyaw[off];
-    vr = ((double)idx < P(JMPC_P_V_REF_CUT)) ? P(JMPC_P_V_REF) : 0.0;
-    vb = M.vb[lane]; th = M.th[lane];
-    w11 = M.W11[lane]; w12 = M.W12[lane]; w22 = M.W22[lane]; wv = M.qv[lane]; wpsi = M.qpsi[lane];
+    vr = ref_speed(A, M.prm, cid, idx);
+    vb = M.vb[gl]; th = M.th[gl];
+  }
+  if (!solved) {
+    // The solver hit its iteration cap without meeting even the reduced tolerances: a failed solve, as when the
+    // reference's solver status is neither OPTIMAL nor OPTIMAL_INACCURATE (mpc.py:199-209): no controls are
+    // reported (the in-out arrays keep their values), xref / target are, and the record brakes with MAX_DECEL.
+    if (active) {
+      carry_inout(A, b, T, gl);
+      if (gl <= T) {
+        double* xo = A.xref + (size_t)b * 4 * T1;
+        xo[gl] = xr; xo[T1 + gl] = yr; xo[2 * T1 + gl] = vr; xo[3 * T1 + gl] = psir;
+      }
+      if (gl == 0) {
+        A.status[b] = JMPC_MAX_ITER; A.target_out[b] = target; if (A.iters) A.iters[b] = total_iters;
+        if (A.work_hint) A.work_hint[b] = total_iters;
+        A.cost[b] = nan("");
+        write_record(A, b, nan(""), P(JMPC_P_MAX_DECEL), nan(""), JMPC_MAX_ITER, target, total_iters, nan(""), nan(""));
+      }
+    }
+    return true;
   }
   double sn, cs;
   sincos(th, &sn, &cs);
   double al = 0.0, be = 0.0, ga = 0.0, ka = 0.0, gk = 0.0;
-  if (lane < T) { al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw; }
+  if (gl < T) { al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw; }
+  // ---------------- 6. states of the linearised model for the solution ---------------------------
+  const double a_sol = (gl < T) ? M.u[gl] : 0.0, d_sol = (gl < T) ? M.u[T + gl] : 0.0;
+  const double v_t = v0 + dt * (grp_scan<G>(a_sol, gl, gm) - a_sol);                  // lane t: v_t
+  const double gd = gk * d_sol;
+  const double psi_t = yaw0 + (grp_scan<G>(gd, gl, gm) - gd);
+  const double tx = (gl < T) ? (al * v_t - be * (psi_t - th)) : 0.0;
+  const double ty = (gl < T) ? (ga * v_t + ka * (psi_t - th)) : 0.0;
+  const double X_t = x0 + (grp_scan<G>(tx, gl, gm) - tx);
+  const double Y_t = y0 + (grp_scan<G>(ty, gl, gm) - ty);
+
+  if (!last && A.du_th > 0.0) {
+    // the exit the reference left commented out (mpc.py:236-240): du = sum|oa - poa| + sum|od - pod| <= DU_TH
+    const double du = grp_sum<G>((gl < T) ? fabs(a_sol - oa_k) + fabs(d_sol - od_k) : 0.0, gm);
+    last = du <= A.du_th;
+  }
+  if (!last) {
+    // feed the solution back as the next linearisation point (mpc.py:231-236)
+    oa_k = a_sol; od_k = d_sol; ov_k = v_t;
+    return false;
+  }
+  // objective value, evaluated term by term as mpc.py:159-187 writes it
   const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
   const double Rea = P(JMPC_P_REND_A), Red = P(JMPC_P_REND_D);
-  {
-    // ---------------- 6. states of the linearised model for the solution ---------------------------
-    const double a_sol = (lane < T) ? M.u[lane] : 0.0, d_sol = (lane < T) ? M.u[T + lane] : 0.0;
-    const double v_t = v0 + dt * (warp_scan(a_sol, lane) - a_sol);                  // lane t: v_t
-    const double gd = gk * d_sol;
-    const double psi_t = yaw0 + (warp_scan(gd, lane) - gd);
-    const double tx = (lane < T) ? (al * v_t - be * (psi_t - th)) : 0.0;
-    const double ty = (lane < T) ? (ga * v_t + ka * (psi_t - th)) : 0.0;
-    const double X_t = x0 + (warp_scan(tx, lane) - tx);
-    const double Y_t = y0 + (warp_scan(ty, lane) - ty);
-
-    if (last) {
-      // objective value, evaluated term by term as mpc.py:159-187 writes it
-      double cterm = 0.0;
-      if (lane >= 1 && lane <= T) {
-        const double dx = xr - X_t, dy = yr - Y_t, dv = vr - v_t, dp = psir - psi_t;
-        cterm = dx * (w11 * dx + w12 * dy) + dy * (w12 * dx + w22 * dy) + wv * dv * dv + wpsi * dp * dp;
-      }
-      if (lane < T) {
-        const bool e_t = (end_mask >> lane) & 1u;
-        cterm += (e_t ? Rea : Ra) * a_sol * a_sol + (e_t ? Red : Rd_) * d_sol * d_sol;
-      }
-      const double a_next = __shfl_down_sync(kFull, a_sol, 1), d_next = __shfl_down_sync(kFull, d_sol, 1);
-      if (lane < T - 1) cterm += Rda * (a_next - a_sol) * (a_next - a_sol) + Rdd * (d_next - d_sol) * (d_next - d_sol);
-      const double cost = warp_sum(cterm);
-      if (lane < T) { A.oa_out[(size_t)b * T + lane] = a_sol; A.od_out[(size_t)b * T + lane] = d_sol; }
-      if (lane <= T) {
-        A.ox[(size_t)b * T1 + lane] = X_t; A.oy[(size_t)b * T1 + lane] = Y_t;
-        A.ov[(size_t)b * T1 + lane] = v_t; A.oyaw[(size_t)b * T1 + lane] = psi_t;
-        double* xo = A.xref + (size_t)b * 4 * T1;
-        xo[lane] = xr; xo[T1 + lane] = yr; xo[2 * T1 + lane] = vr; xo[3 * T1 + lane] = psir;
-      }
-      const double v1 = __shfl_sync(kFull, v_t, 1), yaw1 = __shfl_sync(kFull, psi_t, 1);
-      if (lane == 0) {
-        A.cost[b] = cost; A.status[b] = status; A.target_out[b] = target;
-        if (A.iters) A.iters[b] = total_iters;
-        if (A.work_hint) A.work_hint[b] = total_iters;
-#ifdef JMPC_DEBUG_RESID
-        write_record(A, b, M.prm[29], a_sol, cost, status, target, total_iters, M.prm[30], M.prm[31]);
-#else
-        write_record(A, b, d_sol, a_sol, cost, status, target, total_iters, v1, yaw1);
-#endif
-      }
+  double cterm = 0.0;
+  if (gl >= 1 && gl <= T) {
+    double w11, w12 = 0.0, w22, wv, wpsi;             // stage weights, recomputed as in step_prep
+    if ((end_mask >> gl) & 1u) {
+      w11 = P(JMPC_P_QF_X); w22 = P(JMPC_P_QF_Y); wv = P(JMPC_P_QF_V); wpsi = P(JMPC_P_QF_YAW);
     } else {
-      // feed the solution back as the next linearisation point (mpc.py:231-236)
-      oa_k = a_sol; od_k = d_sol; ov_k = v_t;
+      double s1, c1, s2, c2;
+      sincos(psir + 0.5 * M_PI, &s1, &c1);
+      sincos(psir, &s2, &c2);
+      const double wp = P(JMPC_P_W_PERP), wl = P(JMPC_P_W_PARA);
+      w11 = (c1 * c1) * wp + (c2 * c2) * wl;
+      w12 = (c1 * s1) * wp + (c2 * s2) * wl;
+      w22 = (s1 * s1) * wp + (s2 * s2) * wl;
+      wv = P(JMPC_P_Q_V); wpsi = P(JMPC_P_Q_YAW);
+    }
+    const double dx = xr - X_t, dy = yr - Y_t, dv = vr - v_t, dp = psir - psi_t;
+    cterm = dx * (w11 * dx + w12 * dy) + dy * (w12 * dx + w22 * dy) + wv * dv * dv + wpsi * dp * dp;
+  }
+  if (gl < T) {
+    const bool e_t = (end_mask >> gl) & 1u;
+    cterm += (e_t ? Rea : Ra) * a_sol * a_sol + (e_t ? Red : Rd_) * d_sol * d_sol;
+  }
+  const double a_next = __shfl_down_sync(gm, a_sol, 1, G), d_next = __shfl_down_sync(gm, d_sol, 1, G);
+  if (gl < T - 1) cterm += Rda * (a_next - a_sol) * (a_next - a_sol) + Rdd * (d_next - d_sol) * (d_next - d_sol);
+  const double cost = grp_sum<G>(cterm, gm);
+  const double v1 = __shfl_sync(gm, v_t, 1, G), yaw1 = __shfl_sync(gm, psi_t, 1, G);
+  if (active) {
+    if (gl < T) { A.oa_out[(size_t)b * T + gl] = a_sol; A.od_out[(size_t)b * T + gl] = d_sol; }
+    if (gl <= T) {
+      A.ox[(size_t)b * T1 + gl] = X_t; A.oy[(size_t)b * T1 + gl] = Y_t;
+      A.ov[(size_t)b * T1 + gl] = v_t; A.oyaw[(size_t)b * T1 + gl] = psi_t;
+      double* xo = A.xref + (size_t)b * 4 * T1;
+      xo[gl] = xr; xo[T1 + gl] = yr; xo[2 * T1 + gl] = vr; xo[3 * T1 + gl] = psir;
+    }
+    if (gl == 0) {
+      A.cost[b] = cost; A.status[b] = JMPC_OPTIMAL; A.target_out[b] = target;
+      if (A.iters) A.iters[b] = total_iters;
+      if (A.work_hint) A.work_hint[b] = total_iters;
+#ifdef JMPC_DEBUG_RESID
+      write_record(A, b, M.prm[29], a_sol, cost, JMPC_OPTIMAL, target, total_iters, M.prm[30], M.prm[31]);
+#else
+      write_record(A, b, d_sol, a_sol, cost, JMPC_OPTIMAL, target, total_iters, v1, yaw1);
+#endif
     }
   }
+  return true;
 }
 
-// The fused step for one instance, executed by one warp.  TT > 0 fixes the horizon at compile time (every
-// shared-memory offset and tile count becomes an immediate); TT == 0 is the generic runtime-T version.  The three
-// phases are separate functions so that the solver's register allocation is not burdened by the values the
-// preparation and the epilogue need; they communicate through the warp's shared memory.
-template <int TT>
-__device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, double* smem_base, double* pscr, int lane,
-                                                  unsigned& tma_parity, const unsigned short* lut) {
+// The fused step for the instances of one warp (one per lane group).  TT > 0 fixes the horizon at compile time
+// (every shared-memory offset and tile count becomes an immediate); TT == 0 is the generic runtime-T version.  The
+// three phases are separate functions so that the solver's register allocation is not burdened by the values the
+// preparation and the epilogue need; they communicate through the group's shared memory.
+template <int TT, int G>
+__device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, bool active, double* smem_base, double* pscr,
+                                                  int gl, unsigned gm, unsigned& tma_parity, const unsigned short* lut) {
   const int T = (TT > 0) ? TT : A.T;
   WarpMem M(smem_base, T);
   // the instance's parameter vector lives in shared memory (uniform reads, no registers held across phases)
-  if (lane < JMPC_NPARAM) M.prm[lane] = A.params ? A.params[(size_t)b * JMPC_NPARAM + lane] : A.defaults[lane];
-  __syncwarp();
+  for (int k = gl; k < JMPC_NPARAM; k += G) M.prm[k] = A.params ? A.params[(size_t)b * JMPC_NPARAM + k] : A.defaults[k];
+  __syncwarp(gm);
   // warm start = linearisation point (mpc.py:225-227: None -> zeros)
   const bool use_warm = A.warm ? (A.warm[b] != 0) : true;
   double oa_k = 0.0, od_k = 0.0, ov_k = 0.0;       // ov: |ov| feedback for lin_iters > 1 (lane k <-> horizon point k)
-  if (use_warm && lane < T) { oa_k = A.oa[(size_t)b * T + lane]; od_k = A.od[(size_t)b * T + lane]; }
+  if (use_warm && gl < T) { oa_k = A.oa[(size_t)b * T + gl]; od_k = A.od[(size_t)b * T + gl]; }
   int target = A.target_ind[b];
   int total_iters = 0;
   for (int lin = 0; lin < A.lin_iters; ++lin) {
     int idx = 0; unsigned end_mask = 0;
     JMPC_TICK(ti_);
-    const int st = step_prep<TT>(A, b, smem_base, pscr, lane, lin, total_iters, oa_k, od_k, ov_k, target, idx, end_mask);
-    if (st != JMPC_OPTIMAL) return;
+    const int st = step_prep<TT, G>(A, b, active, smem_base, pscr, gl, gm, lin, total_iters, oa_k, od_k, ov_k, target,
+                                    idx, end_mask);
+    if (st != JMPC_OPTIMAL) active = false;        // reported by step_prep; the group idles through the rest
+    if (G == 32 ? !active : !__any_sync(kFull, active)) return;
     JMPC_TOCK(ti_, 10);
     bool converged = false;
-    total_iters += step_solve<TT>(A, smem_base, pscr, lane, converged, tma_parity, lut);
+    total_iters += step_solve<TT, G>(A, active, smem_base, pscr, gl, gm, converged, tma_parity, lut);
     JMPC_TOCK(ti_, 11);
-    step_output<TT>(A, b, smem_base, lane, lin == A.lin_iters - 1, converged ? JMPC_OPTIMAL : JMPC_MAX_ITER, target, idx,
-                    end_mask, total_iters, oa_k, od_k, ov_k);
+    const bool finished = step_output<TT, G>(A, b, active, smem_base, gl, gm, lin == A.lin_iters - 1, converged, target,
+                                             idx, end_mask, total_iters, oa_k, od_k, ov_k);
+    if (finished) active = false;
     JMPC_TOCK(ti_, 12);
-    __syncwarp();
+    __syncwarp(gm);
+    if (G == 32 ? !active : !__any_sync(kFull, active)) return;
   }
 }
 
@@ -949,7 +1033,7 @@ __global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int*
   for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&start[key_of(b)], 1)] = b;
 }
 
-// Persistent kernel: every resident warp pulls instances from a global counter.
+// Persistent kernel: every resident warp pulls instances (one per lane group) from a global counter.
 #ifndef JMPC_MINBLOCKS
 #define JMPC_MINBLOCKS 4
 #endif
@@ -959,35 +1043,44 @@ __global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int*
 // resident blocks per SM the register budget is set for: short horizons leave shared memory for more warps, and at
 // T = 8 the extra warps pay for the tighter register budget (80 registers, 24 warps: +5 %; at T = 13 / 20 / 25 they do not)
 constexpr int step_min_blocks(int TT) { return TT == 8 ? (JMPC_MINBLOCKS * 3) / 2 : JMPC_MINBLOCKS; }
-template <int TT>
+template <int TT, int G>
 __global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_kernel(
     const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int NG = 32 / G;                       // instances per warp
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gl = lane & (G - 1), sub = lane / G;
+  const unsigned gm = group_mask<G>(lane);
   const int warps_per_block = blockDim.x >> 5;
   const int T = (TT > 0) ? TT : A.T;
-  double* base = smem + (size_t)wib * warp_smem_doubles(T);
-  const int gw = blockIdx.x * warps_per_block + wib;
+  double* base = smem + (size_t)(wib * NG + sub) * inst_smem_doubles(T);
+  const int gg = (blockIdx.x * warps_per_block + wib) * NG + sub;      // resident-group index
   const int n = 2 * T;
-  double* pscr = A.pscratch + (size_t)gw * tiles_doubles(n);
+  double* pscr = A.pscratch + (size_t)gg * tiles_doubles(n);
   unsigned tma_parity = 0;
   {
     WarpMem M0(base, T);
-    if (lane == 0) mbar_init(M0.mbar, 1);
+    if (gl == 0) mbar_init(M0.mbar, 1);
     __syncwarp();
   }
-  // block-shared task table of the Cholesky trailing update, behind the warps' regions
-  unsigned short* lut = reinterpret_cast<unsigned short*>(smem + (size_t)warps_per_block * warp_smem_doubles(T));
+  // block-shared task table of the Cholesky trailing update, behind the instances' regions
+  unsigned short* lut = reinterpret_cast<unsigned short*>(smem + (size_t)warps_per_block * NG * inst_smem_doubles(T));
   chol_lut_build(lut, nblk(n) + 1, threadIdx.x, blockDim.x);     // one more block row than the factorisation needs: the K assembly uses m = ceil(T / 4) <= nb
   __syncthreads();
   for (;;) {
-    unsigned b = 0;
-    if (lane == 0) b = atomicAdd(A.counter, 1u);
-    b = __shfl_sync(kFull, b, 0);
-    if (b >= (unsigned)A.B) break;
+    // the warp takes NG consecutive tickets: with the longest-first order neighbours in the queue have similar
+    // keys, so the instances that share a warp tend to need a similar number of iterations
+    unsigned t0 = 0;
+    if (lane == 0) t0 = atomicAdd(A.counter, (unsigned)NG);
+    t0 = __shfl_sync(kFull, t0, 0);
+    if (t0 >= (unsigned)A.B) break;
+    const unsigned ticket = t0 + (unsigned)sub;
+    bool active = ticket < (unsigned)A.B;
+    unsigned b = active ? ticket : t0;             // a group without a ticket idles on the warp's first instance (reads only)
     if (A.order) b = (unsigned)A.order[b];
-    if (A.skip && A.skip[b] != 0) continue;
-    mpc_step_instance<TT>(A, (int)b, base, pscr, lane, tma_parity, lut);
+    if (A.skip && A.skip[b] != 0) active = false;
+    if (!__any_sync(kFull, active)) continue;
+    mpc_step_instance<TT, G>(A, (int)b, active, base, pscr, gl, gm, tma_parity, lut);
     __syncwarp();
   }
 }

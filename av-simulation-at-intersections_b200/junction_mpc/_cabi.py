@@ -7,6 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JMPC_LIB", os.path.join(_HERE, "libjmpc.so"))
 
+ABI_VERSION = 2
 JMPC_MAX_T = 31
 RECORD_LEN = 8
 STATUS_OPTIMAL, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_INDEX_RULE = 0, 1, 2, 3
@@ -17,7 +18,7 @@ c_f64p = C.POINTER(C.c_double)
 
 class Options(C.Structure):
     _fields_ = [("max_solver_iters", C.c_int32), ("linearisation_iters", C.c_int32), ("mu_tol", C.c_double),
-                ("warps_per_sm", C.c_int32)]
+                ("warps_per_sm", C.c_int32), ("du_th", C.c_double)]
 
 
 # name -> (restype, argtypes); the exported-symbol test walks this table against include/jmpc.h
@@ -31,6 +32,7 @@ SIGNATURES = {
     "jmpc_set_default_params": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "jmpc_set_courses": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
+    "jmpc_set_course_speed": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "jmpc_set_car_geometry": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "jmpc_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 17 + [C.c_void_p]),
     "jmpc_debug_cycles": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
@@ -38,6 +40,7 @@ SIGNATURES = {
     "jmpc_reset_schedule_hints": (C.c_int32, [C.c_void_p]),
     "jmpc_set_skip_mask": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "jmpc_set_record_peers": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    "jmpc_set_host_transfer": (C.c_int32, [C.c_void_p, C.c_int32]),
     "jmpc_step_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 17),
     "jmpc_step_host_io": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 20),
     "jmpc_host_alloc": (C.c_int32, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -58,6 +61,8 @@ SIGNATURES = {
     "jmpc_launch_count": (C.c_int64, [C.c_void_p]),
     "jmpc_measure_fma_peak": (C.c_int32, [C.c_void_p, c_f64p, c_f64p]),
     "jmpc_debug_linalg": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jmpc_debug_linalg_g": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -80,7 +85,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.jmpc_abi_version() != 1:
+    if lib.jmpc_abi_version() != ABI_VERSION:
         raise JmpcError("libjmpc.so ABI version mismatch")
     _lib = lib
     return lib

@@ -59,8 +59,9 @@ class BatchedMPC:
                  config: Optional[MPCConfig] = None, dt: float = 0.2, L: float = 2.86, speed: float = 30.0 / 3.6,
                  max_batch: int = 1 << 20, device: int = 0, max_solver_iters: int = 40,
                  linearisation_iters: Optional[int] = None, mu_tol: float = 1e-13, warps_per_sm: int = 0,
-                 max_T: Optional[int] = None, schedule: str = "history"):
-        """courses: list of (N_c, >=3) arrays [x, y, yaw(smoothed)]."""
+                 max_T: Optional[int] = None, schedule: str = "history", du_th: float = 0.0):
+        """courses: list of (N_c, >=3) arrays [x, y, yaw(smoothed)].  `du_th` > 0 switches on the early exit of the
+        linearisation loop the reference left commented out (mpc.py:236-240)."""
         self._lib = _cabi.load()
         cfg = config or MPCConfig.default()
         self.T = int(T if T is not None else cfg.T)
@@ -72,7 +73,7 @@ class BatchedMPC:
         lens = [len(c) for c in courses]
         self.max_N = max(lens)
         opt = _cabi.Options(int(max_solver_iters), int(linearisation_iters or cfg.max_iter), float(mu_tol),
-                            int(warps_per_sm))
+                            int(warps_per_sm), float(du_th))
         h = C.c_void_p()
         _cabi.check(self._lib.jmpc_create(self.device, self.max_batch, int(max_T or max(self.T, 25)), self.max_N,
                                           len(courses), _ptr(self.default_params), C.byref(opt), C.byref(h)),
@@ -96,6 +97,31 @@ class BatchedMPC:
         _cabi.check(self._lib.jmpc_set_courses(self._h, len(courses), stride, _ptr(lens), _ptr(tab[0]), _ptr(tab[1]),
                                                _ptr(tab[2])), "jmpc_set_courses")
         self.course_len = lens.copy()
+
+    def set_course_speed(self, speeds: Optional[Sequence[np.ndarray]]):
+        """Reference speed profile per course point (`cv` of main/lib/mpc_with_speed.py:104): one array per uploaded
+        course, or None to go back to the two-level v_ref / v_ref_cut parameters."""
+        if speeds is None:
+            _cabi.check(self._lib.jmpc_set_course_speed(self._h, 0, 0, None), "jmpc_set_course_speed")
+            return
+        if len(speeds) != len(self.course_len):
+            raise ValueError("one speed profile per uploaded course")
+        stride = int(self.course_len.max())
+        tab = np.zeros((len(speeds), stride))
+        for k, v in enumerate(speeds):
+            v = np.asarray(v, dtype=np.float64)
+            if len(v) < self.course_len[k]:
+                raise ValueError("speed profile shorter than its course")
+            tab[k, :self.course_len[k]] = v[:self.course_len[k]]
+        _cabi.check(self._lib.jmpc_set_course_speed(self._h, len(speeds), stride, _ptr(tab)), "jmpc_set_course_speed")
+
+    HOST_TRANSFER = {"staged": 0, "zero_copy_results": 1, "zero_copy": 2}
+
+    def set_host_transfer(self, mode: str):
+        """How `step_host` / `collision_host` move data: "zero_copy_results" (default: inputs by DMA, results stored by
+        the kernel straight into page-locked host memory), "staged" (DMA both ways) or "zero_copy" (inputs read
+        through the mapping as well) -- jmpc_set_host_transfer in include/jmpc.h."""
+        _cabi.check(self._lib.jmpc_set_host_transfer(self._h, self.HOST_TRANSFER[mode]), "jmpc_set_host_transfer")
 
     def set_default_params(self, params: np.ndarray):
         self.default_params = _f64(params, (NPARAM,))
@@ -156,15 +182,19 @@ class BatchedMPC:
         _cabi.check(self._lib.jmpc_measure_fma_peak(self._h, C.byref(a), C.byref(b)), "jmpc_measure_fma_peak")
         return a.value, b.value
 
-    def debug_linalg(self, A, b, x, full: bool = False):
-        """Building-block self-test: returns (A^{-1} b, A x, ok) computed by the tiled warp routines."""
+    def debug_linalg(self, A, b, x, full: bool = False, group_lanes: int = 32, which: int = 0):
+        """Building-block self-test: returns (A^{-1} b, A x, ok) computed by the tiled routines on one lane group
+        (`group_lanes` = 32: a warp; 16: half `which` of a warp whose two halves both run the problem)."""
         A = _f64(A)
         n = A.shape[0]
         b, x = _f64(b, (n,)), _f64(x, (n,))
         sol, prod = np.zeros(2 * n), np.zeros(2 * n)
-        rc = self._lib.jmpc_debug_linalg(self._h, n, _ptr(A), _ptr(b), _ptr(x), _ptr(sol), _ptr(prod))
+        rc = self._lib.jmpc_debug_linalg_g(self._h, n, int(group_lanes), int(which), _ptr(A), _ptr(b), _ptr(x), _ptr(sol),
+                                           _ptr(prod))
         if rc < 0:
             _cabi.check(rc, "jmpc_debug_linalg")
+        if group_lanes != 32:               # only the solver-layout matvec exists for a half warp
+            return (sol, prod, rc == 0) if full else (sol[:n], prod[n:], rc == 0)
         if n % 2 == 0 and not full:         # the matvec in the solver's row layout must agree with the tiled one
             np.testing.assert_allclose(prod[n:], prod[:n], rtol=1e-13, atol=1e-13 * np.abs(A).max())
         return (sol, prod, rc == 0) if full else (sol[:n], prod[:n], rc == 0)

@@ -52,13 +52,21 @@ class BatchedEpisodes:
         self.flags = torch.zeros(self.max_steps, B, dtype=i32, device=self.dev) if record_history else None
         self.iteration = 0
         self.iter_dev = torch.zeros(1, dtype=i32, device=self.dev)     # the same counter on the device (graph replay)
-        engine.set_skip_mask(self.done)          # finished episodes cost nothing in the step / collision kernels
 
     def _p(self, ten):
         return None if ten is None else C.c_void_p(ten.data_ptr())
 
     def iterate(self):
-        """One loop iteration for every episode that is not done."""
+        """One loop iteration for every episode that is not done.  The engine-wide skip mask (finished episodes cost
+        nothing in the step / collision kernels) is installed for the duration of the launches only: the engine never
+        keeps a pointer into this object's tensors between calls."""
+        self.e.set_skip_mask(self.done)
+        try:
+            self._iterate()
+        finally:
+            self.e.set_skip_mask(None)
+
+    def _iterate(self):
         e, lib, torch = self.e, self.e._lib, self.torch
         stream = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
         i = self.iteration
@@ -133,7 +141,6 @@ class BatchedEpisodes:
                                          self._p(self.done), float(e.config.goal_dis), float(e.config.stop_speed), stream),
                     "jmpc_episode_pre")
         self.torch.cuda.synchronize(e.device)
-        e.set_skip_mask(None)
         res = dict(steps=self.steps.cpu().numpy(), done=self.done.cpu().numpy(), state=self.state.cpu().numpy(),
                    iterations=self.iteration)
         if self.history is not None:

@@ -62,6 +62,9 @@ class MPC:
 
     _reload_config_each_step = False      # the sensitivity flavour re-reads its JSON in every solve
     _config = _cfg
+    # The reference left the DU_TH exit of the linearisation loop commented out (mpc.py:236-240), so it is off here
+    # too; setting this to True on the class (or an instance, before the first step) applies DU_TH of the JSON.
+    enable_du_th_exit = False
 
     def __init__(self, cx: np.ndarray, cy: np.ndarray, cyaw: np.ndarray, dl: float, car_dimensions,
                  speed: float = 30 / 3.6, dt: float = 0.2):
@@ -91,23 +94,28 @@ class MPC:
         L = float(self.car_dimensions.distance_back_to_front_wheel)
         self._cfg_used = cfg
         return BatchedMPC([self._full], dl=float(self.dl), T=cfg.T, config=cfg, dt=float(self.dt), L=L,
-                          speed=float(self.speed), max_batch=1, max_T=_cabi.JMPC_MAX_T)
+                          speed=float(self.speed), max_batch=1, max_T=_cabi.JMPC_MAX_T,
+                          du_th=float(cfg.du_th) if self.enable_du_th_exit else 0.0)
 
     def _effective_length(self) -> int:
         """`set_trajectory_fromarray(trajectory_full[:k])` always passes a prefix of the course given to the
         constructor (mpc_intersection.py:138); it is expressed as an effective length on the uploaded table.
-        Anything else is uploaded afresh."""
+        Anything else is uploaded afresh.  "Is a prefix" is decided on all of the data (three vectorised compares of
+        at most a few hundred doubles), never on samples: a different course must not run on the old table."""
         n = len(self.cx)
         full = self._full
-        if n <= len(full) and n >= 1 and self.cx[0] == full[0, 0] and self.cx[n - 1] == full[n - 1, 0] \
-                and self.cy[n - 1] == full[n - 1, 1] and self.cyaw[n - 1] == full[n - 1, 2] \
-                and (n < 3 or self.cx[n // 2] == full[n // 2, 0]):
+        if 1 <= n <= len(full) and np.array_equal(self.cx, full[:n, 0]) and np.array_equal(self.cy, full[:n, 1]) \
+                and np.array_equal(self.cyaw, full[:n, 2]):
             return n
         self._full = np.stack([np.asarray(self.cx, float), np.asarray(self.cy, float), np.asarray(self.cyaw, float)],
                               axis=1)
         self._engine.close()
         self._engine = self._make_engine(self._cfg_used)
+        self._course_changed()
         return n
+
+    def _course_changed(self):
+        """Hook for flavours that keep per-course device tables besides x / y / yaw."""
 
     def _instance_params(self):
         return None                        # handle defaults; flavours with per-step parameters override this
@@ -124,6 +132,7 @@ class MPC:
             if cfg != self._cfg_used:
                 self._engine.close()
                 self._engine = self._make_engine(cfg)
+                self._course_changed()
         n = self._effective_length()
         Th = self._cfg_used.T
         warm = self.oa is not None and self.odelta is not None
@@ -140,8 +149,11 @@ class MPC:
             raise Exception("something wrong")                     # trajectories.py:120
         self.target_ind = int(out.target_ind[0])
         self.xref = out.xref[0]
-        if self.status == _cabi.STATUS_INFEASIBLE:
-            print("Error: Cannot solve mpc...", file=sys.stderr)   # mpc.py:207-209
+        if self.status != _cabi.STATUS_OPTIMAL:
+            # infeasible, or the solver gave up (iteration cap without even the reduced tolerances): the reference
+            # accepts only OPTIMAL / OPTIMAL_INACCURATE (mpc.py:199); otherwise it prints, returns None for all
+            # outputs, keeps di and brakes with MAX_DECEL (mpc.py:207-209, 298-301)
+            print("Error: Cannot solve mpc...", file=sys.stderr)
             self.oa = self.odelta = self.ox = self.oy = self.oyaw = self.ov = None
             self.ai = self._cfg_used.max_decel
             return self.di, self.ai
@@ -202,28 +214,49 @@ class _WithSpeedMPC(MPC):
     _config = _WITH_SPEED_CONFIG
 
     def __init__(self, cx, cy, cv, cyaw, dl, car_dimensions, dt: float = 0.2):
+        self._cv_uploaded = None
         super().__init__(cx, cy, cyaw, dl, car_dimensions, speed=SIM_MAX_SPEED, dt=dt)
         self.cv = cv
-        cv = np.asarray(cv, float)
-        if cv.size and not np.all(cv == cv[0]):
-            raise ValueError("only the reference's two-level speed profiles are supported (constant, or constant "
-                             "up to a cut index as set_trajectory_fromarray builds them)")
-        self._v_ref = float(cv[0]) if cv.size else 0.0
-        self._v_cut = 1e9
+        self._v_ref, self._v_cut = 0.0, 1e9
 
     def set_trajectory_fromarray(self, trajectory: np.ndarray, cutoff_idx: int = 999):
         super().set_trajectory_fromarray(trajectory)
         self.cv = np.full_like(self.cyaw, WITH_SPEED_MAX_SPEED)
-        self._v_ref, self._v_cut = WITH_SPEED_MAX_SPEED, 1e9
         if cutoff_idx != 999:
             self.cv[cutoff_idx:] = 0
-            self._v_cut = float(cutoff_idx)
+
+    def _course_changed(self):
+        self._cv_uploaded = None             # a fresh engine has no speed table
 
     def _instance_params(self):
+        """`cv` is an attribute the reference reads at every step (mpc_with_speed.py:104).  A two-level profile
+        (constant, or constant up to an index and 0 from there on: what set_trajectory_fromarray builds) travels as
+        the two per-instance parameters v_ref / v_ref_cut; anything else is uploaded as a per-course table."""
         from .config import PARAM_INDEX
+        n = len(self.cx)
+        cv = np.asarray(self.cv, float)
+        if cv.ndim != 1 or len(cv) < n:
+            raise ValueError("cv must hold one reference speed per course point")
+        cv = cv[:n]
+        v_ref, v_cut, table = float(cv[0]), 1e9, None
+        changes = np.nonzero(cv != cv[0])[0]
+        if changes.size:
+            if np.all(cv[changes[0]:] == 0.0):
+                v_cut = float(changes[0])
+            else:
+                table = np.zeros(len(self._full))
+                table[:n] = cv
+        if table is None:
+            if self._cv_uploaded is not None:
+                self._engine.set_course_speed(None)
+                self._cv_uploaded = None
+        elif self._cv_uploaded is None or not np.array_equal(self._cv_uploaded, table):
+            self._engine.set_course_speed([table])
+            self._cv_uploaded = table
+        self._v_ref, self._v_cut = v_ref, v_cut
         p = self._engine.default_params.copy()
-        p[PARAM_INDEX["v_ref"]] = self._v_ref
-        p[PARAM_INDEX["v_ref_cut"]] = self._v_cut
+        p[PARAM_INDEX["v_ref"]] = v_ref
+        p[PARAM_INDEX["v_ref_cut"]] = v_cut
         return p[None, :]
 
 

@@ -163,3 +163,34 @@ def make_sweep(T: int, states_per_point: int = 32, max_points: Optional[int] = N
     w.update(T=T, courses=[course], params=params, obstacles=None, frame_window=10, name=f"sweep_T{T}", B=B,
              dl=float(base[PARAM_INDEX["dl"]]))
     return w
+
+
+# The zero-valued points of the reference's sweep lists (mpc_sensitivity_analysis_comulative.py:103-128), each on the
+# sensitivity base configuration (mpc_config_sensitivity.json: R = [0.1, 0.01], Rd = [10, 10]): a vanishing weight
+# can leave the optimiser non-unique in the controls, so this side set is judged on cost and states only.
+DEGENERATE_POINTS = [
+    dict(w_perp=0.0), dict(w_para=0.0),
+    dict(R_a=0.0, R_d=0.01), dict(R_a=0.1, R_d=0.0),
+    dict(Rd_a=0.0, Rd_d=1.0), dict(Rd_a=10.0, Rd_d=0.0),
+]
+
+
+def make_degenerate(T: int, B: int = 1024, seed: int = 55) -> Dict[str, object]:
+    """Config 5's degenerate side set, one horizon: B states spread over DEGENERATE_POINTS."""
+    rng = np.random.default_rng(seed * 1000 + T)
+    course = load_course("intersection")
+    dl = float(np.linalg.norm(course[0, :2] - course[1, :2]))
+    w = make_states(rng, course, B, T)
+    sens = MPCConfig.from_dict({
+        "NX": 4, "NU": 2, "T": T, "w_perp": 20.0, "w_para": 1.0, "R": [0.1, 0.01], "Rd": [10, 10], "Q_v_yaw": [0.0, 0.5],
+        "Qf": [1.0, 1.0, 0.0, 0.5], "GOAL_DIS": 1.5, "STOP_SPEED": 0.1389, "MAX_TIME": 13.0, "MAX_ITER": 1, "DU_TH": 0.1,
+        "MAX_DSTEER": 30.0, "MAX_ACCEL": 2.0, "MAX_DECEL": -10})
+    base = sens.param_vector(dl=dl, dt=0.2, L=2.86, speed=30 / 3.6)
+    params = np.repeat(base[None, :], B, axis=0)
+    point = np.arange(B) % len(DEGENERATE_POINTS)
+    for k, pt in enumerate(DEGENERATE_POINTS):
+        for key, val in pt.items():
+            params[point == k, PARAM_INDEX[key]] = val
+    w.update(T=T, courses=[course], params=params, obstacles=None, frame_window=10, name=f"degenerate_T{T}", B=B, dl=dl,
+             point=point)
+    return w

@@ -21,7 +21,8 @@
  *       xref       [B][4][T+1]    sampled reference         (mpc.py:89-112)
  *       params     [B][JMPC_NPARAM]  optional per-instance parameters (NULL -> handle defaults)
  *       obstacles  [B][n_obs][6]  x, y, v, yaw, a, steer    (main/lib/moving_obstacles.py:229-232 `get()`)
- *   - A warp owns an instance, so instance-major rows are what it reads coalesced.
+ *   - A lane group (a warp, or half a warp for horizons T <= 15) owns an instance, so instance-major rows are
+ *     what it reads coalesced.
  *
  * Threading: one handle per (host thread, device); calls on one handle must be serialised by the caller.
  */
@@ -35,10 +36,10 @@
 extern "C" {
 #endif
 
-#define JMPC_ABI_VERSION 1
+#define JMPC_ABI_VERSION 2
 #define JMPC_RECORD_LEN 8         /* doubles per instance in the packed result record, see jmpc_step */
 #define JMPC_MAX_PEERS 8          /* GPUs of one NVSwitch box */
-#define JMPC_MAX_T 31           /* horizon limit of the warp-per-instance kernels (reference GUI range 5..25) */
+#define JMPC_MAX_T 31           /* horizon limit of the lane-per-stage kernels (reference GUI range 5..25) */
 
 /* Row order of a parameter vector.  Derivations as in main/lib/mpc.py:14-39 and main/lib/simulation.py:23-25:
  * Qf_* already multiplied by T (mpc.py:28), max_dsteer in rad/s (mpc.py:37). */
@@ -68,7 +69,9 @@ enum jmpc_param {
 /* Per-instance status word. */
 enum jmpc_status {
   JMPC_OPTIMAL = 0,      /* cvxpy OPTIMAL / OPTIMAL_INACCURATE branch                     mpc.py:199-205 */
-  JMPC_MAX_ITER = 1,     /* iteration cap hit; outputs hold the last iterate                             */
+  JMPC_MAX_ITER = 1,     /* iteration cap hit without meeting even the reduced tolerances: a failed solve, handled
+                            like any solver status other than OPTIMAL / OPTIMAL_INACCURATE (mpc.py:199-209):
+                            control outputs are left untouched, xref/target_ind are valid, record.ai = MAX_DECEL */
   JMPC_INFEASIBLE = 2,   /* v0 outside [MIN_SPEED, speed]: reference prints "Cannot solve mpc", mpc.py:207-209;
                             control outputs are left untouched, xref/target_ind are valid                */
   JMPC_INDEX_RULE = 3    /* nearest-index rule failed: reference raises at trajectories.py:120;
@@ -83,6 +86,9 @@ typedef struct {
   int32_t linearisation_iters;/* MAX_ITER of mpc_config.json (default 1)                     mpc.py:231   */
   double  mu_tol;             /* complementarity target (default 1e-13)                                    */
   int32_t warps_per_sm;       /* resident solver warps per SM, 0 = auto                                   */
+  double  du_th;              /* > 0: leave the linearisation loop once sum|oa - poa| + sum|od - pod| <= du_th;
+                                 the exit the reference left commented out at mpc.py:236-240 (DU_TH of
+                                 mpc_config.json).  Default 0 = off, as in the reference.                  */
 } jmpc_options;
 
 /* Library / ABI introspection. */
@@ -108,6 +114,12 @@ int32_t jmpc_set_default_params(jmpc_handle h, const double* default_params);
 int32_t jmpc_set_courses(jmpc_handle h, int32_t n_courses, int32_t stride, const int32_t* len,
                          const double* cx, const double* cy, const double* cyaw);
 
+/* Reference speed profile per course point (HOST pointer, same layout as cx; NULL clears it): xref[2, t] = cv[idx_t]
+ * as main/lib/mpc_with_speed.py:104 samples it.  Without a table the speed row of xref is the two-level profile of
+ * JMPC_P_V_REF / JMPC_P_V_REF_CUT (0 for lib.mpc); a finite JMPC_P_V_REF_CUT still zeroes the profile from that
+ * index on (mpc_with_speed.py:280-282).  Call after jmpc_set_courses. */
+int32_t jmpc_set_course_speed(jmpc_handle h, int32_t n_courses, int32_t stride, const double* cv);
+
 /* Collision-circle geometry of the car (main/lib/car_dimensions.py:62-79): x offsets of the front and rear
  * circle centres from the rear axle and the circle radius.  Defaults are BicycleModelDimensions
  * (car_dimensions.py:82-90): 2.18, 0.68, 2/sqrt(2). */
@@ -129,7 +141,8 @@ int32_t jmpc_step(jmpc_handle h, int32_t B, int32_t T, const double* state, cons
                   double* cost, int32_t* status, int32_t* iters, double* record, void* stream);
 
 /* Skip mask (DEVICE pointer, [B] int32, or NULL to clear): instances with skip[b] != 0 are left untouched by
- * subsequent jmpc_step / jmpc_collision calls on the handle -- finished episodes of a closed-loop batch cost nothing. */
+ * subsequent jmpc_step / jmpc_collision calls on the handle -- finished episodes of a closed-loop batch cost nothing.
+ * The mask belongs to the device entry points: the *_host entry points refuse to run while one is set. */
 int32_t jmpc_set_skip_mask(jmpc_handle h, const int32_t* skip);
 
 /* Order in which the work queue hands instances to the solver warps.  A batch of one to a few waves of the resident
@@ -155,15 +168,18 @@ int32_t jmpc_debug_cycles(jmpc_handle h, uint64_t* out32, int32_t reset);
  * tables.  n_peers = 0 switches it off. */
 int32_t jmpc_set_record_peers(jmpc_handle h, int32_t n_peers, const uint64_t* peer_tables, int64_t rank_offset);
 
-/* Same with HOST pointers: runs the step and returns when the results are in the host arrays.  By default no copy
- * engine is involved: the kernel reads the inputs from and stores the results into page-locked host memory through
- * its device mapping -- the caller's arrays where they are page-locked (jmpc_host_alloc), the handle's staging block
- * otherwise (one host memcpy per such array).  Environment JMPC_ZEROCOPY=1 copies the inputs with cudaMemcpyAsync,
- * =0 stages both directions through device memory. */
+/* Same with HOST pointers: runs the step and returns when the results are in the host arrays.  The inputs are
+ * copied to the device with cudaMemcpyAsync; the results take no copy pass: the kernel's epilogue stores them into
+ * page-locked host memory through its device mapping -- the caller's arrays where they are page-locked
+ * (jmpc_host_alloc), the handle's staging block otherwise (one host memcpy per such array).  jmpc_set_host_transfer
+ * selects the other two modes: 0 stages both directions through device memory, 2 also reads the inputs through the
+ * mapping (measured slower: every warp waits a PCIe round trip when it picks an instance up). */
 int32_t jmpc_step_host(jmpc_handle h, int32_t B, int32_t T, const double* state, const int32_t* course_id,
                        const int32_t* course_len, int32_t* target_ind, const int32_t* warm, double* oa,
                        double* od, const double* params, double* ox, double* oy, double* ov, double* oyaw,
                        double* xref, double* cost, int32_t* status, int32_t* iters, double* record);
+
+int32_t jmpc_set_host_transfer(jmpc_handle h, int32_t mode);     /* 0, 1 (default) or 2, see above */
 
 /* jmpc_step_host with separate read and write arrays for the in-out quantities: the previous solution and search
  * start are read from target_in / oa_in / od_in (never written), the new ones go to target_out / oa_out / od_out
@@ -186,7 +202,8 @@ int32_t jmpc_host_free(jmpc_handle h, void* p);
  *   agent_idx [B]: ego index on the full course (traj_agent_idx);  v [B]: ego speed
  *   obstacles [B][n_obs][6];  frame_window: FRAME_WINDOW;  margin: EXTRA_CUTOFF_MARGIN (in course points)
  *   flag [B]: 1 when a collision is predicted;  course_len_out [B]: effective course length to feed
- *   jmpc_step (full length when flag == 0) */
+ *   jmpc_step (full length when flag == 0).  flag = -1 (full length) reports an instance outside the kernel's table
+ *   sizes: more than 160 kept ego points or more than 71 obstacle prediction steps (the reference's scenes: 49 / 35). */
 int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const int32_t* agent_idx,
                        const double* v, const double* obstacles, int32_t n_obs, int32_t frame_window,
                        int32_t margin, double horizon_s, const double* params, int32_t* flag,
@@ -246,6 +263,10 @@ int32_t jmpc_measure_fma_peak(jmpc_handle h, double* fp64_tflops, double* fp32_t
  * factorisation met a non-positive pivot. */
 int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const double* b, const double* x, double* sol,
                           double* prod);
+/* The same on a lane group of `group_lanes` (16 or 32) lanes: with 16, both halves of the warp work on their own copy
+ * and half `which` reports; prod[0, n) is only filled for group_lanes == 32. */
+int32_t jmpc_debug_linalg_g(jmpc_handle h, int32_t n, int32_t group_lanes, int32_t which, const double* A,
+                            const double* b, const double* x, double* sol, double* prod);
 
 #ifdef __cplusplus
 }

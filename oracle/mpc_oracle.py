@@ -125,7 +125,7 @@ def nearest_index_forward(x: float, y: float, cx: np.ndarray, cy: np.ndarray, st
 # row 4: reference sampling along the course                                  main/lib/mpc.py:89-112
 # ----------------------------------------------------------------------------------------------------
 def ref_trajectory(p: Params, x: float, y: float, v: float, cx, cy, cyaw, start: int,
-                   ov: Optional[np.ndarray] = None):
+                   ov: Optional[np.ndarray] = None, cv: Optional[np.ndarray] = None):
     n_course = len(cx)
     start = nearest_index_forward(x, y, cx, cy, start)
     if ov is None:
@@ -137,7 +137,9 @@ def ref_trajectory(p: Params, x: float, y: float, v: float, cx, cy, cyaw, start:
     xref[0] = cx[idx]
     xref[1] = cy[idx]
     xref[3] = cyaw[idx]
-    xref[2] = np.where(idx < p.v_ref_cut, p.v_ref, 0.0)   # 0 in lib.mpc (never tracked); cv[idx] in mpc_with_speed
+    # 0 in lib.mpc (never tracked, mpc.py:107); cv[idx] in mpc_with_speed.py:104 -- either a speed array `cv` or the
+    # two-level profile its set_trajectory_fromarray builds (v_ref before the cut index, 0 from there on, :280-282)
+    xref[2] = np.where(idx < p.v_ref_cut, p.v_ref if cv is None else np.asarray(cv, float)[idx], 0.0)
     reaches_end = idx == n_course - 1
     return xref, int(start), reaches_end
 
@@ -332,8 +334,10 @@ def linear_mpc_control(p: Params, xref, xbar, x0, reaches_end, tol: float = 1e-9
 # ----------------------------------------------------------------------------------------------------
 # row 9: one MPC step (MAX_ITER linearise->solve rounds)                      main/lib/mpc.py:214-242
 # ----------------------------------------------------------------------------------------------------
-def mpc_step(p: Params, x0: Sequence[float], oa, od, cx, cy, cyaw, target_ind: int, tol: float = 1e-9) -> StepResult:
-    """x0 = (x, y, v, yaw).  oa/od = previous solution (unshifted) or None."""
+def mpc_step(p: Params, x0: Sequence[float], oa, od, cx, cy, cyaw, target_ind: int, tol: float = 1e-9,
+             cv: Optional[np.ndarray] = None, du_th: float = 0.0) -> StepResult:
+    """x0 = (x, y, v, yaw).  oa/od = previous solution (unshifted) or None.  `cv`: reference speed per course point
+    (mpc_with_speed.py:104).  `du_th` > 0 enables the exit the reference left commented out (mpc.py:236-240)."""
     if oa is None or od is None:
         oa = np.zeros(p.T)
         od = np.zeros(p.T)
@@ -341,7 +345,7 @@ def mpc_step(p: Params, x0: Sequence[float], oa, od, cx, cy, cyaw, target_ind: i
     out = None
     for _ in range(p.max_iter):
         try:
-            xref, target_ind, reaches_end = ref_trajectory(p, x0[0], x0[1], x0[2], cx, cy, cyaw, target_ind, ov)
+            xref, target_ind, reaches_end = ref_trajectory(p, x0[0], x0[1], x0[2], cx, cy, cyaw, target_ind, ov, cv)
         except IndexRuleError:
             return StepResult(status=STATUS_INDEX_RULE, target_ind=int(target_ind), xref=np.zeros((4, p.T + 1)),
                               reaches_end=np.zeros(p.T + 1, bool))
@@ -352,7 +356,10 @@ def mpc_step(p: Params, x0: Sequence[float], oa, od, cx, cy, cyaw, target_ind: i
         if oa_n is None:
             # the reference would crash in the next round (np.abs(None)); MAX_ITER is 1 everywhere
             break
+        du = float(np.sum(np.abs(oa_n - np.asarray(oa, float))) + np.sum(np.abs(od_n - np.asarray(od, float))))
         oa, od, ov = oa_n, od_n, ov_n
+        if du_th > 0.0 and du <= du_th:               # mpc.py:236-240
+            break
     return out
 
 

@@ -62,7 +62,7 @@ def oracle_batch(w, idx, processes=None, max_iter=1, warm=None, pool=None):
     if pool is not None:
         n = pool._processes
         return pool.map(_one, jobs, chunksize=max(1, len(jobs) // (4 * n)))
-    processes = processes or min(8, os.cpu_count() or 1)
+    processes = processes or min(32, os.cpu_count() or 1)
     if processes == 1 or len(jobs) < 8:
         return [_one(j) for j in jobs]
     with get_context("fork").Pool(processes) as pool:
@@ -75,8 +75,9 @@ def scaled_err(got, ref):
     return float(np.max(np.abs(got - ref) / (ABS_TOL + REL_TOL * np.abs(ref)))) if ref.size else 0.0
 
 
-def compare_step(out, refs, idx, check_cost=True):
-    """Assert parity of a StepOutput against oracle results; returns the worst scaled error."""
+def compare_step(out, refs, idx, check_cost=True, controls=True):
+    """Assert parity of a StepOutput against oracle results; returns the worst scaled error.  `controls=False` judges
+    predicted states and cost only (degenerate parameter points, where the optimal controls need not be unique)."""
     worst = 0.0
     for pos, k in enumerate(idx):
         r = refs[pos]
@@ -87,8 +88,10 @@ def compare_step(out, refs, idx, check_cost=True):
         assert np.array_equal(out.xref[k], r.xref), f"instance {k}: xref differs"
         if r.status != O.STATUS_OPTIMAL:
             continue
-        for name, got, ref in [("oa", out.oa[k], r.oa), ("od", out.od[k], r.od), ("ox", out.ox[k], r.ox),
-                               ("oy", out.oy[k], r.oy), ("ov", out.ov[k], r.ov), ("oyaw", out.oyaw[k], r.oyaw)]:
+        fields = [("ox", out.ox[k], r.ox), ("oy", out.oy[k], r.oy), ("ov", out.ov[k], r.ov), ("oyaw", out.oyaw[k], r.oyaw)]
+        if controls:
+            fields = [("oa", out.oa[k], r.oa), ("od", out.od[k], r.od)] + fields
+        for name, got, ref in fields:
             e = scaled_err(got, ref)
             assert e <= 1.0, f"instance {k}: {name} outside tolerance (scaled err {e:.3g})\n got {got}\n ref {ref}"
             worst = max(worst, e)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
     lib.jmpc_abi_version.restype = ctypes.c_int32
     lib.jmpc_nparam.restype = ctypes.c_int32
-    assert lib.jmpc_abi_version() == 1
+    assert lib.jmpc_abi_version() == _cabi.ABI_VERSION
 
 
 def test_param_enum_matches_python_table():

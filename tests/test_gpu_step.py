@@ -239,19 +239,19 @@ def test_pinned_host_outputs_equal_plain_host_path(jm):
     assert np.array_equal(got.record[:, 3], got.status) and np.array_equal(got.record[:, 4], got.target_ind)
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
-def test_host_transfer_modes_agree(jm, mode, monkeypatch):
-    """jmpc_step_host[_io]: staged DMA (0), zero-copy results (1), zero-copy both ways (2, default) give the same
+@pytest.mark.parametrize("mode", ["staged", "zero_copy_results", "zero_copy"])
+def test_host_transfer_modes_agree(jm, mode):
+    """jmpc_step_host[_io]: staged DMA, zero-copy results (the default), zero-copy both ways give the same
     arrays, for pageable and page-locked callers, including instances that are not solved (in-out values kept)."""
     synth, BatchedMPC = jm
     w = synth.make_workload(2, B=130)
     state = w["state"].copy()
     state[3, 2] = 30.0            # v0 above the speed cap -> infeasible (status 2)
-    monkeypatch.setenv("JMPC_ZEROCOPY", "0")
     mpc = BatchedMPC(w["courses"], dl=w["dl"], T=w["T"], max_batch=256)
+    mpc.set_host_transfer("staged")
     ref = mpc.step_host(state, w["target_ind"], w["oa"], w["od"], course_len=w["course_len"])
     assert ref.status[3] == 2 and np.array_equal(ref.oa[3], w["oa"][3])
-    monkeypatch.setenv("JMPC_ZEROCOPY", mode)
+    mpc.set_host_transfer(mode)
     keys = ["oa", "od", "cost", "status", "iters", "target_ind", "record"]
     solved = ref.status == 0
     def same(got):
@@ -332,3 +332,86 @@ def test_generic_horizons(jm, T):
     out = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"])
     refs = oracle_batch(w, range(40))
     assert compare_step(out, refs, range(40)) <= 1.0
+
+
+def test_iteration_cap_is_a_failed_solve(jm):
+    """max_solver_iters = 2: nothing converges.  Like any solver status other than OPTIMAL / OPTIMAL_INACCURATE in the
+    reference (mpc.py:199-209, 298-301) that is a failed solve: controls untouched, xref / target reported, the
+    record brakes with MAX_DECEL, and the drop-in keeps di, sets ai = MAX_DECEL and drops its warm start."""
+    synth, BatchedMPC = jm
+    for T, cfgno in [(20, 2), (13, 3)]:
+        w = synth.make_workload(cfgno, B=64)
+        mpc, out = _run(BatchedMPC, w, max_solver_iters=2)
+        good = _run(BatchedMPC, w)[1]
+        assert (out.status == O.STATUS_MAX_ITER).all() and (out.iters == 2).all()
+        assert np.array_equal(out.oa, w["oa"]) and np.array_equal(out.od, w["od"])
+        assert np.array_equal(out.xref, good.xref) and np.array_equal(out.target_ind, good.target_ind)
+        assert np.isnan(out.cost).all() and np.isnan(out.record[:, 0]).all()
+        assert (out.record[:, 1] == -10.0).all() and (out.record[:, 3] == O.STATUS_MAX_ITER).all()
+
+
+def test_du_th_exit_of_the_linearisation_loop(jm):
+    """The exit the reference left commented out (mpc.py:236-240), as an option: MAX_ITER = 4 with DU_TH."""
+    synth, BatchedMPC = jm
+    for cfgno, du_th in [(2, 15.0), (3, 10.0)]:      # thresholds inside the spread of du on these batches
+        w = synth.make_workload(cfgno, B=48)
+        w["course_len"][:] = len(w["courses"][0])
+        mpc, out = _run(BatchedMPC, w, linearisation_iters=4, du_th=du_th)
+        base = default_vector(w)
+        refs = []
+        for k in range(48):
+            p = params_from_vector(base, w["T"], 4)
+            c = w["courses"][0]
+            refs.append(O.mpc_step(p, w["state"][k], w["oa"][k], w["od"][k], c[:, 0], c[:, 1], c[:, 2],
+                                   int(w["target_ind"][k]), du_th=du_th))
+        assert compare_step(out, refs, range(48)) <= 1.0
+        full = _run(BatchedMPC, w, linearisation_iters=4)[1]
+        assert (out.iters <= full.iters).all() and (out.iters < full.iters).any()      # some instances left early
+
+
+def test_arbitrary_speed_profile_table(jm):
+    """xref[2] = cv[idx] for a general per-course speed profile (mpc_with_speed.py:104), with Q_v > 0."""
+    synth, BatchedMPC = jm
+    from junction_mpc.config import MPCConfig, PARAM_INDEX as PI
+    w = synth.make_workload(3, B=64)
+    course = w["courses"][0]
+    cv = 3.0 + 2.0 * np.sin(np.arange(len(course)) / 40.0)
+    mpc = BatchedMPC(w["courses"], dl=w["dl"], T=w["T"], max_batch=64)
+    mpc.set_course_speed([cv])
+    prm = np.repeat(mpc.default_params[None, :], 64, axis=0)
+    prm[:, PI["Q_v"]] = 20.0
+    prm[:, PI["v_ref_cut"]] = np.where(np.arange(64) % 2 == 0, 1e9, w["target_ind"] + 25)    # half with a cut index too
+    out = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"], params=prm)
+    refs = []
+    for k in range(64):
+        p = params_from_vector(prm[k], w["T"])
+        n = int(w["course_len"][k])
+        refs.append(O.mpc_step(p, w["state"][k], w["oa"][k], w["od"][k], course[:n, 0], course[:n, 1], course[:n, 2],
+                               int(w["target_ind"][k]), cv=cv[:n]))
+    assert compare_step(out, refs, range(64)) <= 1.0
+    assert np.abs(out.xref[:, 2]).max() > 1.0
+    mpc.set_course_speed(None)
+    out0 = mpc.step_host(w["state"], w["target_ind"], w["oa"], w["od"], course_len=w["course_len"], params=prm)
+    assert (out0.xref[:, 2] == 0).all()
+
+
+def test_half_warp_pairs_are_independent(jm):
+    """T <= 15 runs two instances per warp.  An instance's results must not depend on its partner: odd batch sizes,
+    a failing partner (index rule / infeasible), and any permutation of the batch give identical bits."""
+    synth, BatchedMPC = jm
+    w = synth.make_workload(3, B=257)
+    st = w["state"].copy()
+    st[10, 2] = 30.0                       # infeasible partner of instance 11
+    st[20, :2] += 500.0                    # far away: whatever the index rule says
+    w["state"] = st
+    mpc, ref = _run(BatchedMPC, w)
+    assert ref.status[10] == O.STATUS_INFEASIBLE and (ref.status == 0).sum() >= 250
+    perm = np.random.default_rng(0).permutation(257)
+    out = mpc.step_host(st[perm], w["target_ind"][perm], w["oa"][perm], w["od"][perm], course_len=w["course_len"][perm])
+    solved = ref.status == 0
+    for key in ["oa", "od", "cost", "status", "iters", "target_ind", "xref"]:
+        assert np.array_equal(getattr(out, key), getattr(ref, key)[perm], equal_nan=True), key
+    for key in ["ox", "oy", "ov", "oyaw"]:
+        assert np.array_equal(getattr(out, key)[solved[perm]], getattr(ref, key)[perm][solved[perm]]), key
+    refs = oracle_batch(w, range(0, 257, 4))
+    compare_step(ref, refs, range(0, 257, 4))

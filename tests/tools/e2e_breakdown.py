@@ -1,4 +1,5 @@
-"""Where the host-path time goes (JMPC_TIMING=1 makes jmpc_step_host_io print its own breakdown)."""
+"""Where the host-path time goes (a -DJMPC_EXPERIMENT build with JMPC_TIMING=1 makes jmpc_step_host_io print its own
+breakdown)."""
 import sys, os, time
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/av-simulation-at-intersections_b200'); sys.path.insert(0,'/root/repo/tests')
 import numpy as np
@@ -10,8 +11,8 @@ hout = mpc.host_outputs(B)
 hin = {}
 for key in ("state", "target_ind", "oa", "od", "course_len"):
     hin[key] = mpc.pinned_empty(w[key].shape, w[key].dtype); hin[key][...] = w[key]
-for mode in ("2", "1", "0"):
-    os.environ["JMPC_ZEROCOPY"] = mode
+for mode in ("zero_copy", "zero_copy_results", "staged"):
+    mpc.set_host_transfer(mode)
     os.environ.pop("JMPC_TIMING", None)
     for _ in range(3):
         mpc.step_host(hin["state"], hin["target_ind"], hin["oa"], hin["od"], course_len=hin["course_len"], out=hout)
