@@ -932,6 +932,21 @@ int32_t jmpc_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, double* obst
   return 0;
 }
 
+int32_t jmpc_scripted_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, const double* script, double* model,
+                                    double* obstacles, const int32_t* done, int32_t advance, void* stream) {
+  if (!h) return fail("jmpc_scripted_obstacle_step: NULL handle");
+  if (B < 0 || B > h->max_B || n_obs < 0) return fail("jmpc_scripted_obstacle_step: size out of range");
+  if (B == 0 || n_obs == 0) return 0;
+  if (!script || !model || !obstacles) return fail("jmpc_scripted_obstacle_step: NULL array");
+  CK(cudaSetDevice(h->device));
+  const int count = B * n_obs;
+  jmpc::scripted_obstacle_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      count, script, model, obstacles, done, n_obs, advance, h->defaults[JMPC_P_L]);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
 int64_t jmpc_launch_count(jmpc_handle h) { return h ? h->launches : 0; }
 
 int32_t jmpc_debug_linalg(jmpc_handle h, int32_t n, const double* A, const double* b, const double* x, double* sol,

@@ -7,8 +7,9 @@
 //   collision check -> truncated course length               :111-143                  [collision_kernel]
 //   delta, a = mpc.step(state)                               :146                      [mpc_step_kernel]
 //   xref deviation; plant step; history                      :163, mpc.py:305-312, simulation.py:35-61 [episode_post_kernel]
-// Obstacles move with constant inputs here (the reference's scripted obstacles are outside the hot path):
-//   obstacle_step_kernel uses the same update as their predictor, moving_obstacles_prediction.py:21-29.
+// Obstacles either move with constant inputs (obstacle_step_kernel: the update of their predictor,
+// moving_obstacles_prediction.py:21-29) or follow the reference's scripted steering rules
+// (scripted_obstacle_kernel: MovingObstacleTIntersection / Roundabout / Arterial, moving_obstacles.py:28-232).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -156,6 +157,72 @@ __global__ void obstacle_step_kernel(int count, double* __restrict__ obs, const 
   v = __dadd_rn(v, __dmul_rn(o[4], dt));
   yaw = __dadd_rn(yaw, __dmul_rn(__dmul_rn(v / L, tan(o[5])), dt));
   o[0] = x; o[1] = y; o[2] = v; o[3] = yaw;
+}
+
+// ---- the reference's scripted obstacles (main/lib/moving_obstacles.py) -------------------------------------------
+// One thread per obstacle.  `script` [count][JMPC_OBS_SCRIPT_LEN] is constant: kind, direction (+1 / -1), turning,
+// speed, offset (<= 0: none), the Bicycle's sample time, the dt of the offset test (the roundabout class overwrites
+// its own with 0.2, moving_obstacles.py:45, while its Bicycle keeps the constructor's), and one auxiliary value (the
+// turning steer angle arctan(L / 5) of the roundabout rules, computed on the host; the arterial's initial speed).
+// `model` [count][4] = Bicycle xc, yc, theta and the step counter.  `obs` [count][6] receives what `get()` returns:
+// x, y, forward_velocity, theta, 0, steering_angle -- the tuple the flag kernel consumes.
+//
+// The scenario loop calls get() (prediction), then step() (mpc_intersection.py:123-125, 157-160).  get() evaluates
+// its tuple left to right, so theta is read BEFORE the steering property runs, and the roundabout's steering property
+// overwrites model.theta as a side effect (moving_obstacles.py:82-84, 98-100) -- both reproduced.
+__device__ __forceinline__ double scripted_speed(const double* sc, double counter) {
+  const int kind = (int)sc[JMPC_OBS_KIND];
+  const double offset = sc[JMPC_OBS_OFFSET];
+  const bool moving = !(offset > 0.0) || counter > __ddiv_rn(offset, sc[JMPC_OBS_DT_OFFSET]);
+  if (moving) return sc[JMPC_OBS_SPEED];
+  return kind == JMPC_OBS_ARTERIAL ? sc[JMPC_OBS_AUX] : 0.0;
+}
+__device__ __forceinline__ double scripted_steer(const double* sc, double xc, double yc, double& theta) {
+  const int kind = (int)sc[JMPC_OBS_KIND];
+  const bool right = sc[JMPC_OBS_DIRECTION] >= 0.0, turning = sc[JMPC_OBS_TURNING] != 0.0;
+  double steer = 0.0;
+  if (!turning) return steer;
+  if (kind == JMPC_OBS_TINTERSECTION) {                 // moving_obstacles.py:197-213
+    if (right) { if (xc >= -10.0 && theta > -M_PI / 2) steer = -0.38; }
+    else if (xc <= 12.0 && theta < 3 * M_PI / 2) steer = 0.19;
+  } else if (kind == JMPC_OBS_ROUNDABOUT) {             // moving_obstacles.py:66-103, the ifs in sequence
+    const double ang = sc[JMPC_OBS_AUX];
+    if (right) {
+      if (-7.0 <= xc && xc <= -4.0 && yc < 0.0) steer = -ang;
+      if (-3.0 < xc) steer = ang;
+      if (yc > 0.0 && -5.0 <= xc && xc <= -3.0) steer = -ang;
+      if (xc <= -3.0 && yc > 0.0) { theta = -M_PI; steer = 0.0; }
+    } else {
+      if (4.0 <= xc && xc <= 7.0 && yc > 0.0) steer = -ang;
+      if (xc < 3.0) steer = ang;
+      if (yc < 0.0 && 3.0 <= xc && xc <= 5.0) steer = -ang;
+      if (3.0 <= xc && yc < 0.0) { theta = 0.0; steer = 0.0; }
+    }
+  }
+  return steer;
+}
+__global__ void scripted_obstacle_kernel(int count, const double* __restrict__ script, double* __restrict__ model,
+                                         double* __restrict__ obs, const int* __restrict__ done, int n_obs, int advance,
+                                         double L) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  if (done && done[k / n_obs]) return;
+  const double* sc = script + (size_t)k * JMPC_OBS_SCRIPT_LEN;
+  double* m = model + (size_t)k * 4;
+  double xc = m[0], yc = m[1], theta = m[2], counter = m[3];
+  if (advance) {                                        // step(): moving_obstacles.py:113-116, bicycle/main.py:28-41
+    const double steer = scripted_steer(sc, xc, yc, theta);
+    const double v = scripted_speed(sc, counter), dt = sc[JMPC_OBS_DT_MODEL];
+    const double xd = __dmul_rn(v, cos(theta)), yd = __dmul_rn(v, sin(theta)), td = __dmul_rn(v / L, tan(steer));
+    xc = __dadd_rn(xc, __dmul_rn(xd, dt));
+    yc = __dadd_rn(yc, __dmul_rn(yd, dt));
+    theta = __dadd_rn(theta, __dmul_rn(td, dt));
+    counter += 1.0;
+  }
+  double* o = obs + (size_t)k * 6;                      // get(): moving_obstacles.py:118-120
+  o[0] = xc; o[1] = yc; o[2] = scripted_speed(sc, counter); o[3] = theta; o[4] = 0.0;
+  o[5] = scripted_steer(sc, xc, yc, theta);             // may overwrite theta (after it has been reported)
+  m[0] = xc; m[1] = yc; m[2] = theta; m[3] = counter;
 }
 
 }  // namespace jmpc

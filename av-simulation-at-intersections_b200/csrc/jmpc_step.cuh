@@ -94,11 +94,14 @@ __host__ __device__ inline int k_region_doubles(int T) {
   const int a = tiles_doubles(2 * T), b = MOM_COUNT * even_up(T + 1);
   return a > b ? a : b;
 }
+#ifndef JMPC_PAD_T1E
+#define JMPC_PAD_T1E 0          // layout experiments: unused (T + 1)-arrays between epsi and vb
+#endif
 __host__ __device__ inline int inst_smem_doubles(int T) {
   const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
   return k_region_doubles(T)    // K / L on 4x4 tiles (and the condensing's moment tables)
          + 4 * n4               // u, q, rhs, grad
-         + 9 * T1e              // prefix sums ca, cb, cc, ck; WeX, WeY, epsi; vb, th
+         + (9 + JMPC_PAD_T1E) * T1e   // prefix sums ca, cb, cc, ck; WeX, WeY, epsi; vb, th
          + 4 * Te               // per-iteration row weights wA, wD, wR, SW
          + kParamSlots          // the instance's parameter vector + derived row bounds
          + 2;                   // mbarrier of the TMA Hessian copy (8 bytes, padded to 16)
@@ -249,6 +252,7 @@ struct WarpMem {
     // grad .. epsi are dead while the solver runs: 4 (2T) + 7 (T + 1) >= 8T doubles, the solver's row stash
     ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
     WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e;
+    p += JMPC_PAD_T1E * T1e;
     vb = p; p += T1e; th = p; p += T1e;
     wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; SW = p; p += Te;
     prm = p; p += kParamSlots;
@@ -607,7 +611,10 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
   const int ntd = tiles_doubles(n);
   bool converged = false;
   bool acceptable = false;          // last evaluated iterate meets the reduced tolerances (see below)
-  bool done = !active;              // this group's solve is over (its state is frozen from then on)
+  // kLock: several groups share the warp and iterate in lock step.  A whole-warp instance (G = 32) leaves the loop the
+  // moment it is done, so `done` never guards anything there and the compiler sees the single-instance loop.
+  constexpr bool kLock = (G != 32);
+  bool done = kLock ? !active : false;      // this group's solve is over (its state is frozen from then on)
   int my_iters = 0;
 #ifdef JMPC_DEBUG_RESID
   double dbg_mu = 0, dbg_rp = 0, dbg_rd = 0;
@@ -707,7 +714,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     double rdmax = fmax(fabs(g0), fabs(g1));
     rdmax = grp_max<G>(rdmax, gm);
     __syncwarp(gm);
-    if (!done) {
+    if (!kLock || !done) {
       if (mu <= A.mu_tol && rpmax <= A.tol_res && rdmax <= A.tol_res * gscale) { converged = true; done = true; }
       // Complementarity three orders below its target with the primal rows satisfied: the iterate has converged;
       // what is left in the dual residual is multiplier noise on the active rows (w ~ 1e16 by now, their slacks are
@@ -718,12 +725,12 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       // when the factorisation breaks down numerically a step or two before the strict target (w ~ 1e13 by then),
       // or the iteration cap is hit.  Measured: such iterates are still 5-6x inside the control tolerance.
       else acceptable = (mu <= 1e-9 && rpmax <= 1e-7 && rdmax <= 1e-7 * gscale);
-      if (done) my_iters = it;
+      if (kLock && done) my_iters = it;
 #ifdef JMPC_DEBUG_RESID
       dbg_mu = mu; dbg_rp = rpmax; dbg_rd = rdmax / gscale;
 #endif
     }
-    if (G == 32 ? done : __all_sync(kFull, done)) break;
+    if (kLock ? __all_sync(kFull, done) : done) break;
 
     JMPC_TOCK(ts_, 3);
     // The predictor's right-hand side needs nothing from the factor, so its forward substitution rides along with
@@ -736,8 +743,11 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     // already two orders inside the reduced tolerances: stop here.  The step computed from the patched factor is
     // usually harmless, but on a few instances in 10^5 (weakly active speed rows, T = 25) it threw the iterate far
     // enough out that the iteration cap was reached; which instances depended on the build.
-    if (!done && !clean && mu <= 1e-11 && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) { acceptable = true; done = true; my_iters = it; }
-    if (G == 32 && done) break;
+    if ((!kLock || !done) && !clean && mu <= 1e-11 && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) {
+      acceptable = true; done = true;
+      if (kLock) my_iters = it;
+    }
+    if (!kLock && done) break;
 
     double dsh[4], dsl[4], dlh[4], dll[4];
     double sigma_mu = 0.0, aff_step = 0.0;
@@ -807,7 +817,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
         mu_aff = grp_sum<G>(mu_aff, gm) * inv_rows;
         const double ratio = mu_aff / mu;
         sigma_mu = ratio * ratio * ratio * mu;
-      } else if (!done) {
+      } else if (!kLock || !done) {
         // Fraction to the boundary tied to the length aa of the affine (predictor) step: a long predictor step
         // means the iterate is well centred and the corrector may go almost to the boundary (0.9999); a short
         // one keeps the classical 0.99.  Saves ~13 % of the iterations; a rule driven by mu alone (1 - mu) made
@@ -824,7 +834,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       JMPC_TOCK(ts_, 7);
     }
   }
-  if (!done) my_iters = it;
+  if (!kLock || !done) my_iters = it;
 #ifdef JMPC_DEBUG_RESID
   if (gl == 0) { M.prm[29] = dbg_mu; M.prm[30] = dbg_rp; M.prm[31] = dbg_rd; }
   __syncwarp(gm);
@@ -1041,8 +1051,12 @@ __global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int*
 #define JMPC_WPB 4                 // warps per block; JMPC_WPB x JMPC_MINBLOCKS resident warps per SM set the register budget
 #endif
 // resident blocks per SM the register budget is set for: short horizons leave shared memory for more warps, and at
-// T = 8 the extra warps pay for the tighter register budget (80 registers, 24 warps: +5 %; at T = 13 / 20 / 25 they do not)
-constexpr int step_min_blocks(int TT) { return TT == 8 ? (JMPC_MINBLOCKS * 3) / 2 : JMPC_MINBLOCKS; }
+// T = 8 the extra warps pay for the tighter register budget (80 registers, 24 warps: +5 %; at T = 13 / 20 they do
+// not).  At T = 25 shared memory (18.4 KB per instance) admits only three blocks of four warps anyway, so the kernel
+// is compiled for three: 168 registers instead of 128 (measured: 16.8 -> 15.5 ms on 65 536 instances).
+constexpr int step_min_blocks(int TT) {
+  return TT == 8 ? (JMPC_MINBLOCKS * 3) / 2 : (TT == 25 && JMPC_MINBLOCKS > 3) ? 3 : JMPC_MINBLOCKS;
+}
 template <int TT, int G>
 __global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_kernel(
     const __grid_constant__ StepArgs A) {

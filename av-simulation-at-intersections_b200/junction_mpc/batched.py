@@ -283,14 +283,20 @@ class BatchedMPC:
         return out
 
     def collision_host(self, agent_idx, v, obstacles, frame_window: int, margin: int, course_id=None,
-                       params=None, horizon_s: float = 7.0):
-        """obstacles: [B, n_obs, 6].  Returns (flag[B] int32, course_len[B] int32)."""
+                       params=None, horizon_s: float = 7.0, out=None):
+        """obstacles: [B, n_obs, 6].  Returns (flag[B] int32, course_len[B] int32); `out` = (flag, course_len) arrays
+        to fill instead (page-locked ones from `pinned_empty` are written by the kernel directly)."""
         agent_idx = _i32(agent_idx)
         B = agent_idx.shape[0]
         obstacles = _f64(obstacles)
         n_obs = obstacles.shape[1] if obstacles.ndim == 3 else 0
-        flag = np.zeros(B, np.int32)
-        clen = np.zeros(B, np.int32)
+        if out is not None:
+            flag, clen = out
+            if flag.dtype != np.int32 or clen.dtype != np.int32 or flag.shape != (B,) or clen.shape != (B,):
+                raise ValueError("`out` must be two int32 arrays of shape [B]")
+        else:
+            flag = np.zeros(B, np.int32)
+            clen = np.zeros(B, np.int32)
         _cabi.check(self._lib.jmpc_collision_host(
             self._h, B, _ptr(None if course_id is None else _i32(course_id, (B,))), _ptr(agent_idx), _ptr(_f64(v, (B,))),
             _ptr(obstacles) if n_obs else None, n_obs, int(frame_window), int(margin), float(horizon_s),

@@ -3,8 +3,9 @@
 One iteration = the body of `for i in itertools.count()` in main/scenarios/mpc_intersection.py:99-163:
 goal test -> ego index on the full course -> collision flag / cut -> MPC step -> plant step + history.
 Everything runs in libjmpc.so kernels on torch-owned device tensors; the host only sequences launches and looks
-at the `done` flags every few iterations.  Obstacles are either a per-step script (e.g. a recording of the
-reference's scripted obstacles) or constant-input vehicles advanced on the device.
+at the `done` flags every few iterations.  Obstacles are the reference's scripted vehicles stepped on the device
+(`obstacle_program`, see `scripted_obstacles`), constant-input vehicles advanced on the device (`obstacles`), or a
+per-step recording (`obstacle_script`).
 """
 from __future__ import annotations
 
@@ -17,10 +18,44 @@ from . import _cabi
 from .batched import BatchedMPC
 
 
+OBS_KINDS = {"constant": 0, "t_intersection": 1, "roundabout": 2, "arterial": 3}
+
+
+def scripted_obstacles(specs, L: float = 2.86):
+    """Device-side description of the reference's scripted obstacles (main/lib/moving_obstacles.py).
+
+    specs: nested list [B][n_obs] of dicts with the constructor arguments of the reference classes:
+      kind = "t_intersection" | "roundabout" | "arterial", direction, turning, speed, offset, dt, and for the arterial
+      x_init, y_init, initial_speed.
+    Returns (script [B, n_obs, 8], model [B, n_obs, 4]) float64 arrays for `BatchedEpisodes(obstacle_program=...)`:
+    the constant script rows (enum jmpc_obs_script in include/jmpc.h) and the initial Bicycle state + step counter
+    (start poses of moving_obstacles.py:52-61, 134-137, 190-199)."""
+    B, n = len(specs), len(specs[0])
+    script, model = np.zeros((B, n, 8)), np.zeros((B, n, 4))
+    for b, row in enumerate(specs):
+        if len(row) != n:
+            raise ValueError("every episode needs the same number of obstacles")
+        for k, s in enumerate(row):
+            kind = OBS_KINDS[s["kind"]]
+            direction = 1.0 if s.get("direction", 1) >= 0 else -1.0
+            dt = float(s.get("dt", 0.2))
+            offset = s.get("offset")
+            aux = float(np.arctan((1 / 5) * 2.86)) if kind == 2 else float(s.get("initial_speed", 0.0))
+            script[b, k] = [kind, direction, 1.0 if s.get("turning", False) else 0.0, float(s.get("speed", 25 / 3.6)),
+                            -1.0 if (offset is None or offset <= 0) else float(offset), dt, 0.2 if kind == 2 else dt, aux]
+            if kind == 3:
+                model[b, k] = [float(s["x_init"]), float(s["y_init"]), np.pi / 2, 0.0]
+            elif direction > 0:
+                model[b, k] = [-30.0, -3.0, 0.0, 0.0]
+            else:
+                model[b, k] = [30.0, 3.0, np.pi, 0.0]
+    return script, model
+
+
 class BatchedEpisodes:
     def __init__(self, engine: BatchedMPC, state0, course_id=None, obstacles=None, obstacle_script=None,
                  frame_window: int = 10, margin: int = 72, params=None, max_steps: int = 256,
-                 record_history: bool = True, horizon_s: float = 7.0):
+                 record_history: bool = True, horizon_s: float = 7.0, obstacle_program=None):
         import torch
         self.torch = torch
         self.e = engine
@@ -34,6 +69,12 @@ class BatchedEpisodes:
         self.params = t(params, f64)
         self.obstacles = t(obstacles, f64)                       # [B, n_obs, 6], advanced on the device
         self.script = t(obstacle_script, f64)                    # [S, B, n_obs, 6], read per step
+        self.program = None
+        if obstacle_program is not None:                         # the reference's scripted obstacles, stepped on the device
+            if obstacles is not None or obstacle_script is not None:
+                raise ValueError("give one of obstacles / obstacle_script / obstacle_program")
+            self.program = (t(obstacle_program[0], f64), t(obstacle_program[1], f64))
+            self.obstacles = torch.zeros(B, self.program[0].shape[1], 6, dtype=f64, device=self.dev)
         if self.obstacles is not None and self.script is not None:
             raise ValueError("give either constant-input obstacles or a script")
         self.frame_window, self.margin, self.horizon_s = int(frame_window), int(margin), float(horizon_s)
@@ -52,6 +93,15 @@ class BatchedEpisodes:
         self.flags = torch.zeros(self.max_steps, B, dtype=i32, device=self.dev) if record_history else None
         self.iteration = 0
         self.iter_dev = torch.zeros(1, dtype=i32, device=self.dev)     # the same counter on the device (graph replay)
+        if self.program is not None:                                 # get() before the first iteration
+            self._scripted_step(advance=0)
+
+    def _scripted_step(self, advance: int):
+        e = self.e
+        stream = C.c_void_p(self.torch.cuda.current_stream(e.device).cuda_stream)
+        _cabi.check(e._lib.jmpc_scripted_obstacle_step(
+            e._h, self.B, int(self.program[0].shape[1]), self._p(self.program[0]), self._p(self.program[1]),
+            self._p(self.obstacles), self._p(self.done), int(advance), stream), "jmpc_scripted_obstacle_step")
 
     def _p(self, ten):
         return None if ten is None else C.c_void_p(ten.data_ptr())
@@ -92,7 +142,9 @@ class BatchedEpisodes:
             self._p(self.target_ind), self._p(self.steps), self._p(self.done), self._p(self.di), self._p(self.warm),
             self._p(self.history), self.max_steps, self._p(self.flags) if has_flags else None, self._p(self.flag),
             self._p(self.iter_dev), float(e.dt), stream), "jmpc_episode_post_dev")
-        if self.obstacles is not None and self.obstacles.shape[1] > 0:
+        if self.program is not None:
+            self._scripted_step(advance=1)
+        elif self.obstacles is not None and self.obstacles.shape[1] > 0:
             _cabi.check(lib.jmpc_obstacle_step(e._h, self.B, int(self.obstacles.shape[1]), self._p(self.obstacles),
                                                self._p(self.done), float(e.dt), stream), "jmpc_obstacle_step")
         _cabi.check(lib.jmpc_counter_add(e._h, self._p(self.iter_dev), 1, stream), "jmpc_counter_add")

@@ -165,6 +165,65 @@ def make_sweep(T: int, states_per_point: int = 32, max_points: Optional[int] = N
     return w
 
 
+
+# ---- config 5 at full size: 4 horizons x 8192 parameter points x 32 states = 1 048 576 instances -----------------
+SWEEP_HORIZONS = (8, 13, 20, 25)
+SWEEP_CHUNKS = 16                       # a horizon slice is generated in 16 independent chunks of 16 384 instances
+
+
+def sweep_grid() -> np.ndarray:
+    """The 8192 parameter points of one horizon, [8192, 7] in the fixed order dt, w_perp, w_para, R_a, R_d, Rd_a, Rd_d."""
+    axes = [SWEEP_AXES[k] for k in ["dt", "w_perp", "w_para", "R_acc", "R_steer", "Rd_acc", "Rd_steer"]]
+    return np.array(np.meshgrid(*axes, indexing="ij")).reshape(len(axes), -1).T
+
+
+def sweep_slice_size(states_per_point: int = 32) -> int:
+    return sweep_grid().shape[0] * states_per_point
+
+
+def make_sweep_shard(T: int, lo: int, hi: int, states_per_point: int = 32, cfg: Optional[MPCConfig] = None,
+                     seed: int = 5) -> Dict[str, object]:
+    """Instances [lo, hi) of the horizon-T slice of config 5 (instance i = parameter point i // states_per_point).
+    The slice is defined chunk by chunk (each chunk has its own seeded generator), so a rank of a sharded run only
+    generates the chunks its shard touches and every world size sees the same global batch."""
+    cfg = cfg or MPCConfig.default()
+    grid = sweep_grid()
+    total = grid.shape[0] * states_per_point
+    if not (0 <= lo <= hi <= total):
+        raise ValueError("shard out of range")
+    per_chunk = total // SWEEP_CHUNKS
+    course = load_course("intersection")
+    dl = float(np.linalg.norm(course[0, :2] - course[1, :2]))
+    base = cfg.with_T(T).param_vector(dl=dl, dt=0.2, L=2.86, speed=30 / 3.6)
+    parts = []
+    for c in range(lo // per_chunk, (max(hi, lo + 1) - 1) // per_chunk + 1):
+        rng = np.random.default_rng([seed, T, c])
+        w = make_states(rng, course, per_chunk, T)
+        first = c * per_chunk
+        point = (first + np.arange(per_chunk)) // states_per_point
+        params = np.repeat(base[None, :], per_chunk, axis=0)
+        for col, key in enumerate(["dt", "w_perp", "w_para", "R_a", "R_d", "Rd_a", "Rd_d"]):
+            params[:, PARAM_INDEX[key]] = grid[point, col]
+        w["params"] = params
+        a, b = max(lo, first) - first, min(hi, first + per_chunk) - first
+        parts.append({k: v[a:b] for k, v in w.items()})
+    out = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in parts[0]}
+    out.update(T=T, courses=[course], obstacles=None, frame_window=10, name=f"sweep_T{T}[{lo}:{hi}]", B=hi - lo, dl=dl)
+    return out
+
+
+def make_sweep_sample(T: int, n: int, states_per_point: int = 32, seed: int = 5) -> Dict[str, object]:
+    """A bounded sample of the horizon-T slice of config 5 for the CPU legs: the first `n` states of the slice's
+    generator, each on one of `n` parameter points strided evenly over the 8192-point grid."""
+    w = make_sweep_shard(T, 0, n, states_per_point=states_per_point, seed=seed)
+    grid = sweep_grid()
+    pts = (np.arange(n) * (grid.shape[0] // max(n, 1))) % grid.shape[0]
+    for col, key in enumerate(["dt", "w_perp", "w_para", "R_a", "R_d", "Rd_a", "Rd_d"]):
+        w["params"][:, PARAM_INDEX[key]] = grid[pts, col]
+    w["name"] = f"sweep_T{T}_sample{n}"
+    return w
+
+
 # The zero-valued points of the reference's sweep lists (mpc_sensitivity_analysis_comulative.py:103-128), each on the
 # sensitivity base configuration (mpc_config_sensitivity.json: R = [0.1, 0.01], Rd = [10, 10]): a vanishing weight
 # can leave the optimiser non-unique in the controls, so this side set is judged on cost and states only.

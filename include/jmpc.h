@@ -246,6 +246,30 @@ int32_t jmpc_episode_post_dev(jmpc_handle h, int32_t B, double* state, const int
                               int32_t* warm, double* history_base, int32_t history_rows, int32_t* flags_base,
                               const int32_t* flag, const int32_t* iter_dev, double dt_loop, void* stream);
 int32_t jmpc_counter_add(jmpc_handle h, int32_t* counter, int32_t delta, void* stream);
+
+/* The reference's scripted obstacles on the device (main/lib/moving_obstacles.py: MovingObstacleTIntersection :166-232,
+ * MovingObstacleRoundabout :28-123 including its dt = 0.2 quirk at :45 and the theta overwrite inside its steering
+ * property, MovingObstacleArterial :125-164).  DEVICE pointers.
+ *   script [B][n_obs][JMPC_OBS_SCRIPT_LEN]  constant description of each obstacle (enum jmpc_obs_script)
+ *   model  [B][n_obs][4]   in-out: Bicycle xc, yc, theta, step counter
+ *   obstacles [B][n_obs][6] out: what `get()` returns (x, y, forward_velocity, theta, 0, steering_angle), the tuple
+ *             jmpc_collision consumes
+ *   advance: 0 = only evaluate get() (before the first loop iteration), 1 = step() first (moving_obstacles.py:113-116)
+ * Episodes with done != 0 are left untouched. */
+enum jmpc_obs_kind { JMPC_OBS_CONSTANT = 0, JMPC_OBS_TINTERSECTION = 1, JMPC_OBS_ROUNDABOUT = 2, JMPC_OBS_ARTERIAL = 3 };
+enum jmpc_obs_script {
+  JMPC_OBS_KIND = 0,     /* jmpc_obs_kind                                                                     */
+  JMPC_OBS_DIRECTION,    /* +1 left to right, -1 right to left                        moving_obstacles.py:41 */
+  JMPC_OBS_TURNING,      /* 0 / 1                                                                             */
+  JMPC_OBS_SPEED,        /* forward speed once moving                                                         */
+  JMPC_OBS_OFFSET,       /* seconds before it starts moving; <= 0: moves at once           :44, :107-111      */
+  JMPC_OBS_DT_MODEL,     /* Bicycle.sample_time (the constructor's dt)                                        */
+  JMPC_OBS_DT_OFFSET,    /* dt of the offset test: the constructor's dt, 0.2 for the roundabout class (:45)   */
+  JMPC_OBS_AUX,          /* roundabout: arctan(L / 5), the turning steer angle (:15-25); arterial: initial speed */
+  JMPC_OBS_SCRIPT_LEN
+};
+int32_t jmpc_scripted_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, const double* script, double* model,
+                                    double* obstacles, const int32_t* done, int32_t advance, void* stream);
 int32_t jmpc_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, double* obstacles, const int32_t* done,
                            double dt, void* stream);
 

@@ -477,8 +477,47 @@ def run_new_ref_episode(courses, max_steps=400):
     return out
 
 
+def record_scripted_obstacles(steps=160):
+    """The reference's scripted obstacles (main/lib/moving_obstacles.py) stepped as the scenario loops step them:
+    `get()` (whose steering property has side effects on the roundabout model) then `step()`.  One row per spec:
+    [kind, direction, turning, speed, offset (-1 = None), dt, x_init, y_init, initial_speed]."""
+    import contextlib
+    import io
+    from lib.car_dimensions import BicycleModelDimensions
+    from lib.moving_obstacles import MovingObstacleArterial, MovingObstacleRoundabout, MovingObstacleTIntersection
+    cd = BicycleModelDimensions(skip_back_circle_collision_checking=False)
+    specs, tracks = [], []
+    for kind, cls in [(1, MovingObstacleTIntersection), (2, MovingObstacleRoundabout)]:
+        for direction in (1, -1):
+            for turning in (False, True):
+                for speed, offset, dt in [(25 / 3.6, 2.0, 0.2), (25 / 3.6, 4.0, 0.2), (30 / 3.6, None, 0.2),
+                                          (20 / 3.6, 3.0, 0.2), (15 / 3.6, 0.0, 0.1), (25 / 3.6, 1.0, 0.2)]:
+                    o = cls(cd, direction=direction, turning=turning, speed=speed, offset=offset, dt=dt)
+                    rows = []
+                    with contextlib.redirect_stdout(io.StringIO()):         # the roundabout property prints
+                        for _ in range(steps):
+                            rows.append(list(o.get()))
+                            o.step()
+                    specs.append([kind, direction, float(turning), speed, -1.0 if offset is None else offset, dt, 0, 0, 0])
+                    tracks.append(rows)
+    for x0, y0, speed, v_init, offset in [(3.0, -20.0, 25 / 3.6, 5 / 3.6, 2.0), (-3.0, -35.0, 30 / 3.6, 0.0, None),
+                                          (1.5, -10.0, 20 / 3.6, 10 / 3.6, 5.0)]:
+        o = MovingObstacleArterial(cd, x_init=x0, y_init=y0, speed=speed, initial_speed=v_init, offset=offset, dt=0.2)
+        rows = []
+        for _ in range(steps):
+            rows.append(list(o.get()))
+            o.step()
+        specs.append([3, 1, 0.0, speed, -1.0 if offset is None else offset, 0.2, x0, y0, v_init])
+        tracks.append(rows)
+    print(f"scripted obstacles: {len(specs)} specs x {steps} steps")
+    return dict(specs=np.array(specs, float), tracks=np.array(tracks, float))
+
+
 def main():
     install_shims()
+    if "--obstacles" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "scripted_obstacles.npz"), **record_scripted_obstacles())
+        return
     rng = np.random.default_rng(20261018)
     courses = plan_courses()
     np.savez_compressed(os.path.join(HERE, "courses.npz"), **courses)
@@ -487,6 +526,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"episode_{kind}.npz"), **run_episode(kind, courses))
     np.savez_compressed(os.path.join(HERE, "sensitivity_runs.npz"), **run_sensitivity_runs(courses))
     np.savez_compressed(os.path.join(HERE, "episode_new_ref.npz"), **run_new_ref_episode(courses))
+    np.savez_compressed(os.path.join(HERE, "scripted_obstacles.npz"), **record_scripted_obstacles())
 
 
 if __name__ == "__main__":

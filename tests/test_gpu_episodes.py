@@ -21,18 +21,33 @@ def jm():
     return synth, BatchedMPC, BatchedEpisodes
 
 
+# the scripted obstacles of the two reference scenarios (mpc_intersection.py:46-49, mpc_roundabout.py:48-51)
+SCENARIO_OBSTACLES = {
+    "intersection": [dict(kind="t_intersection", direction=1, offset=2., turning=False, speed=25 / 3.6, dt=0.2),
+                     dict(kind="t_intersection", direction=-1, offset=4., turning=True, speed=25 / 3.6, dt=0.2)],
+    "roundabout": [dict(kind="roundabout", direction=1, offset=1., turning=True, speed=25 / 3.6, dt=0.2),
+                   dict(kind="roundabout", direction=-1, offset=4., turning=True, speed=25 / 3.6, dt=0.2)],
+}
+
+
+@pytest.mark.parametrize("obstacle_source", ["device_program", "recording"])
 @pytest.mark.parametrize("name", ["intersection", "roundabout"])
-def test_replay_of_reference_episode(jm, golden_dir, name):
-    """Config 1 on the device: obstacles scripted from the recording, everything else computed by the kernels."""
+def test_replay_of_reference_episode(jm, golden_dir, name, obstacle_source):
+    """Config 1 on the device.  "device_program": nothing comes from the recording but the initial state -- the
+    reference's scripted obstacles (moving_obstacles.py) are stepped by a kernel too (obstacle_script=None);
+    "recording": their poses are replayed from the fixture, everything else is computed by the kernels."""
     synth, BatchedMPC, BatchedEpisodes = jm
+    from junction_mpc.episodes import scripted_obstacles
     e = np.load(os.path.join(golden_dir, f"episode_{name}.npz"))
     course = e["course_smoothed"]
     n = len(e["state"])
     engine = BatchedMPC([course], dl=float(e["dl"]), T=13, max_batch=8)
     state0 = np.repeat(e["state"][:1], 3, axis=0)                      # three identical egos
-    script = np.repeat(e["obs"][:, None], 3, axis=1)                   # [steps, B, n_obs, 6]
-    ep = BatchedEpisodes(engine, state0, obstacle_script=script, frame_window=int(e["frame_window"]),
-                         margin=int(e["margin"]), max_steps=160)
+    if obstacle_source == "recording":
+        kw = dict(obstacle_script=np.repeat(e["obs"][:, None], 3, axis=1))      # [steps, B, n_obs, 6]
+    else:
+        kw = dict(obstacle_script=None, obstacle_program=scripted_obstacles([SCENARIO_OBSTACLES[name]] * 3))
+    ep = BatchedEpisodes(engine, state0, frame_window=int(e["frame_window"]), margin=int(e["margin"]), max_steps=160, **kw)
     res = ep.run(check_every=4)
     assert (res["done"] == 1).all()
     assert (res["steps"] == n).all()                                    # 91 / 116 iterations, as the reference
@@ -146,3 +161,35 @@ def test_graph_replay_equals_plain_launches(jm):
     n = int(a["steps"].max())
     assert np.array_equal(a["history"][:n], b["history"][:n], equal_nan=True)
     assert np.array_equal(a["flags"][:n], b["flags"][:n])
+
+
+def test_scripted_obstacles_match_the_reference_tracks(jm, golden_dir):
+    """The reference's MovingObstacleTIntersection / Roundabout / Arterial, 51 parameter combinations x 160 steps
+    recorded from its own classes: the device kernel reproduces every get() tuple."""
+    import ctypes as Ct
+    import torch
+    synth, BatchedMPC, BatchedEpisodes = jm
+    from junction_mpc import _cabi
+    from junction_mpc.episodes import scripted_obstacles
+    z = np.load(os.path.join(golden_dir, "scripted_obstacles.npz"))
+    specs, tracks = z["specs"], z["tracks"]
+    kinds = {1: "t_intersection", 2: "roundabout", 3: "arterial"}
+    rows = [[dict(kind=kinds[int(s[0])], direction=int(s[1]), turning=bool(s[2]), speed=float(s[3]),
+                  offset=None if s[4] < 0 else float(s[4]), dt=float(s[5]), x_init=float(s[6]), y_init=float(s[7]),
+                  initial_speed=float(s[8]))] for s in specs]
+    script, model = scripted_obstacles(rows)
+    B = len(rows)
+    engine = BatchedMPC([synth.load_course("intersection")], dl=0.083, T=13, max_batch=64)
+    dev = torch.device("cuda", 0)
+    d_script, d_model = torch.as_tensor(script, device=dev), torch.as_tensor(model, device=dev)
+    d_obs = torch.zeros(B, 1, 6, dtype=torch.float64, device=dev)
+    p = lambda t: Ct.c_void_p(t.data_ptr())        # noqa: E731
+    got = []
+    for i in range(tracks.shape[1]):
+        _cabi.check(engine._lib.jmpc_scripted_obstacle_step(engine._h, B, 1, p(d_script), p(d_model), p(d_obs), None,
+                                                            0 if i == 0 else 1, None), "jmpc_scripted_obstacle_step")
+        got.append(d_obs[:, 0].cpu().numpy().copy())
+    got = np.stack(got, axis=1)                     # [B, steps, 6]
+    # discrete outputs (speed on / off, steering rule) exact; poses to rounding of sin / cos / tan
+    assert np.array_equal(got[:, :, 2], tracks[:, :, 2]) and np.array_equal(got[:, :, 5], tracks[:, :, 5])
+    np.testing.assert_allclose(got, tracks, rtol=0, atol=1e-9)
