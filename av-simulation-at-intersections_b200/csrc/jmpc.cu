@@ -13,6 +13,7 @@
 #include "jmpc_collision.cuh"
 #include "jmpc_step.cuh"
 #include "jmpc_episode.cuh"
+#include "jmpc_planner.cuh"
 
 namespace {
 
@@ -581,6 +582,9 @@ int32_t jmpc_step_host_io(jmpc_handle h, int32_t B, int32_t T, const double* sta
     return fail("jmpc_step_host: NULL array");
   if (h->n_courses < 1) return fail("jmpc_step_host: no courses uploaded (jmpc_set_courses)");
   if (h->skip) return fail("jmpc_step_host: a skip mask is set (jmpc_set_skip_mask is for the device entry points)");
+  if (course_id)             // host arrays can be validated (the device entry points clamp instead, jmpc_step.cuh)
+    for (int k = 0; k < B; ++k)
+      if (course_id[k] < 0 || course_id[k] >= h->n_courses) return fail("jmpc_step_host: course_id out of range");
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   const size_t T1 = T + 1, b = (size_t)B;
@@ -726,7 +730,7 @@ int32_t jmpc_collision(jmpc_handle h, int32_t B, const int32_t* course_id, const
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   jmpc::CollisionArgs a;
-  a.B = B; a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
+  a.B = B; a.n_courses = h->n_courses; a.cx = h->d_cx; a.cy = h->d_cy; a.cyaw = h->d_cyaw; a.course_n = h->d_course_n;
   a.ccfx = h->d_ccfx; a.ccfy = h->d_ccfy; a.ccrx = h->d_ccrx; a.ccry = h->d_ccry;
   a.arc_tab = h->d_arc; a.arc_off = h->d_arc_off;
 #ifdef JMPC_EXPERIMENT
@@ -765,6 +769,9 @@ int32_t jmpc_collision_host(jmpc_handle h, int32_t B, const int32_t* course_id, 
   if (n_obs < 0 || n_obs > jmpc::kMaxObstacles) return fail("jmpc_collision_host: n_obs out of range");
   if (n_obs > 0 && !obstacles) return fail("jmpc_collision_host: obstacles is NULL");
   if (h->skip) return fail("jmpc_collision_host: a skip mask is set (jmpc_set_skip_mask is for the device entry points)");
+  if (course_id)
+    for (int k = 0; k < B; ++k)
+      if (course_id[k] < 0 || course_id[k] >= h->n_courses) return fail("jmpc_collision_host: course_id out of range");
   if (B == 0) return 0;
   CK(cudaSetDevice(h->device));
   const size_t b = (size_t)B;
@@ -945,6 +952,106 @@ int32_t jmpc_scripted_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, con
   CK(cudaGetLastError());
   h->launches++;
   return 0;
+}
+
+int32_t jmpc_plan_host(int32_t device, int32_t B, int32_t n_mp, int32_t n_pts, int32_t n_cc, const double* mp_pts,
+                       const double* mp_len, const double* mp_cc, int32_t n_scenes, int32_t max_obs, const double* hp,
+                       const int32_t* hp_n, const int32_t* n_obs, const int32_t* scene_id, const double* start,
+                       const double* goal_point, const double* goal_area, const double* allowed, const double* weights,
+                       int32_t max_expansions, int32_t max_path, int32_t max_log, double* cost, int32_t* status,
+                       int32_t* n_path, double* path, int32_t* path_mp, int32_t* n_traj, double* traj,
+                       int32_t* expansions, double* log, double* kernel_ms) {
+  if (!mp_pts || !mp_len || !mp_cc || !hp || !hp_n || !n_obs || !start || !goal_point || !goal_area || !allowed || !weights ||
+      !cost || !status || !n_path || !path || !path_mp || !n_traj || !traj || !expansions)
+    return fail("jmpc_plan_host: NULL argument");
+  if (B < 0 || n_mp < 1 || n_mp > 32 || n_pts < 2 || n_cc < 1 || n_scenes < 1 || max_obs < 0)
+    return fail("jmpc_plan_host: size out of range (1 <= n_mp <= 32)");
+  if (max_expansions < 1 || max_path < 2 || max_log < 0) return fail("jmpc_plan_host: limits out of range");
+  for (int s = 0; s < n_scenes; ++s) {
+    if (n_obs[s] < 0 || n_obs[s] > max_obs) return fail("jmpc_plan_host: n_obs out of range");
+    for (int o = 0; o < n_obs[s]; ++o)
+      if (hp_n[(size_t)s * max_obs + o] < 1 || hp_n[(size_t)s * max_obs + o] > JMPC_PLAN_MAX_HP)
+        return fail("jmpc_plan_host: hp_n out of range");
+  }
+  if (scene_id)
+    for (int b = 0; b < B; ++b)
+      if (scene_id[b] < 0 || scene_id[b] >= n_scenes) return fail("jmpc_plan_host: scene_id out of range");
+  if (B == 0) return 0;
+  int count = 0;
+  CK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail("jmpc_plan_host: no such CUDA device");
+  CK(cudaSetDevice(device));
+  jmpc::PlanArgs a;
+  memset(&a, 0, sizeof a);
+  a.B = B; a.n_mp = n_mp; a.n_pts = n_pts; a.n_cc = n_cc; a.max_obs = max_obs;
+  a.max_expansions = max_expansions; a.max_path = max_path; a.max_traj = (max_path - 1) * (n_pts - 1); a.max_log = max_log;
+  a.pool_cap = max_expansions * n_mp + 1;
+  int ts = 64;
+  while (ts < 2 * max_expansions + 2) ts <<= 1;
+  a.table_size = ts;
+  const size_t b = (size_t)B;
+  // one device block [inputs | workspace | results]
+  size_t off = 0;
+  auto seg = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  const size_t hp_doubles = (size_t)n_scenes * max_obs * JMPC_PLAN_MAX_HP * 3;
+  const size_t o_pts = seg((size_t)n_mp * n_pts * 3 * 8), o_len = seg((size_t)n_mp * 8), o_cc = seg((size_t)n_mp * n_cc * 2 * 8);
+  const size_t o_hp = seg(hp_doubles * 8), o_hpn = seg((size_t)n_scenes * max_obs * 4 + 4), o_nobs = seg((size_t)n_scenes * 4);
+  const size_t o_sid = seg(b * 4), o_start = seg(b * 24), o_goal = seg(b * 24), o_area = seg(b * 32), o_allow = seg(b * 8);
+  const size_t o_w = seg(b * 72);
+  const size_t o_pool = seg(b * a.pool_cap * sizeof(jmpc::PlanNode)), o_heap = seg(b * a.pool_cap * 4), o_tab = seg(b * ts * 4);
+  const size_t o_res = off;
+  const size_t o_cost = seg(b * 8), o_status = seg(b * 4), o_npath = seg(b * 4), o_path = seg(b * max_path * 24);
+  const size_t o_pmp = seg(b * max_path * 4), o_ntraj = seg(b * 4), o_traj = seg(b * a.max_traj * 24), o_exp = seg(b * 4);
+  const size_t o_log = seg(log ? b * max_log * 40 : 0);
+  char* d = nullptr;
+  cudaError_t err = cudaMalloc(&d, off);
+  if (err != cudaSuccess) return fail("jmpc_plan_host: workspace allocation failed (lower max_expansions or B)", err);
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = 0;
+  auto up = [&](size_t o, const void* src, size_t bytes) {
+    if (!rc && bytes && cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = fail("jmpc_plan_host: upload failed");
+  };
+  auto down = [&](void* dst, size_t o, size_t bytes) {
+    if (!rc && bytes && cudaMemcpyAsync(dst, d + o, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail("jmpc_plan_host: download failed");
+  };
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess ||
+      cudaEventCreate(&e1) != cudaSuccess)
+    rc = fail("jmpc_plan_host: stream / event creation failed");
+  up(o_pts, mp_pts, (size_t)n_mp * n_pts * 24); up(o_len, mp_len, (size_t)n_mp * 8); up(o_cc, mp_cc, (size_t)n_mp * n_cc * 16);
+  up(o_hp, hp, hp_doubles * 8); up(o_hpn, hp_n, (size_t)n_scenes * max_obs * 4); up(o_nobs, n_obs, (size_t)n_scenes * 4);
+  if (scene_id) up(o_sid, scene_id, b * 4);
+  up(o_start, start, b * 24); up(o_goal, goal_point, b * 24); up(o_area, goal_area, b * 32); up(o_allow, allowed, b * 8);
+  up(o_w, weights, b * 72);
+  if (!rc) {
+    a.mp_pts = (const double*)(d + o_pts); a.mp_len = (const double*)(d + o_len); a.mp_cc = (const double*)(d + o_cc);
+    a.hp = (const double*)(d + o_hp); a.hp_n = (const int*)(d + o_hpn); a.n_obs = (const int*)(d + o_nobs);
+    a.scene_id = scene_id ? (const int*)(d + o_sid) : nullptr;
+    a.start = (const double*)(d + o_start); a.goal_point = (const double*)(d + o_goal); a.goal_area = (const double*)(d + o_area);
+    a.allowed = (const double*)(d + o_allow); a.weights = (const double*)(d + o_w);
+    a.pool = (jmpc::PlanNode*)(d + o_pool); a.heap = (int*)(d + o_heap); a.table = (int*)(d + o_tab);
+    a.cost = (double*)(d + o_cost); a.status = (int*)(d + o_status); a.n_path = (int*)(d + o_npath); a.path = (double*)(d + o_path);
+    a.path_mp = (int*)(d + o_pmp); a.n_traj = (int*)(d + o_ntraj); a.traj = (double*)(d + o_traj); a.expansions = (int*)(d + o_exp);
+    a.log = log ? (double*)(d + o_log) : nullptr;
+    if (cudaMemsetAsync(d + o_res, 0, off - o_res, st) != cudaSuccess) rc = fail("jmpc_plan_host: memset failed");
+  }
+  if (!rc) {
+    cudaEventRecord(e0, st);
+    jmpc::plan_kernel<<<(B + 3) / 4, 128, 0, st>>>(a);
+    cudaEventRecord(e1, st);
+    if ((err = cudaGetLastError()) != cudaSuccess) rc = fail("jmpc_plan_host: launch failed", err);
+  }
+  down(cost, o_cost, b * 8); down(status, o_status, b * 4); down(n_path, o_npath, b * 4); down(path, o_path, b * max_path * 24);
+  down(path_mp, o_pmp, b * max_path * 4); down(n_traj, o_ntraj, b * 4); down(traj, o_traj, b * a.max_traj * 24);
+  down(expansions, o_exp, b * 4);
+  if (log) down(log, o_log, b * max_log * 40);
+  if (!rc && (err = cudaStreamSynchronize(st)) != cudaSuccess) rc = fail("jmpc_plan_host: kernel failed", err);
+  if (!rc && kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *kernel_ms = ms; }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  cudaFree(d);
+  return rc;
 }
 
 int64_t jmpc_launch_count(jmpc_handle h) { return h ? h->launches : 0; }

@@ -27,7 +27,7 @@ constexpr int kMaxEgoFrames = 160;     // points kept by resample_curve (<= 49 i
 struct ParamBlock { double v[JMPC_NPARAM]; };
 
 struct CollisionArgs {
-  int B;
+  int B, n_courses;
   const double* cx; const double* cy; const double* cyaw;
   const double* ccfx; const double* ccfy; const double* ccrx; const double* ccry;   // circle-centre tables
   const int* course_n; int course_stride;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) collision_kernel(const CollisionArgs A) {
   const double* prm = A.params ? A.params + (size_t)b * JMPC_NPARAM : A.defaults.v;
   const double dt = prm[JMPC_P_DT], L = prm[JMPC_P_L];
   const double max_accel = prm[JMPC_P_MAX_ACCEL], max_speed = prm[JMPC_P_SIM_MAX_SPEED];
-  const int cid = A.course_id ? A.course_id[b] : 0;
+  const int cid = A.course_id ? min(max(A.course_id[b], 0), A.n_courses - 1) : 0;
   const size_t coff = (size_t)cid * A.course_stride;
   const double* cx = A.cx + coff; const double* cy = A.cy + coff;
   const double* fx = A.ccfx + coff; const double* fy = A.ccfy + coff;

@@ -324,7 +324,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
   const int n = 2 * T, T1 = T + 1, nb = nblk(n), n4 = nb << 2;
   WarpMem M(smem_base, T);
   auto P = [&](int k) -> double { return M.prm[k]; };
-  const int cid = A.course_id ? A.course_id[b] : 0;
+  const int cid = A.course_id ? min(max(A.course_id[b], 0), A.n_courses - 1) : 0;     // device arrays are clamped, host arrays validated
   const double* cx = A.cx + (size_t)cid * A.course_stride;
   const double* cy = A.cy + (size_t)cid * A.course_stride;
   const double* cyaw = A.cyaw + (size_t)cid * A.course_stride;
@@ -857,7 +857,7 @@ __device__ __noinline__ bool step_output(const StepArgs& A, int b, bool active, 
   const double v0 = A.state[(size_t)b * 4 + 2], yaw0 = A.state[(size_t)b * 4 + 3];
   const double dt = P(JMPC_P_DT), Lw = P(JMPC_P_L);
   // per-lane data of phase A, re-read or recomputed instead of being held in registers across the solve
-  const int cid = A.course_id ? A.course_id[b] : 0;
+  const int cid = A.course_id ? min(max(A.course_id[b], 0), A.n_courses - 1) : 0;
   double xr = 0.0, yr = 0.0, psir = 0.0, vr = 0.0, vb = 0.0, th = 0.0;
   if (gl <= T) {
     const size_t off = (size_t)cid * A.course_stride + idx;

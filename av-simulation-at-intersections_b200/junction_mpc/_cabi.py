@@ -60,6 +60,8 @@ SIGNATURES = {
     "jmpc_obstacle_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "jmpc_scripted_obstacle_step": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_int32, C.c_void_p]),
+    "jmpc_plan_host": (C.c_int32, [C.c_int32] * 5 + [C.c_void_p] * 3 + [C.c_int32] * 2 + [C.c_void_p] * 9 + [C.c_int32] * 3
+                       + [C.c_void_p] * 10),
     "jmpc_launch_count": (C.c_int64, [C.c_void_p]),
     "jmpc_measure_fma_peak": (C.c_int32, [C.c_void_p, c_f64p, c_f64p]),
     "jmpc_debug_linalg": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

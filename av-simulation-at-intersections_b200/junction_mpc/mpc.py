@@ -308,13 +308,20 @@ def install(reference_main: Optional[str] = None) -> None:
     ws.MAX_SPEED = WITH_SPEED_MAX_SPEED
     ws.MPC = type("MPC", (_WithSpeedMPC,), {})
     sys.modules["lib.mpc_with_speed"] = ws
+    from . import planner as _planner          # the planner drop-in
+    pl = types.ModuleType("lib.mp_search_ww_generic")
+    pl.__doc__ = "junction_mpc drop-in for the reference module lib.mp_search_ww_generic"
+    pl.MotionPrimitiveSearch = _planner.MotionPrimitiveSearch
+    sys.modules["lib.mp_search_ww_generic"] = pl
     try:                                   # `import lib.mpc` also needs the attribute on the package
         import lib                         # the reference's package, when reference_main is on sys.path
         lib.mpc = sys.modules["lib.mpc"]
         lib.mpc_sensitivity = sys.modules["lib.mpc_sensitivity"]
         lib.mpc_with_speed = ws
+        lib.mp_search_ww_generic = pl
     except ImportError:
         pkg = types.ModuleType("lib")
         pkg.__path__ = []
         pkg.mpc, pkg.mpc_sensitivity, pkg.mpc_with_speed = sys.modules["lib.mpc"], sys.modules["lib.mpc_sensitivity"], ws
+        pkg.mp_search_ww_generic = pl
         sys.modules["lib"] = pkg

@@ -273,6 +273,40 @@ int32_t jmpc_scripted_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, con
 int32_t jmpc_obstacle_step(jmpc_handle h, int32_t B, int32_t n_obs, double* obstacles, const int32_t* done,
                            double dt, void* stream);
 
+/* Batched motion-primitive A* planner: B independent searches, one warp each.  Replaces
+ * MotionPrimitiveSearch.run (main/lib/mp_search_ww_generic.py:136-140 -> AStar.run, main/lib/a_star.py:31-78,
+ * neighbour / cost / heuristic / goal functions :147-243, path_to_full_trajectory :245-256, collision test
+ * main/lib/obstacles.py:157-176).  HOST pointers; no handle: the call allocates its workspace on `device`, runs, copies
+ * the results back and frees it.
+ *   primitives  mp_pts [n_mp][n_pts][3] points relative to the start pose, mp_len [n_mp] total_length,
+ *               mp_cc [n_mp][n_cc][2] collision-check points (resampled at the car radius, one per collision circle,
+ *               mp_search_ww_generic.py:121-138 -- derived on the host, once per primitive set)
+ *   scenes      hp [n_scenes][max_obs][JMPC_PLAN_MAX_HP][3] half-plane rows a, b, c of every obstacle
+ *               (Obstacle.to_convex(margin), obstacles.py:83-95,135-150), hp_n [n_scenes][max_obs] rows used,
+ *               n_obs [n_scenes]; scene_id [B] or NULL (all scene 0)
+ *   searches    start, goal_point [B][3]; goal_area [B][4] = x1, y1, x2, y2 of the goal box; allowed [B]
+ *               allowed_goal_theta_difference; weights [B][9] = wh_dist, wh_theta, wh_steering, wh_obstacle,
+ *               wh_center, wc_dist, wc_steering, wc_obstacle, wc_center (mp_search_ww_generic.py:27-31)
+ *   limits      max_expansions nodes expanded per search, max_path nodes per path
+ *   results     cost [B] (NaN unless found), status [B] (jmpc_plan_status), n_path [B], path [B][max_path][3],
+ *               path_mp [B][max_path] primitive index of every edge, n_traj [B],
+ *               traj [B][(max_path-1)*(n_pts-1)][3] = trajectory_full, expansions [B];
+ *               log [B][max_log][5] or NULL: g, h, x, y, theta of every expanded node in order (AStar debug data);
+ *               kernel_ms or NULL: duration of the search kernel by CUDA events */
+#define JMPC_PLAN_MAX_HP 8
+enum jmpc_plan_status {
+  JMPC_PLAN_FOUND = 0,
+  JMPC_PLAN_NO_SOLUTION = 1,  /* the open list ran empty: the reference raises "No solution found." (a_star.py:78) */
+  JMPC_PLAN_LIMIT = 2         /* max_expansions / max_path reached (the reference has no limit)                  */
+};
+int32_t jmpc_plan_host(int32_t device, int32_t B, int32_t n_mp, int32_t n_pts, int32_t n_cc, const double* mp_pts,
+                       const double* mp_len, const double* mp_cc, int32_t n_scenes, int32_t max_obs, const double* hp,
+                       const int32_t* hp_n, const int32_t* n_obs, const int32_t* scene_id, const double* start,
+                       const double* goal_point, const double* goal_area, const double* allowed, const double* weights,
+                       int32_t max_expansions, int32_t max_path, int32_t max_log, double* cost, int32_t* status,
+                       int32_t* n_path, double* path, int32_t* path_mp, int32_t* n_traj, double* traj,
+                       int32_t* expansions, double* log, double* kernel_ms);
+
 /* Number of kernel launches issued through this handle since creation (for bench.py's gpu_launches). */
 int64_t jmpc_launch_count(jmpc_handle h);
 

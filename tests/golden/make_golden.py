@@ -513,8 +513,105 @@ def record_scripted_obstacles(steps=160):
     return dict(specs=np.array(specs, float), tracks=np.array(tracks, float))
 
 
+def record_planner(max_seconds=20):
+    """The reference's motion-primitive A* (main/lib/mp_search_ww_generic.py + a_star.py) on scenario / weight
+    variants: inputs as plain arrays (start, goal, goal area, obstacle half-planes, weights) and what the search
+    returned (cost, node path, primitive per edge, full trajectory, the order in which nodes were expanded)."""
+    import signal
+    from lib.car_dimensions import BicycleModelDimensions
+    from lib.motion_primitive import load_motion_primitives
+    from lib.mp_search_ww_generic import MotionPrimitiveSearch
+    from envs.intersection import intersection
+    from envs.roundabout import roundabout
+    from envs.intersection_multi_lanes import intersection as intersection_ml
+    from envs.t_intersection import t_intersection
+
+    cd = BicycleModelDimensions(skip_back_circle_collision_checking=False)
+    mps = load_motion_primitives(version="bicycle_model")
+    names = sorted(mps)
+    out = {"mp_names": np.array(names), "mp_points": np.stack([mps[n].points for n in names]),
+           "mp_total_length": np.array([mps[n].total_length for n in names]),
+           "car_radius": np.array(cd.radius), "car_circle_centers": np.array(cd.circle_centers)}
+    variants = []
+    for sp in (1, 2, 3, 4):
+        for ti in (1, 2, 3):
+            variants.append((f"intersection_{sp}_{ti}", lambda sp=sp, ti=ti: intersection(start_pos=sp, turn_indicator=ti), {}))
+    for sp in (1, 2, 3, 4):
+        for ti in (1, 2, 3, 4):
+            variants.append((f"roundabout_{sp}_{ti}_big", lambda sp=sp, ti=ti: roundabout(start_pos=sp, turn_indicator=ti, size="big"), {}))
+    for sp, ti in [(1, 1), (1, 2), (2, 3), (3, 1)]:
+        variants.append((f"roundabout_{sp}_{ti}_normal", lambda sp=sp, ti=ti: roundabout(start_pos=sp, turn_indicator=ti), {}))
+    for sp, ti, sl, gl in [(1, 1, 1, 1), (1, 1, 2, 2), (1, 2, 1, 2), (2, 3, 2, 1), (3, 1, 1, 2), (4, 2, 2, 2)]:
+        variants.append((f"multilane_{sp}_{ti}_{sl}_{gl}",
+                         lambda sp=sp, ti=ti, sl=sl, gl=gl: intersection_ml(start_pos=sp, turn_indicator=ti, start_lane=sl,
+                                                                          goal_lane=gl, number_of_lanes=2), {}))
+    for sp, ti in [(1, 1), (1, 3), (2, 2), (2, 3)]:
+        variants.append((f"t_intersection_{sp}_{ti}", lambda sp=sp, ti=ti: t_intersection(start_pos=sp, turn_indicator=ti), {}))
+    # weight variants of the reference's default scene (the knobs of mp_search_ww_generic.py:27-31)
+    for k, w in enumerate([dict(wh_theta=1.0), dict(wh_steering=5.0), dict(wc_steering=1.0), dict(wh_dist=1.5, wc_dist=0.8),
+                           dict(wh_obstacle=0.2, wc_obstacle=0.5), dict(wh_center=0.1, wc_center=0.1),
+                           dict(wh_theta=4.0, wh_steering=25.0), dict(wc_obstacle=1.0, wh_obstacle=0.05)]):
+        variants.append((f"intersection_1_1_w{k}", lambda: intersection(start_pos=1, turn_indicator=1), w))
+        variants.append((f"roundabout_1_4_big_w{k}", lambda: roundabout(start_pos=1, turn_indicator=4, size="big"), w))
+
+    class _Timeout(Exception):
+        pass
+
+    def _alarm(*_):
+        raise _Timeout()
+    signal.signal(signal.SIGALRM, _alarm)
+    wkeys = ["wh_dist", "wh_theta", "wh_steering", "wh_obstacle", "wh_center", "wc_dist", "wc_steering", "wc_obstacle", "wc_center"]
+    defaults = dict(wh_dist=1.0, wh_theta=2.7, wh_steering=15.0, wh_obstacle=0.0, wh_center=0.0, wc_dist=1.0, wc_steering=5.0,
+                    wc_obstacle=0.1, wc_center=0.0)
+    kept = []
+    for name, make, w in variants:
+        try:
+            scen = make()
+        except Exception as exc:          # noqa: BLE001  (some start / turn combinations do not exist in an env)
+            print(f"planner variant {name}: scenario not available ({type(exc).__name__})")
+            continue
+        search = MotionPrimitiveSearch(scen, cd, mps, margin=cd.radius, **w)
+        signal.alarm(max_seconds)
+        try:
+            cost, path, traj = search.run(debug=True)
+        except _Timeout:
+            print(f"planner variant {name}: more than {max_seconds} s, skipped")
+            continue
+        except Exception as exc:          # noqa: BLE001
+            if "No solution" not in str(exc) or name not in ("roundabout_2_3_big", "roundabout_4_4_big"):
+                print(f"planner variant {name}: {exc}")
+                continue
+            cost, path, traj = float("nan"), [], np.zeros((0, 3))      # the open list ran empty (a_star.py:78)
+        finally:
+            signal.alarm(0)
+        hp = search._obstacles_hp
+        hp_tab = np.zeros((len(hp), 8, 3))
+        hp_n = np.array([len(h) for h in hp])
+        for k, h in enumerate(hp):
+            hp_tab[k, :len(h)] = h
+        ww = dict(defaults, **w)
+        mp_idx = [names.index(search._points_to_mp_names[a, b]) for a, b in zip(path[:-1], path[1:])]
+        pre = f"{name}/"
+        out.update({pre + "start": np.array(scen.start, float), pre + "goal_point": np.array(scen.goal_point, float),
+                    pre + "goal_area": np.array([*scen.goal_area.xy1, *scen.goal_area.xy2], float),
+                    pre + "allowed_dtheta": np.array(scen.allowed_goal_theta_difference), pre + "hp": hp_tab, pre + "hp_n": hp_n,
+                    pre + "weights": np.array([ww[k] for k in wkeys]), pre + "cost": np.array(cost),
+                    pre + "path": np.array(path, float).reshape(-1, 3), pre + "mp_idx": np.array(mp_idx), pre + "trajectory": traj,
+                    pre + "expanded": np.array([[d.g, d.h, *d.node] for d in search.debug_data], float)})
+        kept.append(name)
+        print(f"planner variant {name}: cost {cost:.6f}, {len(path)} nodes, {len(search.debug_data)} expansions, traj {traj.shape}")
+    out["variants"] = np.array(kept)
+    # the collision-check points the reference derives per primitive (mp_search_ww_generic.py:121-138), for the
+    # host-side restatement of that derivation
+    out["mp_collision_points"] = np.stack([search._mp_collision_points[n] for n in names])
+    return out
+
+
 def main():
     install_shims()
+    if "--planner" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "planner.npz"), **record_planner())
+        return
     if "--obstacles" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "scripted_obstacles.npz"), **record_scripted_obstacles())
         return
