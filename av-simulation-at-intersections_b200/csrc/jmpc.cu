@@ -64,12 +64,16 @@ struct jmpc_handle_s {
   double* peer_rec[JMPC_MAX_PEERS] = {};
   int n_peers = 0;
   long long rank_offset = 0;
+  unsigned long long* peer_flag[JMPC_MAX_PEERS] = {};      // jmpc_set_record_flags
+  int n_flag_peers = 0;
+  unsigned long long gather_step = 0;
+  int* d_gather_timeout = nullptr;
   bool collision_attr_set = false;
   const int* skip = nullptr;           // jmpc_set_skip_mask
   // longest-first scheduling (jmpc_set_schedule)
   int host_transfer = 1;               // jmpc_set_host_transfer
   int schedule = 0;                     // 0 index order, 1 a-priori key, 2 previous step's iteration counts (+ 1 as fallback)
-  int* d_order = nullptr; int* d_hint = nullptr;
+  int* d_order = nullptr; int* d_hint = nullptr; unsigned char* d_keys = nullptr; int* d_sched_work = nullptr;
   int hint_B = 0, hint_T = 0;           // batch the hints were recorded for (0 = none)
   struct HostBlock { char* base; size_t bytes; char* dev; };
   std::vector<HostBlock> host_blocks;   // page-locked blocks from jmpc_host_alloc (+ h_stage) with their device mapping
@@ -312,7 +316,9 @@ int32_t jmpc_create(int32_t device, int32_t max_B, int32_t max_T, int32_t max_N,
       (e = cudaMalloc(&h->d_ccfy, cbytes)) != cudaSuccess || (e = cudaMalloc(&h->d_ccrx, cbytes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_ccry, cbytes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_course_n, max_courses * sizeof(int))) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_counter, 64)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_counter, 64)) != cudaSuccess || (e = cudaMemset(h->d_counter, 0, 64)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_gather_timeout, sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(h->d_gather_timeout, 0, sizeof(int))) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     jmpc_destroy(h);
     return fail("jmpc_create: device allocation failed", e);
@@ -327,6 +333,7 @@ int32_t jmpc_destroy(jmpc_handle h) {
   cudaFree(h->d_cx); cudaFree(h->d_cy); cudaFree(h->d_cyaw); cudaFree(h->d_cv); cudaFree(h->d_course_n);
   cudaFree(h->d_ccfx); cudaFree(h->d_ccfy); cudaFree(h->d_ccrx); cudaFree(h->d_ccry); cudaFree(h->d_arc); cudaFree(h->d_arc_off);
   cudaFree(h->d_pscratch); cudaFree(h->d_counter); cudaFree(h->d_stage); cudaFree(h->d_order); cudaFree(h->d_hint);
+  cudaFree(h->d_keys); cudaFree(h->d_sched_work); cudaFree(h->d_gather_timeout);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -424,30 +431,42 @@ int launch_step(jmpc_handle h, int B, int T, const double* state, const int* cou
   a.ox = ox; a.oy = oy; a.ov = ov; a.oyaw = oyaw; a.xref = xref;
   a.cost = cost; a.status = status; a.iters = iters; a.record = record;
   a.n_peers = h->n_peers; a.rank_offset = h->rank_offset; a.skip = h->skip;
-  for (int p = 0; p < JMPC_MAX_PEERS; ++p) a.peer_rec[p] = h->peer_rec[p];
+  for (int p = 0; p < JMPC_MAX_PEERS; ++p) { a.peer_rec[p] = h->peer_rec[p]; a.peer_flag[p] = h->peer_flag[p]; }
+  a.n_flag_peers = h->n_flag_peers; a.gather_step = h->gather_step; a.blocks_done = h->d_counter + 1;
   a.pscratch = h->d_pscratch; a.counter = h->d_counter;
   a.order = nullptr; a.work_hint = nullptr;
   if (h->schedule > 0) {
     if (!h->d_order) {
       CK(cudaMalloc(&h->d_order, (size_t)h->max_B * sizeof(int)));
       CK(cudaMalloc(&h->d_hint, (size_t)h->max_B * sizeof(int)));
+      CK(cudaMalloc(&h->d_keys, (size_t)h->max_B));
+      CK(cudaMalloc(&h->d_sched_work, 2 * jmpc::kSchedKeys * sizeof(int)));
       CK(cudaMemsetAsync(h->d_hint, 0, (size_t)h->max_B * sizeof(int), s));
     }
-    // ordering only matters while the batch is a few waves of the resident instance slots deep (measured: no gain
-    // at 28 waves, where the one-block ordering kernel starts to cost as much as it saves)
+    // Ordering pays in two ways: a batch of a few waves of the resident instance slots finishes when its slowest
+    // late-started instance does (longest first), and on the half-warp kernels neighbours in the queue share a warp
+    // and iterate in lock step (similar keys = less idling).  With the previous step's iteration counts as keys it
+    // pays at any size (measured on 65 536 / 262 144 instances, T = 13: +8 % / +6 %); the a-priori key is a weaker
+    // predictor and is only used while the batch is a few waves deep.
     long long sched_max_waves = 16;
     double acc_weight = 2.0;                         // weight of the acceleration-saturation stages in the a-priori key
 #ifdef JMPC_EXPERIMENT
     if (const char* e = getenv("JMPC_SCHED_MAX_WAVES")) sched_max_waves = atoll(e);
     if (const char* e = getenv("JMPC_KEY_ACC_WEIGHT")) acc_weight = atof(e);
 #endif
-    if (B > g.groups_total && (long long)B <= sched_max_waves * (long long)g.groups_total) {
-      const bool have_hint = h->schedule >= 2 && h->hint_B == B && h->hint_T == T;
+    const bool have_hint = h->schedule >= 2 && h->hint_B == B && h->hint_T == T;
+    // (two instances per warp: with the previous step's counts the pairing alone pays, even when the whole batch is resident)
+    const bool pairing = have_hint && h->geom[T].groups > 1 && B >= 1024;
+    if (pairing || (B > g.groups_total && (have_hint || (long long)B <= sched_max_waves * (long long)g.groups_total))) {
       jmpc::ParamVec dv;
       memcpy(dv.v, h->defaults, sizeof dv.v);
-      jmpc::schedule_kernel<<<1, 1024, 0, s>>>(B, T, have_hint ? h->d_hint : nullptr, state, params, dv, h->d_order, acc_weight);
+      const int sblocks = std::max(1, std::min((B + jmpc::kSchedThreads - 1) / jmpc::kSchedThreads, 2 * h->sm_count));
+      CK(cudaMemsetAsync(h->d_sched_work, 0, 2 * jmpc::kSchedKeys * sizeof(int), s));
+      jmpc::schedule_count_kernel<<<sblocks, jmpc::kSchedThreads, 0, s>>>(B, T, have_hint ? h->d_hint : nullptr, state, params, dv,
+                                                                         acc_weight, h->d_keys, h->d_sched_work);
+      jmpc::schedule_place_kernel<<<sblocks, jmpc::kSchedThreads, 0, s>>>(B, h->d_keys, h->d_sched_work, h->d_order);
       CK(cudaGetLastError());
-      h->launches++;
+      h->launches += 2;
       a.order = h->d_order;
     }
     if (h->schedule >= 2) { a.work_hint = h->d_hint; h->hint_B = B; h->hint_T = T; }
@@ -558,6 +577,34 @@ int32_t jmpc_set_record_peers(jmpc_handle h, int32_t n_peers, const uint64_t* pe
   if (rank_offset < 0) return fail("jmpc_set_record_peers: negative rank_offset");
   for (int p = 0; p < JMPC_MAX_PEERS; ++p) h->peer_rec[p] = (p < n_peers) ? reinterpret_cast<double*>(peer_tables[p]) : nullptr;
   h->n_peers = n_peers; h->rank_offset = rank_offset;
+  return 0;
+}
+
+int32_t jmpc_set_record_flags(jmpc_handle h, int32_t n_peers, const uint64_t* peer_flags, uint64_t step) {
+  if (!h) return fail("jmpc_set_record_flags: NULL handle");
+  if (n_peers < 0 || n_peers > JMPC_MAX_PEERS) return fail("jmpc_set_record_flags: n_peers out of range");
+  if (n_peers > 0 && !peer_flags) return fail("jmpc_set_record_flags: NULL flag list");
+  for (int p = 0; p < JMPC_MAX_PEERS; ++p)
+    h->peer_flag[p] = (p < n_peers) ? reinterpret_cast<unsigned long long*>(peer_flags[p]) : nullptr;
+  h->n_flag_peers = n_peers; h->gather_step = step;
+  return 0;
+}
+
+int32_t jmpc_gather_wait(jmpc_handle h, const uint64_t* flags, int32_t world, uint64_t step, void* stream) {
+  if (!h || !flags) return fail("jmpc_gather_wait: NULL argument");
+  if (world < 1 || world > JMPC_MAX_PEERS) return fail("jmpc_gather_wait: world out of range");
+  CK(cudaSetDevice(h->device));
+  jmpc::gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(flags), world, step,
+                                                              h->d_gather_timeout);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int32_t jmpc_gather_timed_out(jmpc_handle h, int32_t* out) {
+  if (!h || !out) return fail("jmpc_gather_timed_out: NULL argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out, h->d_gather_timeout, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 

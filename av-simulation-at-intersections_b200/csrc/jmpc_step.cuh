@@ -70,6 +70,12 @@ struct StepArgs {
   double* peer_rec[JMPC_MAX_PEERS];
   int n_peers;
   long long rank_offset;
+  // completion flags of the fused all-gather (jmpc_set_record_flags): when the last block of the launch retires it
+  // stores gather_step into this rank's slot of every peer's flag array (release, system scope), after every record
+  unsigned long long* peer_flag[JMPC_MAX_PEERS];
+  int n_flag_peers;
+  unsigned long long gather_step;
+  unsigned int* blocks_done;       // retired-block counter of the launch (reset by the last block)
   // scratch
   double* pscratch;         // [resident groups][tiles_doubles(n)] condensed Hessian on tiles, L2 resident
   unsigned int* counter;    // dynamic work queue
@@ -1007,40 +1013,64 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, bool
 // an a-priori key: the number of horizon stages on which the speed cap can bind at full throttle (v0 close to the
 // cap => many active, nearly degenerate speed rows) plus the stages on which the acceleration box binds while a slow
 // ego catches up with the reference points (correlation 0.56 with the iteration count on config 2).
-// One block; counting sort on 64 key values; the order inside a key class is not deterministic (it only affects timing).
 constexpr int kSchedKeys = 64;
-__global__ void __launch_bounds__(1024) schedule_kernel(int B, int T, const int* __restrict__ hint,
-                                                        const double* __restrict__ state, const double* __restrict__ params,
-                                                        ParamVec defaults, int* __restrict__ order, double acc_weight) {
+constexpr int kSchedThreads = 1024;
+__device__ __forceinline__ int schedule_key(int b, int T, const int* __restrict__ hint, const double* __restrict__ state,
+                                            const double* __restrict__ params, const ParamVec& defaults, double acc_weight) {
+  int key;
+  if (hint) {
+    key = hint[b];
+  } else {
+    const double* pv = params ? params + (size_t)b * JMPC_NPARAM : defaults.v;
+    const double v0 = state[(size_t)b * 4 + 2];
+    const double dv_stage = fmax(pv[JMPC_P_MAX_ACCEL] * pv[JMPC_P_DT], 1e-9);        // speed gained per stage at full throttle
+    // stages on which the speed cap can bind
+    const double cap_stages = fmin(fmax((double)T - (pv[JMPC_P_SPEED] - v0) / dv_stage, 0.0), (double)T);
+    // stages at full throttle to reach the speed the reference points advance with (mpc.py:98: max(v, 10/3.6)); the
+    // acceleration box binds on those and, to close the gap opened meanwhile, on about as many again
+    const double acc_stages = fmin(fmax((pv[JMPC_P_V_REF_MIN] - v0) / dv_stage, 0.0), (double)T);
+    key = (int)(2.0 * (cap_stages + acc_weight * acc_stages));
+  }
+  return min(max(key, 0), kSchedKeys - 1);
+}
+// Counting sort on 64 key values in two launches over any number of blocks (a block owns a contiguous chunk of the
+// batch): (1) keys and the global histogram, (2) every block reserves, per key, a range of the output for its chunk
+// with one global atomic and scatters into it.  The order inside a key class is not deterministic (it only affects
+// timing, never results).  work: [0, 64) histogram, [64, 128) per-key cursors, both zeroed before the first launch.
+__global__ void __launch_bounds__(kSchedThreads) schedule_count_kernel(int B, int T, const int* __restrict__ hint,
+                                                                       const double* __restrict__ state,
+                                                                       const double* __restrict__ params, ParamVec defaults,
+                                                                       double acc_weight, unsigned char* __restrict__ keys,
+                                                                       int* __restrict__ work) {
   __shared__ int count[kSchedKeys];
-  __shared__ int start[kSchedKeys];
   for (int k = threadIdx.x; k < kSchedKeys; k += blockDim.x) count[k] = 0;
   __syncthreads();
-  auto key_of = [&](int b) -> int {
-    int key;
-    if (hint) {
-      key = hint[b];
-    } else {
-      const double* pv = params ? params + (size_t)b * JMPC_NPARAM : defaults.v;
-      const double v0 = state[(size_t)b * 4 + 2];
-      const double dv_stage = fmax(pv[JMPC_P_MAX_ACCEL] * pv[JMPC_P_DT], 1e-9);        // speed gained per stage at full throttle
-      // stages on which the speed cap can bind
-      const double cap_stages = fmin(fmax((double)T - (pv[JMPC_P_SPEED] - v0) / dv_stage, 0.0), (double)T);
-      // stages at full throttle to reach the speed the reference points advance with (mpc.py:98: max(v, 10/3.6)); the
-      // acceleration box binds on those and, to close the gap opened meanwhile, on about as many again
-      const double acc_stages = fmin(fmax((pv[JMPC_P_V_REF_MIN] - v0) / dv_stage, 0.0), (double)T);
-      key = (int)(2.0 * (cap_stages + acc_weight * acc_stages));
-    }
-    return min(max(key, 0), kSchedKeys - 1);
-  };
-  for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&count[key_of(b)], 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int k = kSchedKeys - 1; k >= 0; --k) { start[k] = acc; acc += count[k]; }      // descending keys
+  const int chunk = (B + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * chunk, hi = min(B, lo + chunk);
+  for (int b = lo + threadIdx.x; b < hi; b += blockDim.x) {
+    const int key = schedule_key(b, T, hint, state, params, defaults, acc_weight);
+    keys[b] = (unsigned char)key;
+    atomicAdd(&count[key], 1);
   }
   __syncthreads();
-  for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&start[key_of(b)], 1)] = b;
+  for (int k = threadIdx.x; k < kSchedKeys; k += blockDim.x) if (count[k]) atomicAdd(&work[k], count[k]);
+}
+__global__ void __launch_bounds__(kSchedThreads) schedule_place_kernel(int B, const unsigned char* __restrict__ keys,
+                                                                       int* __restrict__ work, int* __restrict__ order) {
+  __shared__ int count[kSchedKeys];
+  __shared__ int base[kSchedKeys];
+  for (int k = threadIdx.x; k < kSchedKeys; k += blockDim.x) count[k] = 0;
+  __syncthreads();
+  const int chunk = (B + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * chunk, hi = min(B, lo + chunk);
+  for (int b = lo + threadIdx.x; b < hi; b += blockDim.x) atomicAdd(&count[keys[b]], 1);
+  __syncthreads();
+  if (threadIdx.x < kSchedKeys) {
+    const int k = threadIdx.x;
+    int start = 0;                                     // descending keys: everything with a larger key comes first
+    for (int q = k + 1; q < kSchedKeys; ++q) start += work[q];
+    base[k] = start + (count[k] ? atomicAdd(&work[kSchedKeys + k], count[k]) : 0);
+  }
+  __syncthreads();
+  for (int b = lo + threadIdx.x; b < hi; b += blockDim.x) order[atomicAdd(&base[keys[b]], 1)] = b;
 }
 
 // Persistent kernel: every resident warp pulls instances (one per lane group) from a global counter.
@@ -1097,6 +1127,36 @@ __global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_k
     mpc_step_instance<TT, G>(A, (int)b, active, base, pscr, gl, gm, tma_parity, lut);
     __syncwarp();
   }
+  // Fused all-gather, completion signal: the block that retires last has (through the fences and the counter) every
+  // record store of this launch before it; it publishes the step number to every peer.  A reader waits for all ranks'
+  // flags (gather_wait_kernel) and then owns a complete table -- no barrier kernel, no collective call.
+  if (A.n_flag_peers > 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned prev = atomicAdd(A.blocks_done, 1u);
+      if (prev == gridDim.x - 1) {
+        *A.blocks_done = 0u;
+        __threadfence_system();
+        for (int p = 0; p < A.n_flag_peers; ++p)
+          asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(A.peer_flag[p]), "l"(A.gather_step) : "memory");
+      }
+    }
+  }
+}
+
+// Wait until every rank of the fused all-gather has published `step` (or a later one): lane p watches rank p's slot
+// of the local flag array.  Gives up after ~2 s of spinning and reports it in *timed_out instead of hanging the GPU.
+__global__ void gather_wait_kernel(const unsigned long long* flags, int world, unsigned long long step, int* timed_out) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  unsigned long long v = 0;
+  for (long long spin = 0; spin < (1ll << 24); ++spin) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flags + p) : "memory");
+    if (v >= step) return;
+    __nanosleep(100);
+  }
+  atomicExch(timed_out, 1);
 }
 
 }  // namespace jmpc

@@ -40,6 +40,9 @@ SIGNATURES = {
     "jmpc_reset_schedule_hints": (C.c_int32, [C.c_void_p]),
     "jmpc_set_skip_mask": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "jmpc_set_record_peers": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    "jmpc_set_record_flags": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]),
+    "jmpc_gather_wait": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]),
+    "jmpc_gather_timed_out": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "jmpc_set_host_transfer": (C.c_int32, [C.c_void_p, C.c_int32]),
     "jmpc_step_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 17),
     "jmpc_step_host_io": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 20),

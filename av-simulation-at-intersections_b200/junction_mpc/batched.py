@@ -158,6 +158,25 @@ class BatchedMPC:
         _cabi.check(self._lib.jmpc_set_record_peers(self._h, len(peer_table_ptrs), ptrs, int(rank_offset)),
                     "jmpc_set_record_peers")
 
+    def set_record_flags(self, peer_flag_ptrs, step: int):
+        """Completion flags of the fused all-gather (jmpc_set_record_flags): from now on the last retiring block of
+        every step launch stores `step` into the given addresses (this rank's slot in every rank's flag array)."""
+        ptrs = (C.c_uint64 * max(len(peer_flag_ptrs), 1))(*[int(p) for p in peer_flag_ptrs])
+        _cabi.check(self._lib.jmpc_set_record_flags(self._h, len(peer_flag_ptrs), ptrs, int(step)), "jmpc_set_record_flags")
+
+    def gather_wait(self, flags, world: int, step: int, stream: Optional[int] = None):
+        """Enqueue the wait for all `world` ranks to have published `step` in the local flag array `flags` (CUDA int64)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _cabi.check(self._lib.jmpc_gather_wait(self._h, C.c_void_p(flags.data_ptr()), int(world), int(step),
+                                               C.c_void_p(stream)), "jmpc_gather_wait")
+
+    def gather_timed_out(self) -> bool:
+        v = C.c_int32(0)
+        _cabi.check(self._lib.jmpc_gather_timed_out(self._h, C.byref(v)), "jmpc_gather_timed_out")
+        return bool(v.value)
+
     def close(self):
         if getattr(self, "_h", None):
             self._host_out = {}

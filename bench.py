@@ -36,7 +36,6 @@ import numpy as np  # noqa: E402
 
 METRIC = "batched MPC step solves/sec"
 UNIT = "solves/s"
-SYNC_EVERY = 8          # deferred gather: cross-GPU barrier every SYNC_EVERY steps (see FusedRecordGather)
 
 
 def flops_per_solve(T: int, iters: float) -> float:
@@ -249,8 +248,9 @@ def main():
     ap.add_argument("--states-per-point", type=int, default=32, help="config 5: states per parameter point (32 = 1M instances)")
     ap.add_argument("--ref-sample", type=int, default=1024, help="reference arm: instances per step for configs 3-5")
     ap.add_argument("--cpu-sample", type=int, default=2048)
-    ap.add_argument("--gather", default="every", choices=["every", "deferred", "nccl"],
-                    help="N > 1: cross-GPU barrier after every step (default), every SYNC_EVERY steps, or NCCL all-gather")
+    ap.add_argument("--gather", default="flags", choices=["flags", "barrier", "nccl"],
+                    help="N > 1: fused gather completed by flags the step kernel publishes (default), fused gather + "
+                         "cross-GPU barrier after every step, or one NCCL all-gather per step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -324,18 +324,20 @@ def main():
         if args.gather != "nccl":
             try:
                 from junction_mpc.distributed import FusedRecordGather
-                fused = FusedRecordGather(mpc, B_global, slices[0]["row0"])
+                fused = FusedRecordGather(mpc, B_global, slices[0]["row0"], sync=args.gather)
                 gather_kind = ("fused: the step kernel's epilogue stores every record into every rank's table (NVLink "
-                               "symmetric memory, double-buffered); cross-GPU signal-pad barrier " +
-                               ("after every step" if args.gather == "every" else
-                                f"every {SYNC_EVERY} steps (deferred, SURVEY.md 8e), a second barrier releasing the table"))
+                               "symmetric memory, ring of %d tables); " % fused.buffers +
+                               ("completion by flags: the kernel's last block publishes the step number to every rank, and "
+                                "every step ends with the wait for all ranks' records of the PREVIOUS step (the last timed "
+                                "step also waits for its own), so the gather runs one step behind the solves"
+                                if args.gather == "flags" else "cross-GPU signal-pad barrier after every step"))
             except Exception as exc:            # noqa: BLE001
                 if rank == 0:
                     print(f"[bench] fused gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
                 fused = None
     step_no = [0]
 
-    def one_step(e0=None, e1=None, ec=None, cold=True, marks=None):
+    def one_step(e0=None, e1=None, ec=None, cold=True, marks=None, final=False):
         flush.zero_()
         for d in devs:
             d.tgt.copy_(d.tgt0); d.oa.copy_(d.oa0); d.od.copy_(d.od0)
@@ -354,16 +356,15 @@ def main():
                 ec.record()
         for k, d in enumerate(devs):
             if fused is not None:
-                fused.begin_step(d.w["row0"])
+                fused.begin_step(d.w["row0"], publish=(k == len(devs) - 1))
             mpc.step(d.state, d.tgt, d.oa, d.od, d.out, course_len=d.clen, params=d.params, T=d.T)
             if marks is not None:
                 marks[k].record()
         step_no[0] += 1
         if fused is not None:
-            sync = args.gather == "every" or step_no[0] % SYNC_EVERY == 0
-            fused.finish(sync=sync)            # the records are already in every peer's table
-            if sync and args.gather == "deferred":
-                fused.release()
+            fused.finish()                     # the records are already on their way into every peer's table
+            if args.gather == "flags":
+                fused.wait(fused.step_no if final else fused.step_no - 1)
         elif world > 1:
             for d in devs:
                 allgather_records(d.out.record)   # [world * B, 8] on every rank, straight from the kernel's buffer
@@ -374,17 +375,14 @@ def main():
         one_step()
     torch.cuda.synchronize()
     if fused is not None and len(devs) == 1:   # the fused table must equal what the NCCL all-gather delivers
-        one_step()
-        if args.gather == "deferred":
-            fused.handle.barrier(channel=0)
+        one_step(final=True)
         torch.cuda.synchronize()
-        got = fused.tables[(fused.step_no - 1) % fused.buffers]
+        got = fused.table_of(fused.step_no)
         ref = allgather_records(devs[0].out.record)
         torch.cuda.synchronize()
         same = torch.equal(torch.nan_to_num(got, nan=-1.0), torch.nan_to_num(ref, nan=-1.0))
         assert same, "fused record gather differs from the NCCL all-gather"
-        if args.gather == "deferred":
-            fused.release()
+        assert not mpc.gather_timed_out(), "gather wait timed out"
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -394,8 +392,8 @@ def main():
     evs = [(ev(), ev(), ev(), [ev() for _ in devs]) for _ in range(args.steps)]
     step_no[0] = 0
     torch.cuda.synchronize()
-    for e0, e1, ec, marks in evs:
-        one_step(e0, e1, ec, marks=marks)
+    for k, (e0, e1, ec, marks) in enumerate(evs):
+        one_step(e0, e1, ec, marks=marks, final=(k == len(evs) - 1))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -442,6 +440,7 @@ def main():
         hint = (float(hint_ms.item()), hint_steps)
     if fused is not None:
         torch.cuda.synchronize()
+        assert not mpc.gather_timed_out(), "gather wait timed out"
         dist.barrier()
         fused.close()
 

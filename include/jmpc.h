@@ -168,6 +168,18 @@ int32_t jmpc_debug_cycles(jmpc_handle h, uint64_t* out32, int32_t reset);
  * tables.  n_peers = 0 switches it off. */
 int32_t jmpc_set_record_peers(jmpc_handle h, int32_t n_peers, const uint64_t* peer_tables, int64_t rank_offset);
 
+/* Completion flags of the fused all-gather.  After jmpc_set_record_flags every jmpc_step on the handle ends with the
+ * last retiring block storing `step` (release, system scope, after all record stores of the launch) into
+ * `peer_flags[p]` for every peer p: the address of THIS rank's slot in rank p's flag array (DEVICE pointers valid on
+ * this GPU, uint64 slots, monotonically increasing step numbers).  n_peers = 0 switches it off.
+ * jmpc_gather_wait enqueues a one-warp kernel on `stream` that returns once all `world` slots of the LOCAL flag array
+ * hold a value >= step, i.e. once every rank's records of that step are in this GPU's table: the only synchronisation
+ * of the gather, placed where (and as late as) the reader wants it.  It gives up after ~2 s instead of hanging the GPU;
+ * jmpc_gather_timed_out reports (and synchronises the device for) that. */
+int32_t jmpc_set_record_flags(jmpc_handle h, int32_t n_peers, const uint64_t* peer_flags, uint64_t step);
+int32_t jmpc_gather_wait(jmpc_handle h, const uint64_t* flags, int32_t world, uint64_t step, void* stream);
+int32_t jmpc_gather_timed_out(jmpc_handle h, int32_t* out);
+
 /* Same with HOST pointers: runs the step and returns when the results are in the host arrays.  The inputs are
  * copied to the device with cudaMemcpyAsync; the results take no copy pass: the kernel's epilogue stores them into
  * page-locked host memory through its device mapping -- the caller's arrays where they are page-locked
