@@ -85,6 +85,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self._armed = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -104,6 +105,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
+        self._armed.wait()                  # started early, records only inside the timed region
         while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -118,8 +120,12 @@ class ClockSampler(threading.Thread):
                 pass
             self._halt.wait(self.period)
 
+    def arm(self):
+        self._armed.set()
+
     def finish(self):
         self._halt.set()
+        self._armed.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -270,6 +276,11 @@ def main():
         g.build()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    if world > 1 and os.environ.get("BENCH_PIN") and hasattr(os, "sched_setaffinity"):
+        # one disjoint set of host cores per rank (experiment: launch jitter of eight processes on one host)
+        n = os.cpu_count() or world
+        per = max(1, n // world)
+        os.sched_setaffinity(0, set(range(local * per, min(n, (local + 1) * per))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -383,21 +394,31 @@ def main():
         same = torch.equal(torch.nan_to_num(got, nan=-1.0), torch.nan_to_num(ref, nan=-1.0))
         assert same, "fused record gather differs from the NCCL all-gather"
         assert not mpc.gather_timed_out(), "gather wait timed out"
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = mpc.launch_count
+    sampler = ClockSampler(local, period=float(os.environ.get("BENCH_SAMPLER_PERIOD", "0.005")))     # NVML init: milliseconds
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     evs = [(ev(), ev(), ev(), [ev() for _ in devs]) for _ in range(args.steps)]
     step_no[0] = 0
+    # Align the ranks on the DEVICE right before the timed loop: the NCCL barrier is a kernel on each rank's stream, so
+    # all streams leave it within microseconds.  (Anything host-side between the barrier and the loop -- NVML start-up,
+    # event creation -- skews the ranks by milliseconds, and with a cross-rank gather inside the step the early ranks
+    # then time their waiting for the late ones.)
+    import gc
+    sampler.start()                          # the thread idles until arm(): its start-up stays outside the timed region
+    gc.collect()
+    gc.disable()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    sampler.arm()
+    launches0 = mpc.launch_count
     for k, (e0, e1, ec, marks) in enumerate(evs):
         one_step(e0, e1, ec, marks=marks, final=(k == len(evs) - 1))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.finish()
+    gc.enable()
     launches = mpc.launch_count - launches0
     # per step: [flag kernel] + step launches + gather.  The metric counts MPC step solves: flag production is timed
     # separately ("solves/s must not be diluted or inflated by it").
@@ -409,7 +430,11 @@ def main():
         start = [(ec if has_obs else e0) if k == 0 else marks[k - 1] for e0, e1, ec, marks in evs]
         slice_ms.append(float(np.mean([s.elapsed_time(marks[k]) for s, (_, _, _, marks) in zip(start, evs)])))
     tot = torch.tensor([per_step.sum(), coll_ms.sum(), total_step_ms.sum()], dtype=f64, device=dev)
+    per_rank_ms = [float(per_step.mean())]
     if world > 1:
+        allr = [torch.zeros(1, dtype=f64, device=dev) for _ in range(world)]
+        dist.all_gather(allr, torch.tensor([per_step.mean()], dtype=f64, device=dev))
+        per_rank_ms = [float(x.item()) for x in allr]
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     ms_per_step = float(tot[0].item()) / args.steps
     coll_ms_per_step = float(tot[1].item()) / args.steps
@@ -551,8 +576,11 @@ def main():
                 "not_solved": not_solved,
                 "schedule": "longest-first work queue by an a-priori key from the step's inputs (speed-cap proximity); "
                             "previous-step iteration counts deliberately forgotten before every step",
-                "gather": gather_kind,
-                "slices": [{"T": d.T, "instances": d.B, "kernel_ms": ms} for d, ms in zip(devs, slice_ms)]},
+                "gather": gather_kind, "ms_per_step_by_rank": per_rank_ms,
+                "ms_by_step_rank0": [round(float(x), 3) for x in per_step[:64]],
+                "slices": [{"T": d.T, "instances": d.B, "kernel_ms": ms, "mean_solver_iters": float(it.mean()),
+                            "fp64_frac": flops_per_solve(d.T, float(it.mean())) * d.B / (ms * 1e-3) / 1e12 / fp64_peak}
+                           for d, ms, it in zip(devs, slice_ms, iters)]},
         "p50_ms": float(np.percentile(per_step, 50)), "p99_ms": float(np.percentile(per_step, 99)),
         "single_instance_step_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                     "api": f"step_host, B=1, T={w0['T']}, host in / host out"},

@@ -1,0 +1,15 @@
+set -x
+cd $GRAFT_REPO_ROOT
+O=gpurun_out
+N=${NGPU:-8}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+show() { python - "$1" "$2" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().split('\n')[-1])
+print(sys.argv[2], 'value %.4g ms %.3f p50 %.3f p99 %.3f e2e %.4g'%(d['value'],d['ms_per_step'],d['p50_ms'],d['p99_ms'],d['e2e']['value']), [round(x,3) for x in d['run']['ms_per_step_by_rank']])
+print('   ', d['run']['ms_by_step_rank0'][:45])
+PY
+}
+timeout 300 $TR bench.py --gpus $N --steps 40 --warmup 5 --no-cpu > $O/r2l_n${N}_c2_flags.json 2> $O/r2l_n${N}_c2_flags.err; show $O/r2l_n${N}_c2_flags.json flags
+timeout 300 $TR bench.py --gpus $N --steps 40 --warmup 5 --no-cpu --gather barrier > $O/r2l_n${N}_c2_barrier.json 2> $O/r2l_n${N}_c2_barrier.err; show $O/r2l_n${N}_c2_barrier.json barrier
+timeout 600 $TR bench.py --gpus $N --config 5 --steps 5 --warmup 3 --no-cpu > $O/r2l_n${N}_c5.json 2> $O/r2l_n${N}_c5.err; show $O/r2l_n${N}_c5.json c5
