@@ -1130,7 +1130,7 @@ int32_t jmpc_debug_linalg_g(jmpc_handle h, int32_t n, int32_t group_lanes, int32
   CK(cudaMemsetAsync(dsol, 0xff, out_doubles * sizeof(double), st));          // NaN where the kernel writes nothing
   const int nb = jmpc::nblk(n);
   const size_t smem = (size_t)groups * (jmpc::tiles_doubles(n) + 8 * nb) * sizeof(double) +
-                      (size_t)jmpc::chol_lut_entries(nb + 1) * 2 + 16;
+                      jmpc::chol_lut_bytes(nb) + 16;
   if (group_lanes == 32) jmpc::linalg_selftest_kernel<32><<<1, 32, smem, st>>>(n, which, dA, db, dx, dsol, dprod, dok);
   else jmpc::linalg_selftest_kernel<16><<<1, 32, smem, st>>>(n, which, dA, db, dx, dsol, dprod, dok);
   CK(cudaGetLastError());

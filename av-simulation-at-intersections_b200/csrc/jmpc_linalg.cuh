@@ -24,15 +24,18 @@
 
 namespace jmpc {
 
-// Unrolling of the block-column loops (experiments: -DJMPC_UNROLL_J=1 keeps them rolled, which shrinks the solver loop's
-// code at the price of run-time tile offsets)
-#ifndef JMPC_UNROLL_J
-#define JMPC_UNROLL_J 0
-#endif
-#if JMPC_UNROLL_J > 0
-#define JMPC_PRAGMA_J _Pragma("unroll 1")
+// The block-column loops of the factorisation, the triangular sweeps and the matvec stay rolled: unrolled (tile offsets as
+// immediates) the interior-point loop is 37-55 KB of SASS, rolled 27-30 KB, and the instruction cache behind the
+// schedulers holds 32 KB -- measured on the B200: T = 8 15.8 -> 21.7 M solves/s, T = 13 / 20 / 25 +2-4 % on top of
+// the shorter row work.  -DJMPC_UNROLL_BLOCKS brings the unrolled loops back for comparison.
+#ifdef JMPC_UNROLL_BLOCKS
+#define JMPC_PRAGMA_CHOL _Pragma("unroll")
+#define JMPC_PRAGMA_SWEEP _Pragma("unroll")
+#define JMPC_PRAGMA_SYMV _Pragma("unroll")
 #else
-#define JMPC_PRAGMA_J
+#define JMPC_PRAGMA_CHOL _Pragma("unroll 1")
+#define JMPC_PRAGMA_SWEEP _Pragma("unroll 1")
+#define JMPC_PRAGMA_SYMV _Pragma("unroll 1")
 #endif
 
 // Cycle accounting of a debug build (-DJMPC_CYCLES): lane 0 accumulates clock64() deltas per code region into
@@ -93,22 +96,42 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
   *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
 }
 
-// Task table of the trailing update: for block column J, task q (half a tile) -> (a, b, half) with tile row
-// I = J + 1 + a, tile column Kc = J + 1 + b (b <= a).  It only depends on m = nb - J - 1, so one table of
-// sum_{m=1}^{nb-1} m (m + 1) 16-bit entries serves every factorisation of the launch; it is built once per block in
-// shared memory.  (Decoding q arithmetically -- float sqrt plus fix-up loops -- was 4 % of the kernel's instructions.)
+// Task table of the trailing update: for block column J, task q (half a tile) -> tile row I = J + 1 + a, tile
+// column Kc = J + 1 + b (b <= a), half h.  (a, b, h) only depend on m = nb - J - 1; the entry also carries the slot
+// numbers of the two factor tiles the task reads for the launch's block count nb (J = nb - 1 - m), so the kernel
+// forms its three addresses with one multiply-add each instead of evaluating tile_off() three times (the integer
+// work was a quarter of the update's instructions).  One table of sum_{m=1}^{nb} m (m + 1) 32-bit entries per block,
+// built once per launch in shared memory.  (Decoding q arithmetically -- float sqrt plus fix-up loops -- was 4 % of
+// the kernel's instructions.)
+//   bits 0-7   slot of tile (I, J)            bits 8-15  slot of tile (Kc, J)
+//   bits 16-19 b + 1 (slot of (I, Kc) = slot of (I, J) + b + 1)       bit 22  h (so (e >> 16) & 0x40 = byte offset of the half)
+//   bits 24-27 a
+// The rows m = nb of the table (no column of the factorisation has that many block rows below it) are there for the
+// solver's K assembly, which walks the accel block with (a, b, h) alone.
+typedef unsigned int chol_task;
 __host__ __device__ inline int chol_lut_entries(int nb) { return ((nb - 1) * nb * (nb + 1)) / 3; }
 __host__ __device__ __forceinline__ int chol_lut_offset(int m) { return ((m - 1) * m * (m + 1)) / 3; }   // tasks of all m' < m
-__device__ inline void chol_lut_build(unsigned short* lut, int nb, int tid, int nthreads) {
-  for (int m = 1; m < nb; ++m) {
+__host__ __device__ inline size_t chol_lut_bytes(int nb) { return ((size_t)chol_lut_entries(nb + 1) * sizeof(chol_task) + 15) & ~(size_t)15; }
+__device__ __forceinline__ int task_a(chol_task e) { return (int)((e >> 24) & 15u); }
+__device__ __forceinline__ int task_b(chol_task e) { return (int)((e >> 16) & 15u) - 1; }
+__device__ __forceinline__ int task_h(chol_task e) { return (int)((e >> 22) & 1u); }
+// table for a factorisation with nb block rows (rows m = 1 .. nb)
+__device__ inline void chol_lut_build(chol_task* lut, int nb, int tid, int nthreads) {
+  for (int m = 1; m <= nb; ++m) {
     const int ntasks = m * (m + 1), off = chol_lut_offset(m);
+    const int J = nb - 1 - m;                       // -1 for the extra row: slots unused there
     for (int q = tid; q < ntasks; q += nthreads) {
       const int t = q >> 1;
       int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
       while (((a + 1) * (a + 2) >> 1) <= t) ++a;
       while (((a * (a + 1)) >> 1) > t) --a;
       const int b = t - ((a * (a + 1)) >> 1);
-      lut[off + q] = (unsigned short)(a | (b << 4) | ((q & 1) << 8));
+      unsigned e = ((unsigned)(b + 1) << 16) | ((unsigned)(q & 1) << 22) | ((unsigned)a << 24);
+      if (J >= 0) {
+        const int I = J + 1 + a, Kc = J + 1 + b;
+        e |= (unsigned)(((I * (I + 1)) >> 1) + J) | ((unsigned)(((Kc * (Kc + 1)) >> 1) + J) << 8);
+      }
+      lut[off + q] = e;
     }
   }
 }
@@ -122,10 +145,10 @@ __device__ inline void chol_lut_build(unsigned short* lut, int nb, int tid, int 
 // row of the panel subtracts that row times y from its rhs entry -- no extra loads of L and no extra
 // synchronisation; rhs holds y afterwards (solve_backward_tiles completes the solve).
 template <int G>
-__device__ inline bool chol_tiles(double* K, int nb, int gl, unsigned gm, const unsigned short* lut,
+__device__ inline bool chol_tiles(double* K, int nb, int gl, unsigned gm, const chol_task* lut,
                                   double* rhs = nullptr) {
   bool all_clean = true;
-  JMPC_PRAGMA_J
+  JMPC_PRAGMA_CHOL
   for (int J = 0; J < nb; ++J) {
     JMPC_TICK(tc_);
     // ---- diagonal block: every lane factors it redundantly in registers (no broadcast needed)
@@ -196,13 +219,14 @@ __device__ inline bool chol_tiles(double* K, int nb, int gl, unsigned gm, const 
     // ---- trailing update: C(I, Kc) -= L(I, J) L(Kc, J)'; a task is half a tile (two rows), so the 45 / 36 / 28 ...
     // tiles of the first block columns fill the 32 lanes better than whole tiles would
     const int m = nb - J - 1, ntasks = m * (m + 1);
-    const unsigned short* tasks = lut + chol_lut_offset(m);
+    const chol_task* tasks = lut + chol_lut_offset(m);
     for (int q = gl; q < ntasks; q += G) {
       const unsigned e = tasks[q];
-      const int I = J + 1 + (int)(e & 15u), Kc = J + 1 + (int)((e >> 4) & 15u), h = (int)((e >> 8) & 1u) << 1;
-      const double* LI = K + tile_off(I, J) + 4 * h;
-      const double* LK = K + tile_off(Kc, J);
-      double* C = K + tile_off(I, Kc) + 4 * h;
+      const unsigned sLI = e & 255u, sLK = (e >> 8) & 255u, sC = sLI + ((e >> 16) & 15u), hb = (e >> 16) & 0x40u;
+      const char* Kh = reinterpret_cast<const char*>(K) + hb;          // rows 2h, 2h + 1 of a tile start 64 h bytes in
+      const double* LI = reinterpret_cast<const double*>(Kh + sLI * (unsigned)(kTS * sizeof(double)));
+      const double* LK = K + sLK * (unsigned)kTS;
+      double* C = reinterpret_cast<double*>(const_cast<char*>(Kh) + sC * (unsigned)(kTS * sizeof(double)));
       double k00, k01, k02, k03, k10, k11, k12, k13, k20, k21, k22, k23, k30, k31, k32, k33;
       ld4(LK, k00, k01, k02, k03); ld4(LK + 4, k10, k11, k12, k13);
       ld4(LK + 8, k20, k21, k22, k23); ld4(LK + 12, k30, k31, k32, k33);
@@ -229,7 +253,7 @@ __device__ inline bool chol_tiles(double* K, int nb, int gl, unsigned gm, const 
 template <int G>
 __device__ inline void solve_forward_tiles(const double* K, double* b, int nb, int gl, unsigned gm) {
   const int n4 = nb << 2;
-  JMPC_PRAGMA_J
+  JMPC_PRAGMA_SWEEP
   for (int J = 0; J < nb; ++J) {                      // forward: L y = b
     const double* Mw = K + tile_off(J, J);
     double b0, b1, b2, b3;
@@ -254,7 +278,7 @@ __device__ inline void solve_forward_tiles(const double* K, double* b, int nb, i
 }
 template <int G>
 __device__ inline void solve_backward_tiles(const double* K, double* b, int nb, int gl, unsigned gm) {
-  JMPC_PRAGMA_J
+  JMPC_PRAGMA_SWEEP
   for (int J = nb - 1; J >= 0; --J) {                 // backward: L' x = y
     const double* Mw = K + tile_off(J, J);
     double y0, y1, y2, y3;
@@ -334,7 +358,7 @@ __device__ __forceinline__ void symv_rows(const double* P, const double* x, int 
   const double* cola = P + Ia * kTS + (ia & 3);
   const double* colb = P + Ib * kTS + (ib & 3);
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-#pragma unroll
+  JMPC_PRAGMA_SYMV
   for (int J = 0; J < nb; ++J) {
     double x0, x1, x2, x3, p0, p1, p2, p3;
     ld4(x + (J << 2), x0, x1, x2, x3);
@@ -363,7 +387,7 @@ __global__ void linalg_selftest_kernel(int n, int which, const double* __restric
   double* K = sm + sub * per_group;
   double* rhs = K + tiles_doubles(n);
   double* xv = rhs + n4;
-  unsigned short* lut = reinterpret_cast<unsigned short*>(sm + (32 / G) * per_group);
+  chol_task* lut = reinterpret_cast<chol_task*>(sm + (32 / G) * per_group);
   chol_lut_build(lut, nb, lane, 32);
   __syncwarp();
   const bool report = sub == which;

@@ -119,8 +119,7 @@ __host__ __device__ inline int group_lanes_for(int T) { return (T + 1 <= 16) ? 1
 // dynamic shared memory of a block of `wpb` warps with `groups` instances each: the instances' regions plus the
 // block-shared Cholesky task table
 __host__ __device__ inline size_t step_block_smem_bytes(int T, int wpb, int groups) {
-  return (size_t)wpb * groups * inst_smem_doubles(T) * sizeof(double) +
-         (((size_t)chol_lut_entries(nblk(2 * T) + 1) * 2 + 15) & ~(size_t)15);
+  return (size_t)wpb * groups * inst_smem_doubles(T) * sizeof(double) + chol_lut_bytes(nblk(2 * T));
 }
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -131,6 +130,9 @@ __device__ __forceinline__ unsigned group_mask(int lane) {
   if constexpr (G == 32) return kFull;
   else return ((1u << G) - 1u) << (lane & ~(G - 1));
 }
+// a > b ? a : b -- two selects; fmax() costs a NaN fix-up and three more moves per call, and nothing here is NaN unless
+// the solve has already failed
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 template <int G>
 __device__ __forceinline__ double grp_sum(double v, unsigned gm) {
 #pragma unroll
@@ -140,27 +142,56 @@ __device__ __forceinline__ double grp_sum(double v, unsigned gm) {
 template <int G>
 __device__ __forceinline__ double grp_max(double v, unsigned gm) {
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o));
+  for (int o = G / 2; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(gm, v, o));
   return v;
+}
+// true when `p` holds on every lane of the group.  The half-warp kernels vote with the whole warp (their groups run
+// in lock step through every place this is used) and look at their own half of the ballot.
+template <int G>
+__device__ __forceinline__ bool grp_all(bool p) {
+  if constexpr (G == 32) return __all_sync(kFull, p);
+  else {
+    const unsigned sh = (threadIdx.x & 31u) & ~(unsigned)(G - 1), ones = (1u << G) - 1u;
+    return ((__ballot_sync(kFull, p) >> sh) & ones) == ones;
+  }
+}
+// One step of a scan inside a lane group: v += the value held `o` lanes below (above), when that lane belongs to
+// the group.  shfl.sync reports that in a predicate, which saves the lane-index compares of `if (gl >= o) v += t`
+// (ptxas still turns the predicated add into an add and a select): 4 % fewer instructions in the solver loop.
+template <int G>
+__device__ __forceinline__ void scan_step_up(double& v, unsigned o, unsigned gm) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tlo, thi;\n\t.reg .f64 t;\n\t"
+               "mov.b64 {lo, hi}, %0;\n\t"
+               "shfl.sync.up.b32 tlo|p, lo, %1, %2, %3;\n\t"
+               "shfl.sync.up.b32 thi, hi, %1, %2, %3;\n\t"
+               "mov.b64 t, {tlo, thi};\n\t"
+               "@p add.rn.f64 %0, %0, t;\n\t}"
+               : "+d"(v) : "r"(o), "n"((32 - G) << 8), "r"(gm));
+}
+template <int G>
+__device__ __forceinline__ void scan_step_down(double& v, unsigned o, unsigned gm) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tlo, thi;\n\t.reg .f64 t;\n\t"
+               "mov.b64 {lo, hi}, %0;\n\t"
+               "shfl.sync.down.b32 tlo|p, lo, %1, %2, %3;\n\t"
+               "shfl.sync.down.b32 thi, hi, %1, %2, %3;\n\t"
+               "mov.b64 t, {tlo, thi};\n\t"
+               "@p add.rn.f64 %0, %0, t;\n\t}"
+               : "+d"(v) : "r"(o), "n"(((32 - G) << 8) | 0x1f), "r"(gm));
 }
 // inclusive prefix sum over the group's lanes
 template <int G>
 __device__ __forceinline__ double grp_scan(double v, int gl, unsigned gm) {
 #pragma unroll
-  for (int o = 1; o < G; o <<= 1) {
-    double t = __shfl_up_sync(gm, v, o, G);
-    if (gl >= o) v += t;
-  }
+  for (int o = 1; o < G; o <<= 1) scan_step_up<G>(v, (unsigned)o, gm);
+  (void)gl;
   return v;
 }
 // inclusive suffix sum: out[gl] = sum_{l >= gl} v[l]
 template <int G>
 __device__ __forceinline__ double grp_rscan(double v, int gl, unsigned gm) {
 #pragma unroll
-  for (int o = 1; o < G; o <<= 1) {
-    double t = __shfl_down_sync(gm, v, o, G);
-    if (gl + o < G) v += t;
-  }
+  for (int o = 1; o < G; o <<= 1) scan_step_down<G>(v, (unsigned)o, gm);
+  (void)gl;
   return v;
 }
 
@@ -296,11 +327,14 @@ __device__ __forceinline__ void rows_apply(const double* u, int T, int gl, unsig
   const double dn = __shfl_down_sync(gm, d, 1, G);
   z[0] = a; z[1] = d; z[2] = dn - d; z[3] = grp_scan<G>(a, gl, gm);
 }
-// the same for a vector held in registers (a = entry gl, d = entry T + gl; 0 beyond the horizon)
+// the same for a vector held in registers (a = entry gl, d = entry T + gl; 0 beyond the horizon), with exact zeros
+// on the dead rows (z[0], z[1] are zero there by construction)
 template <int G>
-__device__ __forceinline__ void rows_apply_reg(double a, double d, int gl, unsigned gm, double z[4]) {
+__device__ __forceinline__ void rows_apply_reg(double a, double d, int gl, unsigned gm, bool live013, bool live2,
+                                               double z[4]) {
   const double dn = __shfl_down_sync(gm, d, 1, G);
-  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = grp_scan<G>(a, gl, gm);
+  const double run = grp_scan<G>(a, gl, gm);
+  z[0] = a; z[1] = d; z[2] = live2 ? dn - d : 0.0; z[3] = live013 ? run : 0.0;
 }
 // (A' t): this lane's entries for a_k (ra) and delta_k (rd); dead rows must carry t = 0
 template <int G>
@@ -586,7 +620,12 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
 // its own data with its commits switched off, so the iterate it reports is the one it was done with.
 template <int TT, int G>
 __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* smem_base, const double* pscr, int gl,
-                                       unsigned gm, bool& converged_out, unsigned& tma_parity, const unsigned short* lut) {
+                                       bool& converged_out, unsigned& tma_parity, const chol_task* lut) {
+  // The groups of a warp go through this whole phase in lock step (uniform control flow, see above), so its
+  // shuffles and synchronisations name the whole warp: a mask held in a register costs a MATCH / REDUX / VOTE
+  // sequence in front of every group of shuffles (3.5 % of the half-warp kernel's instructions); the shuffles' width
+  // (G) keeps the groups' data apart.  Phases A and C have group-uniform early exits and keep the group masks.
+  constexpr unsigned gm = kFull;
   const int T = (TT > 0) ? TT : A.T;
   const int n = 2 * T, nb = nblk(n);
   WarpMem M(smem_base, T);
@@ -595,6 +634,10 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
   // Stage k = lane owns four two-sided rows: r = 0 accel box, 1 steer box, 2 steer rate k -> k+1, 3 speed
   // (running sum of a up to k).  Only slacks and multipliers stay in registers across the factorisation;
   // bounds are rebuilt from the parameter block when needed.
+  // Dead rows (lanes beyond the horizon; the rate row of the last stage) keep lambda = 0 and ds = dl = 0 exactly for
+  // the whole solve, so every product with their multipliers vanishes by itself: only the quantities that would
+  // otherwise be non-zero on them (row residuals, the rate / running-sum rows of A du, the centring term) are
+  // switched off explicitly.
   double sh[4], sl[4], lh[4], ll[4];
   const bool live013 = gl < T, live2 = gl < T - 1;
   auto is_live = [&](int r) -> bool { return r == 2 ? live2 : live013; };
@@ -642,7 +685,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     double* stash = M.grad;                         // [8][T]: rph[0..3], rpl[0..3] of stage = lane
     double z[4], ish[4], isl[4], t4[4];
     rows_apply<G>(M.u, T, gl, gm, z);
-    double mu = 0.0, rpmax = 0.0;
+    double mu = 0.0, rpmax = 0.0;                   // rpmax: this lane's largest primal row residual
     double w2, w3;
     {
       double w[4];
@@ -654,10 +697,10 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
         const double rpl_r = lv ? (-z[r] + sl[r] + bound_lo(r)) : 0.0;
         if (gl < T) { stash[r * T + gl] = rph_r; stash[(4 + r) * T + gl] = rpl_r; }
         // predictor (affine) complementarity target rc = lambda s:  (lambda rp - rc) / s = lambda (rp - s) / s
-        t4[r] = lv ? (fma(lh[r], rph_r, -lh[r] * sh[r]) * ish[r] - fma(ll[r], rpl_r, -ll[r] * sl[r]) * isl[r]) : 0.0;
-        w[r] = lv ? fma(lh[r], ish[r], ll[r] * isl[r]) : 0.0;
+        t4[r] = fma(lh[r], rph_r, -lh[r] * sh[r]) * ish[r] - fma(ll[r], rpl_r, -ll[r] * sl[r]) * isl[r];
+        w[r] = fma(lh[r], ish[r], ll[r] * isl[r]);
         mu += lh[r] * sh[r] + ll[r] * sl[r];
-        rpmax = fmax(rpmax, fmax(fabs(rph_r), fabs(rpl_r)));
+        rpmax = dmax(rpmax, dmax(fabs(rph_r), fabs(rpl_r)));
       }
       w2 = w[2]; w3 = w[3];
       double wup = __shfl_up_sync(gm, w2, 1, G);
@@ -666,7 +709,6 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       if (gl < T) { M.wA[gl] = w[0]; M.wD[gl] = w[1] + w2 + wup; M.wR[gl] = w2; M.SW[gl] = sw; }
     }
     mu = grp_sum<G>(mu, gm) * inv_rows;
-    rpmax = grp_max<G>(rpmax, gm);
     double ra_p, rd_p;                              // A' (predictor row terms)
     rows_apply_T<G>(t4, gl, gm, ra_p, rd_p);
     // P u is formed from the clean Hessian: folding the barrier weights in first and subtracting them again
@@ -679,7 +721,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     double pu0, pu1;                              // rows gl and T + gl of P u
     symv_rows<(TT > 0) ? ((2 * TT + 3) >> 2) : 0>(M.K, M.u, T, nb, gl, pu0, pu1);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) t4[r] = is_live(r) ? (lh[r] - ll[r]) : 0.0;
+    for (int r = 0; r < 4; ++r) t4[r] = lh[r] - ll[r];
     double ra, rd;
     rows_apply_T<G>(t4, gl, gm, ra, rd);
     // gradient of the Lagrangian (dual residual), kept in registers: g0 for a_gl, g1 for delta_gl
@@ -691,10 +733,10 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       // accel x accel block: + SW[max(i, j)] (+ wA on the diagonal), done by half tiles; the task table of the
       // Cholesky update for m = ceil(T / 4) block rows enumerates exactly these tiles
       const int ma = (T + 3) >> 2, ntasks = ma * (ma + 1);
-      const unsigned short* tasks = lut + chol_lut_offset(ma);
+      const chol_task* tasks = lut + chol_lut_offset(ma);
       for (int q = gl; q < ntasks; q += G) {
-        const unsigned e = tasks[q];
-        const int I = (int)(e & 15u), Jc = (int)((e >> 4) & 15u), h = (int)((e >> 8) & 1u) << 1;
+        const chol_task e = tasks[q];
+        const int I = task_a(e), Jc = task_b(e), h = task_h(e) << 1;
         double* tile = M.K + tile_off(I, Jc) + 4 * h;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -717,23 +759,31 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       M.K[elem_off(i, i)] += M.wD[gl];
       if (gl >= 1) M.K[elem_off(i, i - 1)] -= M.wR[gl - 1];
     }
-    double rdmax = fmax(fabs(g0), fabs(g1));
-    rdmax = grp_max<G>(rdmax, gm);
+    // The exit tests only compare the largest primal / dual residual of the group with three thresholds each, so the
+    // lanes compare their own maxima and vote (six votes) instead of reducing two maxima over the group (ten
+    // 64-bit shuffle steps with their compares and selects).
+    const double rdmax_l = dmax(fabs(g0), fabs(g1));
+    const bool rp_strict = grp_all<G>(rpmax <= A.tol_res), rp_red = grp_all<G>(rpmax <= 1e-7), rp_brk = grp_all<G>(rpmax <= 1e-9);
+    const bool rd_strict = grp_all<G>(rdmax_l <= A.tol_res * gscale), rd_red = grp_all<G>(rdmax_l <= 1e-7 * gscale);
+    const bool rd_brk = grp_all<G>(rdmax_l <= 1e-9 * gscale);
+#ifdef JMPC_DEBUG_RESID
+    const double rpmax_g = grp_max<G>(rpmax, gm), rdmax = grp_max<G>(rdmax_l, gm);
+#endif
     __syncwarp(gm);
     if (!kLock || !done) {
-      if (mu <= A.mu_tol && rpmax <= A.tol_res && rdmax <= A.tol_res * gscale) { converged = true; done = true; }
+      if (mu <= A.mu_tol && rp_strict && rd_strict) { converged = true; done = true; }
       // Complementarity three orders below its target with the primal rows satisfied: the iterate has converged;
       // what is left in the dual residual is multiplier noise on the active rows (w ~ 1e16 by now, their slacks are
       // at roundoff), which lies in the span of the active normals and does not move u.  Iterating further only
       // amplifies it.  Measured on 200k instances: controls at such exits are within 1e-8 of the oracle.
-      else if (mu <= 1e-3 * A.mu_tol && rpmax <= A.tol_res) { converged = true; done = true; }
+      else if (mu <= 1e-3 * A.mu_tol && rp_strict) { converged = true; done = true; }
       // Reduced tolerances, the analogue of the OPTIMAL_INACCURATE status the reference accepts (mpc.py:199): used
       // when the factorisation breaks down numerically a step or two before the strict target (w ~ 1e13 by then),
       // or the iteration cap is hit.  Measured: such iterates are still 5-6x inside the control tolerance.
-      else acceptable = (mu <= 1e-9 && rpmax <= 1e-7 && rdmax <= 1e-7 * gscale);
+      else acceptable = (mu <= 1e-9 && rp_red && rd_red);
       if (kLock && done) my_iters = it;
 #ifdef JMPC_DEBUG_RESID
-      dbg_mu = mu; dbg_rp = rpmax; dbg_rd = rdmax / gscale;
+      dbg_mu = mu; dbg_rp = rpmax_g; dbg_rd = rdmax / gscale;
 #endif
     }
     if (kLock ? __all_sync(kFull, done) : done) break;
@@ -749,7 +799,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     // already two orders inside the reduced tolerances: stop here.  The step computed from the patched factor is
     // usually harmless, but on a few instances in 10^5 (weakly active speed rows, T = 25) it threw the iterate far
     // enough out that the iteration cap was reached; which instances depended on the build.
-    if ((!kLock || !done) && !clean && mu <= 1e-11 && rpmax <= 1e-9 && rdmax <= 1e-9 * gscale) {
+    if ((!kLock || !done) && !clean && mu <= 1e-11 && rp_brk && rd_brk) {
       acceptable = true; done = true;
       if (kLock) my_iters = it;
     }
@@ -767,12 +817,14 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       }
       if (phase == 1) {
         double th[4];
+        const double sm013 = live013 ? sigma_mu : 0.0, sm2 = live2 ? sigma_mu : 0.0;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const double rch = fma(lh[r], sh[r], dsh[r] * dlh[r] - sigma_mu), rcl = fma(ll[r], sl[r], dsl[r] * dll[r] - sigma_mu);
+          const double sm = (r == 2) ? sm2 : sm013;
+          const double rch = fma(lh[r], sh[r], dsh[r] * dlh[r] - sm), rcl = fma(ll[r], sl[r], dsl[r] * dll[r] - sm);
           const double a_h = fma(lh[r], rph[r], -rch) * ish[r];
           const double a_l = fma(ll[r], rpl[r], -rcl) * isl[r];
-          th[r] = is_live(r) ? (a_h - a_l) : 0.0;
+          th[r] = a_h - a_l;
           dlh[r] = rch; dll[r] = rcl;               // stash rc for the direction recovery below
         }
         rows_apply_T<G>(th, gl, gm, ra, rd);
@@ -791,28 +843,27 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       const double du0 = (gl < T) ? M.rhs[gl] : 0.0, du1 = (gl < T) ? M.rhs[T + gl] : 0.0;
       JMPC_TOCK(ts_, 6);
       double dz[4];
-      rows_apply_reg<G>(du0, du1, gl, gm, dz);
-      // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l).  The maximum ratio is tracked as a
-      // (numerator, denominator) pair compared by cross-multiplication, so the 16 candidates per lane cost no
-      // division (fp64 division is ~20 instructions); one division remains after the group reduction.
-      double wn = 0.0, wd = 1.0;
+      rows_apply_reg<G>(du0, du1, gl, gm, live013, live2, dz);
+      // largest step keeping s, lambda > 0: alpha_max = 1 / max(-ds/s, -dl/l).  The slacks' reciprocals are at hand
+      // (ish, isl), so their ratios are one multiplication each; the multipliers' ratios are tracked as a
+      // (numerator, denominator) pair compared by cross-multiplication and turned into a ratio once per lane (no
+      // fp64 division anywhere: ~20 instructions each).  Dead rows carry zero directions and never bind.
+      double rho = 0.0, wn = 0.0, wd = 1.0;
       auto cand = [&](double num, double den) { if (num * wd > wn * den) { wn = num; wd = den; } };
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const bool lv = is_live(r);
         const double rch = dlh[r], rcl = dll[r];
-        dsh[r] = lv ? (-rph[r] - dz[r]) : 0.0;
-        dsl[r] = lv ? (-rpl[r] + dz[r]) : 0.0;
-        dlh[r] = lv ? (-(fma(lh[r], dsh[r], rch)) * ish[r]) : 0.0;
-        dll[r] = lv ? (-(fma(ll[r], dsl[r], rcl)) * isl[r]) : 0.0;
-        if (lv) { cand(-dsh[r], sh[r]); cand(-dsl[r], sl[r]); cand(-dlh[r], lh[r]); cand(-dll[r], ll[r]); }
+        dsh[r] = -rph[r] - dz[r];
+        dsl[r] = -rpl[r] + dz[r];
+        dlh[r] = -(fma(lh[r], dsh[r], rch)) * ish[r];
+        dll[r] = -(fma(ll[r], dsl[r], rcl)) * isl[r];
+        rho = dmax(rho, dmax(-dsh[r] * ish[r], -dsl[r] * isl[r]));
+        cand(-dlh[r], lh[r]); cand(-dll[r], ll[r]);
       }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {
-        const double on = __shfl_xor_sync(gm, wn, o), od = __shfl_xor_sync(gm, wd, o);
-        if (on * wd > wn * od) { wn = on; wd = od; }
-      }
-      const double amax = (wn > 0.0) ? wd / wn : INFINITY;
+      rho = dmax(rho, wn * rcp_pos(wd));
+      rho = grp_max<G>(rho, gm);
+      // only amax < 1 / 0.99 matters below (the step is capped at 1)
+      const double amax = (rho > 0.5) ? rcp_pos(rho) : 2.0;
       if (phase == 0) {
         const double aa = fmin(1.0, amax);
         aff_step = aa;
@@ -821,7 +872,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
         for (int r = 0; r < 4; ++r)
           mu_aff += fma(aa, dlh[r], lh[r]) * fma(aa, dsh[r], sh[r]) + fma(aa, dll[r], ll[r]) * fma(aa, dsl[r], sl[r]);
         mu_aff = grp_sum<G>(mu_aff, gm) * inv_rows;
-        const double ratio = mu_aff / mu;
+        const double ratio = mu_aff * rcp_pos(mu);
         sigma_mu = ratio * ratio * ratio * mu;
       } else if (!kLock || !done) {
         // Fraction to the boundary tied to the length aa of the affine (predictor) step: a long predictor step
@@ -971,7 +1022,7 @@ __device__ __noinline__ bool step_output(const StepArgs& A, int b, bool active, 
 // preparation and the epilogue need; they communicate through the group's shared memory.
 template <int TT, int G>
 __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, bool active, double* smem_base, double* pscr,
-                                                  int gl, unsigned gm, unsigned& tma_parity, const unsigned short* lut) {
+                                                  int gl, unsigned gm, unsigned& tma_parity, const chol_task* lut) {
   const int T = (TT > 0) ? TT : A.T;
   WarpMem M(smem_base, T);
   // the instance's parameter vector lives in shared memory (uniform reads, no registers held across phases)
@@ -992,7 +1043,7 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, bool
     if (G == 32 ? !active : !__any_sync(kFull, active)) return;
     JMPC_TOCK(ti_, 10);
     bool converged = false;
-    total_iters += step_solve<TT, G>(A, active, smem_base, pscr, gl, gm, converged, tma_parity, lut);
+    total_iters += step_solve<TT, G>(A, active, smem_base, pscr, gl, converged, tma_parity, lut);
     JMPC_TOCK(ti_, 11);
     const bool finished = step_output<TT, G>(A, b, active, smem_base, gl, gm, lin == A.lin_iters - 1, converged, target,
                                              idx, end_mask, total_iters, oa_k, od_k, ov_k);
@@ -1084,8 +1135,11 @@ __global__ void __launch_bounds__(kSchedThreads) schedule_place_kernel(int B, co
 // T = 8 the extra warps pay for the tighter register budget (80 registers, 24 warps: +5 %; at T = 13 / 20 they do
 // not).  At T = 25 shared memory (18.4 KB per instance) admits only three blocks of four warps anyway, so the kernel
 // is compiled for three: 168 registers instead of 128 (measured: 16.8 -> 15.5 ms on 65 536 instances).
+#ifndef JMPC_T8_BLOCKS
+#define JMPC_T8_BLOCKS ((JMPC_MINBLOCKS * 3) / 2)
+#endif
 constexpr int step_min_blocks(int TT) {
-  return TT == 8 ? (JMPC_MINBLOCKS * 3) / 2 : (TT == 25 && JMPC_MINBLOCKS > 3) ? 3 : JMPC_MINBLOCKS;
+  return TT == 8 ? JMPC_T8_BLOCKS : (TT == 25 && JMPC_MINBLOCKS > 3) ? 3 : JMPC_MINBLOCKS;
 }
 template <int TT, int G>
 __global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_kernel(
@@ -1108,8 +1162,8 @@ __global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_k
     __syncwarp();
   }
   // block-shared task table of the Cholesky trailing update, behind the instances' regions
-  unsigned short* lut = reinterpret_cast<unsigned short*>(smem + (size_t)warps_per_block * NG * inst_smem_doubles(T));
-  chol_lut_build(lut, nblk(n) + 1, threadIdx.x, blockDim.x);     // one more block row than the factorisation needs: the K assembly uses m = ceil(T / 4) <= nb
+  chol_task* lut = reinterpret_cast<chol_task*>(smem + (size_t)warps_per_block * NG * inst_smem_doubles(T));
+  chol_lut_build(lut, nblk(n), threadIdx.x, blockDim.x);        // rows m <= nb: the K assembly uses m = ceil(T / 4) <= nb
   __syncthreads();
   for (;;) {
     // the warp takes NG consecutive tickets: with the longest-first order neighbours in the queue have similar
