@@ -334,10 +334,14 @@ __device__ inline void symv_tiles(const double* P, const double* x, int nb, int 
 
 // ---- rows k and T + k per lane ------------------------------------------------------------------------------------
 // The stage rows keep their part of an n = 2T vector in registers: lane k < T owns entries k (the acceleration part)
-// and T + k (the steering part).  The symmetric matvec below produces its result in that layout.  (A triangular
-// solve in the same layout -- block entries fetched by shuffle, no __syncwarp -- was measured too: 20 % shorter for
-// a warp that runs alone, but 2.3x the instructions and 3x the shared-memory wavefronts of solve_tiles, and 12 %
-// slower on a full batch; it was dropped.)
+// and T + k (the steering part).  The symmetric matvec below produces its result in that layout.  (Triangular
+// sweeps with the vector in registers -- block entries fetched by shuffle, no __syncwarp -- were measured twice.
+// Round 1, in this layout: 20 % shorter for a warp that runs alone, 2.3x the instructions, 12 % slower on a full
+// batch.  Round 2, cyclic layout (lane -> entries gl, gl + G), branch-free block steps so that the factor's loads
+// start in the shadow of the shuffles: the three sweeps of an iteration drop from 14.3 k to 8.7 k cycles on a warp
+// that runs alone (iteration 46.2 k -> 41.5 k), but a full batch is 3-6 % slower at T = 13 / 25 and no faster at
+// T = 20: with four warps per scheduler the kernel is bound by instruction issue and the shared-memory pipe, not by
+// one warp's dependency chains.  Dropped both times.)
 template <int G>
 __device__ inline void solve_tiles(const double* K, double* b, int nb, int gl, unsigned gm) {
   solve_forward_tiles<G>(K, b, nb, gl, gm);

@@ -419,23 +419,28 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
   const unsigned end_mask = (__ballot_sync(gm, at_end) >> ((threadIdx.x & 31) & ~(G - 1))) & (unsigned)((1ull << G) - 1ull);
 
   // ---------------- 3. operating-point rollout ----------------------------------------------------
-  // theta and v recurrences need no trigonometry of the state, so every lane walks them redundantly,
-  // then lane t evaluates sin/cos(theta_t) once and the positions are accumulated in sequence.
+  // The speed recurrence (with the plant's clamp) is walked by every lane redundantly, one shuffle per stage; lane t
+  // keeps vbar_t.  The heading is a running sum of per-stage terms that only need the lane's own vbar_t, so it is one
+  // group scan instead of a second shuffle, an fp64 division (v / L: ~50 instructions) and the adds on every stage of
+  // the walk.  The scan adds in a different order than the reference's loop, and v * (1 / L) differs from v / L in
+  // the last bit: the operating point moves by ~1e-16 relative, like the libm differences in tan / sincos (DESIGN.md
+  // section 3); no integer decision depends on it.
   const double max_steer = P(JMPC_P_MAX_STEER), vmax_sim = P(JMPC_P_SIM_MAX_SPEED);
   const double tan_k = tan(fmax(fmin(od_k, max_steer), -max_steer));
-  double vb = v0, th = yaw0;          // lane t ends up holding vbar_t, phibar_t
+  double vb = v0;                     // lane t ends up holding vbar_t
   {
-    double v = v0, ang = yaw0;
+    double v = v0;
+    const double adt_k = __dmul_rn(oa_k, dt);
     for (int t = 0; t < T; ++t) {
-      const double a_t = __shfl_sync(gm, oa_k, t, G);
-      const double tn_t = __shfl_sync(gm, tan_k, t, G);
-      const double yaw_dot = __dmul_rn(v / Lw, tn_t);
-      ang = __dadd_rn(ang, __dmul_rn(yaw_dot, dt));
-      v = __dadd_rn(v, __dmul_rn(a_t, dt));
-      v = fmax(fmin(v, vmax_sim), min_speed);
-      if (gl == t + 1) { vb = v; th = ang; }
+      v = __dadd_rn(v, __shfl_sync(gm, adt_k, t, G));
+      v = v > vmax_sim ? vmax_sim : v;
+      v = v < min_speed ? min_speed : v;
+      if (gl == t + 1) vb = v;
     }
   }
+  const double inv_L = 1.0 / Lw;
+  const double dth = (gl < T) ? __dmul_rn(__dmul_rn(__dmul_rn(vb, inv_L), tan_k), dt) : 0.0;   // heading gained on stage t
+  const double th = yaw0 + (grp_scan<G>(dth, gl, gm) - dth);                                     // phibar_t
   double sn, cs;
   sincos(th, &sn, &cs);
   // (x, y) are only reported (xbar rows 0,1 do not enter the QP); the QP needs vbar, phibar.
