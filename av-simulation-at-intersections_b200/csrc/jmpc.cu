@@ -130,10 +130,27 @@ int step_geometry(jmpc_handle h, int B, int T, StepGeom* g, StepKernel* kernel) 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, wpb * 32, smem));
     if (per_sm < 1) return fail("step kernel does not fit on an SM for this horizon");
     if (cap > 0) per_sm = std::max(1, std::min(per_sm, cap / wpb));
+    // Shared memory and L1 share 256 KB per SM, and the spilled registers of the solver loop (ish / isl, 64 bytes per
+    // thread, read back three times per iteration) live in L1.  Ask for no more shared memory than the resident
+    // blocks use: T = 20 / T = 8 fit into the 196 KB configuration, which leaves 60 KB of L1 instead of 28 KB
+    // (measured: T = 20 0.833 -> 0.808 ms on config 2, T = 8 +1.5 %); T = 13 / T = 25 need the full 228 KB either way.
+    if (carve == cudaSharedmemCarveoutMaxShared) {
+      int smem_sm = 0;
+      CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+      const size_t need = (size_t)per_sm * (smem + 1024);       // 1 KB per block is reserved by the system
+      if (smem_sm > 0) {
+        const int pct = (int)std::min<size_t>(100, (need * 100 + (size_t)smem_sm - 1) / (size_t)smem_sm);
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        int check = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&check, k, wpb * 32, smem));
+        if (check < per_sm) CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        else carve = pct;
+      }
+    }
     c.kernel = k; c.groups = groups; c.wpb = wpb; c.per_sm = per_sm; c.smem = smem; c.ready = true;
     if (getenv("JMPC_DEBUG"))
-      fprintf(stderr, "[jmpc] step geometry: T=%d %d instance(s) per warp, %d blocks per SM x %d warps, smem/block=%zu\n", T,
-              groups, per_sm, wpb, smem);
+      fprintf(stderr, "[jmpc] step geometry: T=%d %d instance(s) per warp, %d blocks per SM x %d warps, smem/block=%zu, carve-out %d\n",
+              T, groups, per_sm, wpb, smem, carve);
   }
   int blocks = h->sm_count * c.per_sm;
   const int per_block = c.wpb * c.groups;
