@@ -254,9 +254,12 @@ def main():
     ap.add_argument("--states-per-point", type=int, default=32, help="config 5: states per parameter point (32 = 1M instances)")
     ap.add_argument("--ref-sample", type=int, default=1024, help="reference arm: instances per step for configs 3-5")
     ap.add_argument("--cpu-sample", type=int, default=2048)
-    ap.add_argument("--gather", default="flags", choices=["flags", "barrier", "nccl"],
-                    help="N > 1: fused gather completed by flags the step kernel publishes (default), fused gather + "
-                         "cross-GPU barrier after every step, or one NCCL all-gather per step")
+    ap.add_argument("--gather", default="barrier", choices=["barrier", "flags", "deferred", "nccl"],
+                    help="N > 1: fused gather (record stores over NVLink in the step kernel's epilogue) completed by a "
+                         "cross-GPU signal-pad barrier after every step (default: measured fastest and with the "
+                         "tightest p99 at 4 and 8 GPUs); completed by flags the step kernel publishes, every step "
+                         "waiting for its own table (flags) or for the previous step's (deferred: ranks run uncoupled, "
+                         "the last step pays the skew); or one NCCL all-gather per step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -335,13 +338,17 @@ def main():
         if args.gather != "nccl":
             try:
                 from junction_mpc.distributed import FusedRecordGather
-                fused = FusedRecordGather(mpc, B_global, slices[0]["row0"], sync=args.gather)
+                fused = FusedRecordGather(mpc, B_global, slices[0]["row0"], sync="barrier" if args.gather == "barrier" else "flags")
                 gather_kind = ("fused: the step kernel's epilogue stores every record into every rank's table (NVLink "
                                "symmetric memory, ring of %d tables); " % fused.buffers +
                                ("completion by flags: the kernel's last block publishes the step number to every rank, and "
+                                "every step ends with the wait for all ranks' records of THIS step (a complete table "
+                                "inside every timed step, no barrier kernel)" if args.gather == "flags" else
+                                "completion by flags: the kernel's last block publishes the step number to every rank, and "
                                 "every step ends with the wait for all ranks' records of the PREVIOUS step (the last timed "
-                                "step also waits for its own), so the gather runs one step behind the solves"
-                                if args.gather == "flags" else "cross-GPU signal-pad barrier after every step"))
+                                "step also waits for its own and so pays the skew the ranks have built up), so the gather "
+                                "runs one step behind the solves" if args.gather == "deferred" else
+                                "cross-GPU signal-pad barrier after every step"))
             except Exception as exc:            # noqa: BLE001
                 if rank == 0:
                     print(f"[bench] fused gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
@@ -375,6 +382,8 @@ def main():
         if fused is not None:
             fused.finish()                     # the records are already on their way into every peer's table
             if args.gather == "flags":
+                fused.wait(fused.step_no)
+            elif args.gather == "deferred":
                 fused.wait(fused.step_no if final else fused.step_no - 1)
         elif world > 1:
             for d in devs:
