@@ -486,7 +486,10 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
     const double A_ = vt ? ca_t : 0.0, B_ = vt ? cb_t : 0.0, C_ = vt ? cc_t : 0.0, K_ = vt ? ck_t : 0.0;
     double* mom = M.K;
     const int ms = even_up(T + 1);
-    auto put = [&](int m, double v) { const double sfx = grp_rscan<G>(v, gl, gm); if (gl <= T) mom[m * ms + gl] = sfx; };
+    // every lane (stage) stores its 23 terms; the suffix sums are then taken along the stages by one lane per sequence
+    // (a serial add chain of T + 1 terms in shared memory: ~100 instructions per lane instead of 23 group scans of
+    // 4-5 shuffle steps each, ~900)
+    auto put = [&](int m, double v) { if (gl <= T) mom[m * ms + gl] = v; };
     put(MOM_11, w11); put(MOM_11_A, w11 * A_); put(MOM_11_B, w11 * B_);
     put(MOM_11_AA, w11 * A_ * A_); put(MOM_11_AB, w11 * A_ * B_); put(MOM_11_BB, w11 * B_ * B_);
     put(MOM_12, w12); put(MOM_12_A, w12 * A_); put(MOM_12_B, w12 * B_); put(MOM_12_C, w12 * C_); put(MOM_12_K, w12 * K_);
@@ -494,6 +497,12 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
     put(MOM_22, w22); put(MOM_22_C, w22 * C_); put(MOM_22_K, w22 * K_);
     put(MOM_22_CC, w22 * C_ * C_); put(MOM_22_CK, w22 * C_ * K_); put(MOM_22_KK, w22 * K_ * K_);
     put(MOM_QV, wv); put(MOM_QPSI, wpsi);
+    __syncwarp(gm);
+    for (int m = gl; m < MOM_COUNT; m += G) {
+      double* seq = mom + m * ms;
+      double acc = 0.0;
+      for (int t = T; t >= 0; --t) { acc += seq[t]; seq[t] = acc; }
+    }
   }
   const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 - vr, eps = yaw0 - psir;
   if (gl <= T) {
