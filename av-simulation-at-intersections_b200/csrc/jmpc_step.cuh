@@ -87,10 +87,10 @@ static_assert(JMPC_NPARAM + 3 <= kParamSlots, "parameter block too small");
 
 // suffix-moment slots of the Hessian assembly (step_prep): weight x centred prefix products
 enum MomentSlot {
-  MOM_11, MOM_11_A, MOM_11_B, MOM_11_AA, MOM_11_AB, MOM_11_BB,
-  MOM_12, MOM_12_A, MOM_12_B, MOM_12_C, MOM_12_K, MOM_12_AC, MOM_12_AK, MOM_12_BC, MOM_12_BK,
-  MOM_22, MOM_22_C, MOM_22_K, MOM_22_CC, MOM_22_CK, MOM_22_KK,
-  MOM_QV, MOM_QPSI, MOM_COUNT
+  MOM_11, MOM_11_B, MOM_11_BB,
+  MOM_12, MOM_12_B, MOM_12_K, MOM_12_BK,
+  MOM_22, MOM_22_K, MOM_22_KK,
+  MOM_QPSI, MOM_WX, MOM_WY, MOM_COUNT
 };
 
 // shared-memory doubles one instance needs for horizon T (every sub-array starts 16-byte aligned)
@@ -319,27 +319,31 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   } while (!done);
 }
 
-// z = A u for the stage rows (u in shared memory)
+// z = A u for the stage rows (u = [s; delta] in shared memory): acceleration s_k - s_{k-1}, steering angle, steering
+// rate delta_{k+1} - delta_k, cumulative acceleration s_k (the speed row).  Rows beyond the horizon are garbage here
+// and switched off by the caller.
 template <int G>
 __device__ __forceinline__ void rows_apply(const double* u, int T, int gl, unsigned gm, double z[4]) {
-  const double a = (gl < T) ? u[gl] : 0.0;
+  const double sk = (gl < T) ? u[gl] : 0.0, sm = (gl >= 1 && gl <= T) ? u[gl - 1] : 0.0;
   const double d = (gl < T) ? u[T + gl] : 0.0;
   const double dn = __shfl_down_sync(gm, d, 1, G);
-  z[0] = a; z[1] = d; z[2] = dn - d; z[3] = grp_scan<G>(a, gl, gm);
+  z[0] = sk - sm; z[1] = d; z[2] = dn - d; z[3] = sk;
 }
 // the same for a vector held in registers (a = entry gl, d = entry T + gl; 0 beyond the horizon), with exact zeros
-// on the dead rows (z[0], z[1] are zero there by construction)
+// on the dead rows (z[1], z[3] are zero there by construction)
 template <int G>
 __device__ __forceinline__ void rows_apply_reg(double a, double d, int gl, unsigned gm, bool live013, bool live2,
                                                double z[4]) {
   const double dn = __shfl_down_sync(gm, d, 1, G);
-  const double run = grp_scan<G>(a, gl, gm);
-  z[0] = a; z[1] = d; z[2] = live2 ? dn - d : 0.0; z[3] = live013 ? run : 0.0;
+  double am = __shfl_up_sync(gm, a, 1, G);
+  if (gl == 0) am = 0.0;
+  z[0] = live013 ? a - am : 0.0; z[1] = d; z[2] = live2 ? dn - d : 0.0; z[3] = a;
 }
-// (A' t): this lane's entries for a_k (ra) and delta_k (rd); dead rows must carry t = 0
+// (A' t): this lane's entries for s_k (ra) and delta_k (rd); dead rows must carry t = 0
 template <int G>
 __device__ __forceinline__ void rows_apply_T(const double t[4], int gl, unsigned gm, double& ra, double& rd) {
-  ra = t[0] + grp_rscan<G>(t[3], gl, gm);
+  const double t0n = __shfl_down_sync(gm, t[0], 1, G);     // the acceleration row of stage k + 1 (0 behind the horizon;
+  ra = t[0] - t0n + t[3];                                  //  the group's last lane is never a live stage)
   double up = __shfl_up_sync(gm, t[2], 1, G);
   if (gl == 0) up = 0.0;
   rd = t[1] - t[2] + up;
@@ -450,13 +454,19 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
   if (gl < T) {
     al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw;
   }
-  // exclusive prefix sums c*[t] = sum_{j<t} (.)  for t = 0..T  (lane t).  Only differences c[t] - c[k] are ever
-  // used, so each array is centred on its mid-horizon value: that halves the magnitudes entering the moment
-  // expansion of the Hessian below.
-  double ca_t = grp_scan<G>(al, gl, gm) - al, cb_t = grp_scan<G>(be, gl, gm) - be;
-  double cc_t = grp_scan<G>(ga, gl, gm) - ga, ck_t = grp_scan<G>(ka, gl, gm) - ka;
-  ca_t -= __shfl_sync(gm, ca_t, T >> 1, G); cb_t -= __shfl_sync(gm, cb_t, T >> 1, G);
-  cc_t -= __shfl_sync(gm, cc_t, T >> 1, G); ck_t -= __shfl_sync(gm, ck_t, T >> 1, G);
+  // The unknowns of the condensed problem are the CUMULATIVE accelerations s_k = a_0 + ... + a_k and the steering
+  // angles delta_k: v_t = v0 + dt s_{t-1}, so a speed row is a box on s_k and an acceleration row the difference
+  // s_k - s_{k-1} -- no running sums in A or A' (seven group scans per interior-point iteration in the a_k form), and
+  // the barrier term A' W A is tridiagonal in both blocks.  A position depends on s_k through v_{k+1} only:
+  //   dX_t / ds_k = dt alpha_{k+1},  dY_t / ds_k = dt gamma_{k+1}   for t >= k + 2,
+  // constant in t, so the s-block of the Hessian needs plain suffix sums of the stage weights.  The steering
+  // sensitivities are  dX_t / ddelta_i = -g_i (B_t - B_{i+1}),  dY_t / ddelta_i = g_i (K_t - K_{i+1})  with the
+  // exclusive prefix sums B, K of beta, kappa (lane t: t = 0..T).  Only differences of B, K are ever used, so both
+  // are centred on their mid-horizon value: that halves the magnitudes entering the moment expansion below.
+  double cb_t = grp_scan<G>(be, gl, gm) - be, ck_t = grp_scan<G>(ka, gl, gm) - ka;
+  cb_t -= __shfl_sync(gm, cb_t, T >> 1, G); ck_t -= __shfl_sync(gm, ck_t, T >> 1, G);
+  // alpha_{k+1}, gamma_{k+1} for stage k (0 for k = T - 1: s_{T-1} moves no position inside the horizon)
+  const double al_next = __shfl_down_sync(gm, al, 1, G), ga_next = __shfl_down_sync(gm, ga, 1, G);
   // free response (u = 0): v = v0, psi = yaw0
   const double fx_term = (gl < T) ? (al * v0 - be * (yaw0 - th)) : 0.0;
   const double fy_term = (gl < T) ? (ga * v0 + ka * (yaw0 - th)) : 0.0;
@@ -478,25 +488,23 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
       wv = P(JMPC_P_Q_V); wpsi = P(JMPC_P_Q_YAW);
     }
   }
-  // Suffix moments  mom[m][t0] = sum_{t >= t0} W_t * (product of centred prefix values at t),  23 sequences, kept
+  // Suffix moments  mom[m][t0] = sum_{t >= t0} W_t * (product of centred prefix values at t),  13 sequences, kept
   // in the K region (free until the solver starts).  With them every Hessian entry is O(1):
   //   sum_{t>=t0} W (F_t - F0)(G_t - G0) = M_WFG - G0 M_WF - F0 M_WG + F0 G0 M_W.
+  const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 - vr, eps = yaw0 - psir;
+  const double wex = w11 * ex + w12 * ey, wey = w12 * ex + w22 * ey;
   {
     const bool vt = (gl >= 1 && gl <= T);
-    const double A_ = vt ? ca_t : 0.0, B_ = vt ? cb_t : 0.0, C_ = vt ? cc_t : 0.0, K_ = vt ? ck_t : 0.0;
+    const double B_ = vt ? cb_t : 0.0, K_ = vt ? ck_t : 0.0;
     double* mom = M.K;
     const int ms = even_up(T + 1);
-    // every lane (stage) stores its 23 terms; the suffix sums are then taken along the stages by one lane per sequence
-    // (a serial add chain of T + 1 terms in shared memory: ~100 instructions per lane instead of 23 group scans of
-    // 4-5 shuffle steps each, ~900)
+    // every lane (stage) stores its terms; the suffix sums are then taken along the stages by one lane per sequence
+    // (a serial add chain of T + 1 terms in shared memory instead of a group scan of 4-5 shuffle steps per sequence)
     auto put = [&](int m, double v) { if (gl <= T) mom[m * ms + gl] = v; };
-    put(MOM_11, w11); put(MOM_11_A, w11 * A_); put(MOM_11_B, w11 * B_);
-    put(MOM_11_AA, w11 * A_ * A_); put(MOM_11_AB, w11 * A_ * B_); put(MOM_11_BB, w11 * B_ * B_);
-    put(MOM_12, w12); put(MOM_12_A, w12 * A_); put(MOM_12_B, w12 * B_); put(MOM_12_C, w12 * C_); put(MOM_12_K, w12 * K_);
-    put(MOM_12_AC, w12 * A_ * C_); put(MOM_12_AK, w12 * A_ * K_); put(MOM_12_BC, w12 * B_ * C_); put(MOM_12_BK, w12 * B_ * K_);
-    put(MOM_22, w22); put(MOM_22_C, w22 * C_); put(MOM_22_K, w22 * K_);
-    put(MOM_22_CC, w22 * C_ * C_); put(MOM_22_CK, w22 * C_ * K_); put(MOM_22_KK, w22 * K_ * K_);
-    put(MOM_QV, wv); put(MOM_QPSI, wpsi);
+    put(MOM_11, w11); put(MOM_11_B, w11 * B_); put(MOM_11_BB, w11 * B_ * B_);
+    put(MOM_12, w12); put(MOM_12_B, w12 * B_); put(MOM_12_K, w12 * K_); put(MOM_12_BK, w12 * B_ * K_);
+    put(MOM_22, w22); put(MOM_22_K, w22 * K_); put(MOM_22_KK, w22 * K_ * K_);
+    put(MOM_QPSI, wpsi); put(MOM_WX, vt ? wex : 0.0); put(MOM_WY, vt ? wey : 0.0);
     __syncwarp(gm);
     for (int m = gl; m < MOM_COUNT; m += G) {
       double* seq = mom + m * ms;
@@ -504,13 +512,14 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
       for (int t = T; t >= 0; --t) { acc += seq[t]; seq[t] = acc; }
     }
   }
-  const double ex = xf_t - xr, ey = yf_t - yr, ev = v0 - vr, eps = yaw0 - psir;
   if (gl <= T) {
-    M.ca[gl] = ca_t; M.cb[gl] = cb_t; M.cc[gl] = cc_t; M.ck[gl] = ck_t;
-    M.WeX[gl] = w11 * ex + w12 * ey; M.WeY[gl] = w12 * ex + w22 * ey;
+    M.cb[gl] = cb_t; M.ck[gl] = ck_t;
+    M.WeX[gl] = wex; M.WeY[gl] = wey;
     M.epsi[gl] = wpsi * eps;          // weighted yaw error per stage
     M.grad[gl] = wv * ev;             // weighted speed error per stage (grad is free until the solver starts)
+    M.cc[gl] = wv;                    // speed weight of stage t (the s-block's diagonal)
   }
+  if (gl < T) { M.ca[gl] = al_next; M.wD[gl] = ga_next; }     // alpha_{k+1}, gamma_{k+1} (wD is free until the solver starts)
   if (gl < T) M.wA[gl] = gk;          // borrow wA for g_k during condensing
   if (gl <= T) { M.vb[gl] = vb; M.th[gl] = th; }       // operating point, reused by the epilogue
   if (gl == 0) {                      // derived row bounds, read back by the solver
@@ -522,7 +531,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
   const double Ra = P(JMPC_P_R_A), Rd_ = P(JMPC_P_R_D), Rda = P(JMPC_P_RD_A), Rdd = P(JMPC_P_RD_D);
   const double Rea = P(JMPC_P_REND_A), Red = P(JMPC_P_REND_D);
   const double dt2 = dt * dt;
-  // Hessian on 4x4 tiles (jmpc_linalg.cuh), variable order [a_0..a_{T-1}, delta_0..delta_{T-1}]; the last
+  // Hessian on 4x4 tiles (jmpc_linalg.cuh), variable order [s_0..s_{T-1}, delta_0..delta_{T-1}]; the last
   // block row is cleared first so that the identity padding (n -> multiple of 4) is in place
   {
     const int last0 = tile_off(nb - 1, 0), last1 = tiles_doubles(n);
@@ -551,27 +560,36 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
       }
       return (ki == kj + 1) ? -2.0 * rd_w : 0.0;
     };
-    {                                  // accel x accel: sX = dt (A - A0), sY = dt (C - C0), sV = dt
+    // the tridiagonal input-weight matrix of the a_k formulation, any index order, zero outside the horizon
+    auto Mw = [&](int i, int j, double r_run, double r_end, double rd_w) -> double {
+      if (i >= T || j >= T) return 0.0;
+      return input_weights(max(i, j), min(i, j), r_run, r_end, rd_w);
+    };
+    {                                  // s x s: sX_{t,k} = dt alpha_{k+1}, sY_{t,k} = dt gamma_{k+1} for t >= k + 2; sV_{k+1,k} = dt
       int ki = 0, kj = gl;
       while (kj > ki) { kj -= ki + 1; ++ki; }
       for (int e = gl; e < tri(T); e += G) {
-        const double* mom = M.K + ki + 1;                      // t0 = max(ki, kj) + 1 = ki + 1
-        const double ai = M.ca[ki + 1], ci = M.cc[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-        double acc = S(mom, MOM_11, MOM_11_A, MOM_11_A, MOM_11_AA, ai, aj) + S(mom, MOM_12, MOM_12_A, MOM_12_C, MOM_12_AC, ai, cj)
-                   + S(mom, MOM_12, MOM_12_C, MOM_12_A, MOM_12_AC, ci, aj) + S(mom, MOM_22, MOM_22_C, MOM_22_C, MOM_22_CC, ci, cj)
-                   + mom[MOM_QV * ms];
-        acc = 2.0 * dt2 * acc + input_weights(ki, kj, Ra, Rea, Rda);
+        const double* mom = M.K + min(ki + 2, T);              // t0 = max(ki, kj) + 2 (the factor in front is 0 beyond T)
+        const double ai = M.ca[ki], gi = M.wD[ki], aj = M.ca[kj], gj = M.wD[kj];
+        double acc = ai * aj * mom[MOM_11 * ms] + (ai * gj + gi * aj) * mom[MOM_12 * ms] + gi * gj * mom[MOM_22 * ms];
+        if (ki == kj) acc += M.cc[ki + 1];
+        acc *= 2.0 * dt2;
+        // input weights: a = D s (a_k = s_k - s_{k-1}), so the band is D' M D, pentadiagonal
+        if (ki - kj <= 2)
+          acc += Mw(ki, kj, Ra, Rea, Rda) - Mw(ki + 1, kj, Ra, Rea, Rda) - Mw(ki, kj + 1, Ra, Rea, Rda) +
+                 Mw(ki + 1, kj + 1, Ra, Rea, Rda);
         store(ki, kj, acc);
         kj += G;
         while (kj > ki) { kj -= ki + 1; ++ki; }
       }
     }
-    for (int e = gl; e < T * T; e += G) {                      // steer (row) x accel (col): sX_i = -g (B - B0), sY_i = g (K - K0)
+    for (int e = gl; e < T * T; e += G) {                      // steer (row) x s (col): sX_i = -g (B - B0), sY_i = g (K - K0)
       const int ki = e / T, kj = e - ki * T;
-      const double* mom = M.K + max(ki, kj) + 1;
-      const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj + 1], cj = M.cc[kj + 1];
-      double acc = -S(mom, MOM_11, MOM_11_B, MOM_11_A, MOM_11_AB, bi, aj) - S(mom, MOM_12, MOM_12_B, MOM_12_C, MOM_12_BC, bi, cj)
-                 + S(mom, MOM_12, MOM_12_K, MOM_12_A, MOM_12_AK, kki, aj) + S(mom, MOM_22, MOM_22_K, MOM_22_C, MOM_22_CK, kki, cj);
+      const double* mom = M.K + min(max(ki + 1, kj + 2), T);
+      const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj], gj = M.wD[kj];
+      const double s11 = mom[MOM_11 * ms], s12 = mom[MOM_12 * ms], s22 = mom[MOM_22 * ms];
+      double acc = -aj * (mom[MOM_11_B * ms] - bi * s11) - gj * (mom[MOM_12_B * ms] - bi * s12)
+                 + aj * (mom[MOM_12_K * ms] - kki * s12) + gj * (mom[MOM_22_K * ms] - kki * s22);
       acc *= 2.0 * M.wA[ki] * dt;
       store(T + ki, kj, acc);
     }
@@ -594,13 +612,14 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
   // linear term
   if (gl < T) {
     const int k = gl;
-    const double ai = M.ca[k + 1], ci = M.cc[k + 1], bi = M.cb[k + 1], kki = M.ck[k + 1];
-    double qa = 0.0, qd = 0.0;
-    for (int t = k + 1; t <= T; ++t) {
-      qa += dt * ((M.ca[t] - ai) * M.WeX[t] + (M.cc[t] - ci) * M.WeY[t]) + dt * M.grad[t];
+    const double bi = M.cb[k + 1], kki = M.ck[k + 1];
+    const int ms = even_up(T + 1);
+    const double* mom = M.K + min(k + 2, T);
+    const double qs = dt * (M.ca[k] * mom[MOM_WX * ms] + M.wD[k] * mom[MOM_WY * ms]) + dt * M.grad[k + 1];
+    double qd = 0.0;
+    for (int t = k + 1; t <= T; ++t)
       qd += gk * (-(M.cb[t] - bi) * M.WeX[t] + (M.ck[t] - kki) * M.WeY[t]) + gk * M.epsi[t];
-    }
-    M.q[k] = 2.0 * qa; M.q[T + k] = 2.0 * qd;
+    M.q[k] = 2.0 * qs; M.q[T + k] = 2.0 * qd;
     M.u[k] = 0.0; M.u[T + k] = 0.0;
   }
   if (gl < n4 - n) { M.q[n + gl] = 0.0; M.u[n + gl] = 0.0; M.rhs[n + gl] = 0.0; M.grad[n + gl] = 0.0; }
@@ -719,8 +738,10 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       w2 = w[2]; w3 = w[3];
       double wup = __shfl_up_sync(gm, w2, 1, G);
       if (gl == 0) wup = 0.0;
-      const double sw = grp_rscan<G>(w3, gl, gm);
-      if (gl < T) { M.wA[gl] = w[0]; M.wD[gl] = w[1] + w2 + wup; M.wR[gl] = w2; M.SW[gl] = sw; }
+      const double w0n = __shfl_down_sync(gm, w[0], 1, G);          // acceleration row of the next stage (0 behind the horizon)
+      // A' W A is tridiagonal in both blocks: the diagonal terms (wA: s block, wD: steering block) and the
+      // sub-diagonal ones (SW: -w0_k at (k, k-1); wR: -w2_{k-1} at (T+k, T+k-1))
+      if (gl < T) { M.wA[gl] = w[0] + w0n + w3; M.SW[gl] = w[0]; M.wD[gl] = w[1] + w2 + wup; M.wR[gl] = w2; }
     }
     mu = grp_sum<G>(mu, gm) * inv_rows;
     double ra_p, rd_p;                              // A' (predictor row terms)
@@ -742,36 +763,12 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     const double g0 = (gl < T) ? pu0 + M.q[gl] + ra : 0.0, g1 = (gl < T) ? pu1 + M.q[T + gl] + rd : 0.0;
     __syncwarp(gm);                               // every lane is done reading P before K is assembled in place
     JMPC_TOCK(ts_, 2);
-    // K = P + A' diag(w) A: only the accel block and the steer tridiagonal change
-    {
-      // accel x accel block: + SW[max(i, j)] (+ wA on the diagonal), done by half tiles; the task table of the
-      // Cholesky update for m = ceil(T / 4) block rows enumerates exactly these tiles
-      const int ma = (T + 3) >> 2, ntasks = ma * (ma + 1);
-      const chol_task* tasks = lut + chol_lut_offset(ma);
-      for (int q = gl; q < ntasks; q += G) {
-        const chol_task e = tasks[q];
-        const int I = task_a(e), Jc = task_b(e), h = task_h(e) << 1;
-        double* tile = M.K + tile_off(I, Jc) + 4 * h;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int i = (I << 2) + h + r, j0 = Jc << 2;
-          if (i < T) {
-            const double sw = M.SW[i], wa = M.wA[i];
-            double c0, c1, c2, c3;
-            ld4(tile + 4 * r, c0, c1, c2, c3);
-            c0 += (j0 <= i) ? sw + ((j0 == i) ? wa : 0.0) : 0.0;
-            c1 += (j0 + 1 <= i) ? sw + ((j0 + 1 == i) ? wa : 0.0) : 0.0;
-            c2 += (j0 + 2 <= i) ? sw + ((j0 + 2 == i) ? wa : 0.0) : 0.0;
-            c3 += (j0 + 3 <= i) ? sw + ((j0 + 3 == i) ? wa : 0.0) : 0.0;
-            st4(tile + 4 * r, c0, c1, c2, c3);
-          }
-        }
-      }
-    }
+    // K = P + A' diag(w) A: a tridiagonal in each block (only the lower triangle is read by the factorisation)
     if (gl < T) {
       const int i = T + gl;
+      M.K[elem_off(gl, gl)] += M.wA[gl];
       M.K[elem_off(i, i)] += M.wD[gl];
-      if (gl >= 1) M.K[elem_off(i, i - 1)] -= M.wR[gl - 1];
+      if (gl >= 1) { M.K[elem_off(gl, gl - 1)] -= M.SW[gl]; M.K[elem_off(i, i - 1)] -= M.wR[gl - 1]; }
     }
     // The exit tests only compare the largest primal / dual residual of the group with three thresholds each, so the
     // lanes compare their own maxima and vote (six votes) instead of reducing two maxima over the group (ten
@@ -960,8 +957,12 @@ __device__ __noinline__ bool step_output(const StepArgs& A, int b, bool active, 
   double al = 0.0, be = 0.0, ga = 0.0, ka = 0.0, gk = 0.0;
   if (gl < T) { al = dt * cs; be = dt * vb * sn; ga = dt * sn; ka = dt * vb * cs; gk = dt * vb / Lw; }
   // ---------------- 6. states of the linearised model for the solution ---------------------------
-  const double a_sol = (gl < T) ? M.u[gl] : 0.0, d_sol = (gl < T) ? M.u[T + gl] : 0.0;
-  const double v_t = v0 + dt * (grp_scan<G>(a_sol, gl, gm) - a_sol);                  // lane t: v_t
+  // the solver's unknowns are the cumulative accelerations s_k: a_k = s_k - s_{k-1}, v_t = v0 + dt s_{t-1}
+  const double s_sol = (gl < T) ? M.u[gl] : 0.0, d_sol = (gl < T) ? M.u[T + gl] : 0.0;
+  double s_prev = __shfl_up_sync(gm, s_sol, 1, G);
+  if (gl == 0) s_prev = 0.0;
+  const double a_sol = (gl < T) ? s_sol - s_prev : 0.0;
+  const double v_t = v0 + dt * s_prev;                                                // lane t: v_t
   const double gd = gk * d_sol;
   const double psi_t = yaw0 + (grp_scan<G>(gd, gl, gm) - gd);
   const double tx = (gl < T) ? (al * v_t - be * (psi_t - th)) : 0.0;
