@@ -12,6 +12,12 @@ so the states are eliminated exactly: n = 2T unknowns u = [a_0..a_{T-1}, delta_0
 m = 4T-1 two-sided rows (T accel boxes, T steer boxes, T-1 steer-rate rows, T speed rows as bounds on the
 running sum of a).  This file exists to localise a discrepancy (condensing vs solver) and to prototype the
 solver; tests compare it with the sparse oracle.
+
+Since the second half of round 2 the CUDA kernel solves the same problem in the unknowns [s_0..s_{T-1}, delta] with
+s_k = a_0 + ... + a_k (a linear change of variables: same rows, same slacks, same interior-point iterates): the
+speed rows become boxes on s_k, the acceleration rows differences, and A' W A is tridiagonal in both blocks.
+`condense_cumulative` below is the numpy statement of that condensing; the solver model further down is still
+written in the a_k form.
 """
 from __future__ import annotations
 
@@ -94,6 +100,104 @@ def condense(p: Params, xref: np.ndarray, xbar: np.ndarray, x0, reaches_end) -> 
     hi = np.concatenate([np.full(T, p.max_accel), np.full(T, p.max_steer), np.full(T - 1, lim),
                          np.full(T, (p.speed - x0[2]) / dt)])
     return CondensedQP(P=P, q=q, c0=c0, A=A, lo=lo, hi=hi, S=S, xfree=xfree)
+
+
+# ----------------------------------------------------------------------------------------------------
+# The same problem in cumulative accelerations (what csrc/jmpc_step.cuh builds): speed rows are boxes on s_k,
+# acceleration rows differences, A' W A tridiagonal in both blocks.
+# ----------------------------------------------------------------------------------------------------
+def cumulative_transform(T: int) -> np.ndarray:
+    """E with [a; delta] = E [s; delta]:  a_k = s_k - s_{k-1}."""
+    D = np.eye(T) - np.eye(T, k=-1)
+    return np.block([[D, np.zeros((T, T))], [np.zeros((T, T)), np.eye(T)]])
+
+
+def _sfx(v):
+    return np.cumsum(v[::-1])[::-1]
+
+
+def condense_cumulative(p: Params, xref: np.ndarray, xbar: np.ndarray, x0, reach):
+    """(P, q) of the condensed QP in the unknowns the CUDA kernel uses since round 2: [s_0..s_{T-1}, delta_0..delta_{T-1}]
+    with s_k = a_0 + ... + a_k, computed the way the kernel computes it (suffix sums of the stage weights and of
+    their first / second moments).  Must equal E' P E, E' q of `condense` with u = E [s; delta], a_k = s_k - s_{k-1}."""
+    T, dt = p.T, p.dt
+    vb, ph = xbar[2], xbar[3]
+    al = np.append(dt * np.cos(ph[:T]), 0.0)            # index T: 0 (s_{T-1} moves no position)
+    be = dt * vb[:T] * np.sin(ph[:T])
+    ga = np.append(dt * np.sin(ph[:T]), 0.0)
+    ka = dt * vb[:T] * np.cos(ph[:T])
+    g = dt * vb[:T] / p.L
+    cb = np.concatenate([[0.0], np.cumsum(be)])          # exclusive prefix sums, t = 0..T
+    ck = np.concatenate([[0.0], np.cumsum(ka)])
+    cb -= cb[T // 2]; ck -= ck[T // 2]                   # centred as in the kernel
+    W = np.zeros((T + 2, 4, 4))
+    for t in range(1, T + 1):
+        W[t] = stage_state_weight(p, float(xref[3, t]), bool(reach[t]))
+    w11, w12, w22, wv, wpsi = W[:, 0, 0], W[:, 0, 1], W[:, 1, 1], W[:, 2, 2], W[:, 3, 3]
+    # free response (s = 0, delta = 0)
+    xf = np.zeros(T + 1); yf = np.zeros(T + 1)
+    xf[0], yf[0] = x0[0], x0[1]
+    for t in range(T):
+        xf[t + 1] = xf[t] + al[t] * x0[2] - be[t] * (x0[3] - ph[t])
+        yf[t + 1] = yf[t] + ga[t] * x0[2] + ka[t] * (x0[3] - ph[t])
+    ex = np.append(xf - xref[0], 0.0); ey = np.append(yf - xref[1], 0.0)
+    ev = np.append(x0[2] - xref[2], 0.0); eps = np.append(x0[3] - xref[3], 0.0)
+    WeX, WeY = w11 * ex + w12 * ey, w12 * ex + w22 * ey
+    # suffix sums over stages t >= m, m = 0..T+1 (index T+1: 0)
+    B_, K_ = np.append(cb, 0.0), np.append(ck, 0.0)
+    S11, S12, S22 = _sfx(w11), _sfx(w12), _sfx(w22)
+    M11B, M12B, M12K, M22K = _sfx(w11 * B_), _sfx(w12 * B_), _sfx(w12 * K_), _sfx(w22 * K_)
+    M11BB, M12BK, M22KK = _sfx(w11 * B_ * B_), _sfx(w12 * B_ * K_), _sfx(w22 * K_ * K_)
+    SPSI, SX, SY, SE = _sfx(wpsi), _sfx(WeX), _sfx(WeY), _sfx(wpsi * eps)
+    SXB, SYK = _sfx(WeX * B_), _sfx(WeY * K_)
+    n = 2 * T
+    P = np.zeros((n, n)); q = np.zeros(n)
+    dt2 = dt * dt
+    for i in range(T):
+        for j in range(i + 1):
+            m = min(i + 2, T + 1)                        # max(i, j) + 2
+            P[i, j] = 2 * dt2 * (al[i + 1] * al[j + 1] * S11[m] + (al[i + 1] * ga[j + 1] + ga[i + 1] * al[j + 1]) * S12[m]
+                                 + ga[i + 1] * ga[j + 1] * S22[m])
+        P[i, i] += 2 * dt2 * wv[i + 1]
+        m = min(i + 2, T + 1)
+        q[i] = 2 * dt * (al[i + 1] * SX[m] + ga[i + 1] * SY[m]) + 2 * dt * wv[i + 1] * ev[i + 1]
+    # input weights on a = D s: B = D' M D with the tridiagonal M of the a-formulation
+    def Mw(i, j):
+        if i >= T or j >= T or abs(i - j) > 1:
+            return 0.0
+        if i == j:
+            r = (p.R_end if reach[i] else p.R)[0]
+            nbr = (1 if (i == 0 or i == T - 1) else 2) if T >= 2 else 0
+            return 2 * r + 2 * p.Rd[0] * nbr
+        return -2 * p.Rd[0]
+    for i in range(T):
+        for j in range(max(0, i - 2), i + 1):
+            P[i, j] += Mw(i, j) - Mw(i + 1, j) - Mw(i, j + 1) + Mw(i + 1, j + 1)
+    for i in range(T):                                   # steer (row) x cumulative acceleration (col)
+        for j in range(T):
+            m = min(max(i + 1, j + 2), T + 1)
+            bi, ki = cb[i + 1], ck[i + 1]
+            acc = (-al[j + 1] * (M11B[m] - bi * S11[m]) - ga[j + 1] * (M12B[m] - bi * S12[m])
+                   + al[j + 1] * (M12K[m] - ki * S12[m]) + ga[j + 1] * (M22K[m] - ki * S22[m]))
+            P[T + i, j] = 2 * g[i] * dt * acc
+    for i in range(T):                                   # steer x steer, as in the a-formulation
+        for j in range(i + 1):
+            m = i + 1
+            bi, ki, bj, kj = cb[i + 1], ck[i + 1], cb[j + 1], ck[j + 1]
+            s11 = M11BB[m] - (bi + bj) * M11B[m] + bi * bj * S11[m]
+            s12a = M12BK[m] - kj * M12B[m] - bi * M12K[m] + bi * kj * S12[m]
+            s12b = M12BK[m] - bj * M12K[m] - ki * M12B[m] + ki * bj * S12[m]
+            s22 = M22KK[m] - (ki + kj) * M22K[m] + ki * kj * S22[m]
+            P[T + i, T + j] = 2 * g[i] * g[j] * (s11 - s12a - s12b + s22 + SPSI[m])
+        r = (p.R_end if reach[i] else p.R)[1]
+        nbr = (1 if (i == 0 or i == T - 1) else 2) if T >= 2 else 0
+        P[T + i, T + i] += 2 * r + 2 * p.Rd[1] * nbr
+        if i >= 1:
+            P[T + i, T + i - 1] -= 2 * p.Rd[1]
+        m = i + 1
+        q[T + i] = 2 * g[i] * (-(SXB[m] - cb[i + 1] * SX[m]) + (SYK[m] - ck[i + 1] * SY[m]) + SE[m])
+    P = np.tril(P) + np.tril(P, -1).T
+    return P, q
 
 
 def states_from_controls(c: CondensedQP, u: np.ndarray) -> np.ndarray:

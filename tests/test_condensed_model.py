@@ -72,3 +72,19 @@ def test_interior_point_model_meets_the_parity_gate(cases):
         assert scaled_err(u[:T], r.oa) <= 1.0 and scaled_err(u[T:], r.od) <= 1.0
         assert abs(CM.objective(cq, u) - r.cost) <= 1e-6 * max(1.0, abs(r.cost))
     assert np.mean(iters) < 14
+
+
+def test_cumulative_acceleration_form(cases):
+    """The unknowns of the CUDA kernel are s_k = a_0 + ... + a_k (csrc/jmpc_step.cuh, step_prep): its Hessian and
+    linear term, computed from suffix sums as the kernel does, are E' P E and E' q of the a_k formulation."""
+    for p, x0, r in cases:
+        cq = CM.condense(p, r.xref, r.xbar, x0, r.reaches_end)
+        E = CM.cumulative_transform(p.T)
+        P, q = CM.condense_cumulative(p, r.xref, r.xbar, x0, r.reaches_end)
+        Pt, qt = E.T @ cq.P @ E, E.T @ cq.q
+        assert np.abs(P - Pt).max() <= 1e-11 * np.abs(Pt).max()
+        assert np.abs(q - qt).max() <= 1e-11 * max(np.abs(qt).max(), 1.0)
+        # same optimiser: the solution in s maps onto the controls
+        u_ref = np.concatenate([r.oa, r.od])
+        s_ref = np.linalg.solve(E, u_ref)
+        np.testing.assert_allclose(s_ref[:p.T], np.cumsum(r.oa), rtol=0, atol=1e-12)
