@@ -97,41 +97,32 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
 }
 
 // Task table of the trailing update: for block column J, task q (half a tile) -> tile row I = J + 1 + a, tile
-// column Kc = J + 1 + b (b <= a), half h.  (a, b, h) only depend on m = nb - J - 1; the entry also carries the slot
+// column Kc = J + 1 + b (b <= a), half h.  (a, b, h) only depend on m = nb - J - 1; the entry carries the slot
 // numbers of the two factor tiles the task reads for the launch's block count nb (J = nb - 1 - m), so the kernel
 // forms its three addresses with one multiply-add each instead of evaluating tile_off() three times (the integer
-// work was a quarter of the update's instructions).  One table of sum_{m=1}^{nb} m (m + 1) 32-bit entries per block,
-// built once per launch in shared memory.  (Decoding q arithmetically -- float sqrt plus fix-up loops -- was 4 % of
-// the kernel's instructions.)
+// work was a quarter of the update's instructions).  One table of sum_{m=1}^{nb-1} m (m + 1) 32-bit entries per
+// block, built once per launch in shared memory.  (Decoding q arithmetically -- float sqrt plus fix-up loops -- was
+// 4 % of the kernel's instructions.)
 //   bits 0-7   slot of tile (I, J)            bits 8-15  slot of tile (Kc, J)
 //   bits 16-19 b + 1 (slot of (I, Kc) = slot of (I, J) + b + 1)       bit 22  h (so (e >> 16) & 0x40 = byte offset of the half)
-//   bits 24-27 a
-// The rows m = nb of the table (no column of the factorisation has that many block rows below it) are there for the
-// solver's K assembly, which walks the accel block with (a, b, h) alone.
 typedef unsigned int chol_task;
 __host__ __device__ inline int chol_lut_entries(int nb) { return ((nb - 1) * nb * (nb + 1)) / 3; }
 __host__ __device__ __forceinline__ int chol_lut_offset(int m) { return ((m - 1) * m * (m + 1)) / 3; }   // tasks of all m' < m
-__host__ __device__ inline size_t chol_lut_bytes(int nb) { return ((size_t)chol_lut_entries(nb + 1) * sizeof(chol_task) + 15) & ~(size_t)15; }
-__device__ __forceinline__ int task_a(chol_task e) { return (int)((e >> 24) & 15u); }
-__device__ __forceinline__ int task_b(chol_task e) { return (int)((e >> 16) & 15u) - 1; }
-__device__ __forceinline__ int task_h(chol_task e) { return (int)((e >> 22) & 1u); }
-// table for a factorisation with nb block rows (rows m = 1 .. nb)
+__host__ __device__ inline size_t chol_lut_bytes(int nb) { return ((size_t)chol_lut_entries(nb) * sizeof(chol_task) + 15) & ~(size_t)15; }
+// table for a factorisation with nb block rows (rows m = 1 .. nb - 1)
 __device__ inline void chol_lut_build(chol_task* lut, int nb, int tid, int nthreads) {
-  for (int m = 1; m <= nb; ++m) {
+  for (int m = 1; m < nb; ++m) {
     const int ntasks = m * (m + 1), off = chol_lut_offset(m);
-    const int J = nb - 1 - m;                       // -1 for the extra row: slots unused there
+    const int J = nb - 1 - m;
     for (int q = tid; q < ntasks; q += nthreads) {
       const int t = q >> 1;
       int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
       while (((a + 1) * (a + 2) >> 1) <= t) ++a;
       while (((a * (a + 1)) >> 1) > t) --a;
       const int b = t - ((a * (a + 1)) >> 1);
-      unsigned e = ((unsigned)(b + 1) << 16) | ((unsigned)(q & 1) << 22) | ((unsigned)a << 24);
-      if (J >= 0) {
-        const int I = J + 1 + a, Kc = J + 1 + b;
-        e |= (unsigned)(((I * (I + 1)) >> 1) + J) | ((unsigned)(((Kc * (Kc + 1)) >> 1) + J) << 8);
-      }
-      lut[off + q] = e;
+      const int I = J + 1 + a, Kc = J + 1 + b;
+      lut[off + q] = ((unsigned)(b + 1) << 16) | ((unsigned)(q & 1) << 22) | (unsigned)(((I * (I + 1)) >> 1) + J) |
+                     ((unsigned)(((Kc * (Kc + 1)) >> 1) + J) << 8);
     }
   }
 }

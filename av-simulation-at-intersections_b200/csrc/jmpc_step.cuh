@@ -107,8 +107,8 @@ __host__ __device__ inline int inst_smem_doubles(int T) {
   const int n = 2 * T, n4 = nblk(n) << 2, T1e = even_up(T + 1), Te = even_up(T);
   return k_region_doubles(T)    // K / L on 4x4 tiles (and the condensing's moment tables)
          + 4 * n4               // u, q, rhs, grad
-         + (9 + JMPC_PAD_T1E) * T1e   // prefix sums ca, cb, cc, ck; WeX, WeY, epsi; vb, th
-         + 4 * Te               // per-iteration row weights wA, wD, wR, SW
+         + (9 + JMPC_PAD_T1E) * T1e   // alp, cb, wvs, ck (condensing); WeX, WeY, epsi; vb, th
+         + 4 * Te               // per-iteration barrier terms wA, wD, wR, wS
          + kParamSlots          // the instance's parameter vector + derived row bounds
          + 2;                   // mbarrier of the TMA Hessian copy (8 bytes, padded to 16)
 }
@@ -276,9 +276,9 @@ __device__ inline int nearest_index(const double* __restrict__ cx, const double*
 // ---- per-instance shared-memory views ------------------------------------------------------------------
 struct WarpMem {
   double *K, *u, *q, *rhs, *grad;
-  double *ca, *cb, *cc, *ck;
+  double *alp, *cb, *wvs, *ck;          // condensing: alpha_{k+1}, centred prefix sums B, speed weight per stage, K
   double *WeX, *WeY, *epsi, *vb, *th;
-  double *wA, *wD, *wR, *SW;
+  double *wA, *wD, *wR, *wS;            // solver: barrier terms of K (wA / wD diagonal, wS / wR sub-diagonal, s / steering block)
   double *prm;
   unsigned long long* mbar;
   __device__ WarpMem(double* base, int T) {
@@ -287,11 +287,11 @@ struct WarpMem {
     K = p; p += k_region_doubles(T);
     u = p; p += n4; q = p; p += n4; rhs = p; p += n4; grad = p; p += n4;
     // grad .. epsi are dead while the solver runs: 4 (2T) + 7 (T + 1) >= 8T doubles, the solver's row stash
-    ca = p; p += T1e; cb = p; p += T1e; cc = p; p += T1e; ck = p; p += T1e;
+    alp = p; p += T1e; cb = p; p += T1e; wvs = p; p += T1e; ck = p; p += T1e;
     WeX = p; p += T1e; WeY = p; p += T1e; epsi = p; p += T1e;
     p += JMPC_PAD_T1E * T1e;
     vb = p; p += T1e; th = p; p += T1e;
-    wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; SW = p; p += Te;
+    wA = p; p += Te; wD = p; p += Te; wR = p; p += Te; wS = p; p += Te;
     prm = p; p += kParamSlots;
     mbar = reinterpret_cast<unsigned long long*>(p);
   }
@@ -517,10 +517,10 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
     M.WeX[gl] = wex; M.WeY[gl] = wey;
     M.epsi[gl] = wpsi * eps;          // weighted yaw error per stage
     M.grad[gl] = wv * ev;             // weighted speed error per stage (grad is free until the solver starts)
-    M.cc[gl] = wv;                    // speed weight of stage t (the s-block's diagonal)
+    M.wvs[gl] = wv;                   // speed weight of stage t (the s-block's diagonal)
   }
-  if (gl < T) { M.ca[gl] = al_next; M.wD[gl] = ga_next; }     // alpha_{k+1}, gamma_{k+1} (wD is free until the solver starts)
-  if (gl < T) M.wA[gl] = gk;          // borrow wA for g_k during condensing
+  if (gl < T) { M.alp[gl] = al_next; M.wD[gl] = ga_next; }    // alpha_{k+1}, gamma_{k+1} (gamma borrows wD, free until the solver starts)
+  if (gl < T) M.wA[gl] = gk;          // g_k borrows wA during condensing
   if (gl <= T) { M.vb[gl] = vb; M.th[gl] = th; }       // operating point, reused by the epilogue
   if (gl == 0) {                      // derived row bounds, read back by the solver
     M.prm[kSlotHi3] = (speed - v0) / dt; M.prm[kSlotLo3] = (min_speed - v0) / dt;
@@ -540,7 +540,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
     if (gl < n4 - n) pscr[elem_off(n + gl, n + gl)] = 1.0;
   }
   {
-    // Three passes, one per block type (accel x accel, steer x accel, steer x steer): a single pass over the packed
+    // Three passes, one per block type (s x s, steer x s, steer x steer): a single pass over the packed
     // triangle mixed steer x accel and steer x steer entries in every group of lanes, so the warp executed both paths.
     const int ms = even_up(T + 1);
     // S(W; F, G)(F0, G0) = sum_{t >= t0} W_t (F_t - F0)(G_t - G0) from the suffix moments
@@ -570,9 +570,9 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
       while (kj > ki) { kj -= ki + 1; ++ki; }
       for (int e = gl; e < tri(T); e += G) {
         const double* mom = M.K + min(ki + 2, T);              // t0 = max(ki, kj) + 2 (the factor in front is 0 beyond T)
-        const double ai = M.ca[ki], gi = M.wD[ki], aj = M.ca[kj], gj = M.wD[kj];
+        const double ai = M.alp[ki], gi = M.wD[ki], aj = M.alp[kj], gj = M.wD[kj];
         double acc = ai * aj * mom[MOM_11 * ms] + (ai * gj + gi * aj) * mom[MOM_12 * ms] + gi * gj * mom[MOM_22 * ms];
-        if (ki == kj) acc += M.cc[ki + 1];
+        if (ki == kj) acc += M.wvs[ki + 1];
         acc *= 2.0 * dt2;
         // input weights: a = D s (a_k = s_k - s_{k-1}), so the band is D' M D, pentadiagonal
         if (ki - kj <= 2)
@@ -586,7 +586,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
     for (int e = gl; e < T * T; e += G) {                      // steer (row) x s (col): sX_i = -g (B - B0), sY_i = g (K - K0)
       const int ki = e / T, kj = e - ki * T;
       const double* mom = M.K + min(max(ki + 1, kj + 2), T);
-      const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.ca[kj], gj = M.wD[kj];
+      const double bi = M.cb[ki + 1], kki = M.ck[ki + 1], aj = M.alp[kj], gj = M.wD[kj];
       const double s11 = mom[MOM_11 * ms], s12 = mom[MOM_12 * ms], s22 = mom[MOM_22 * ms];
       double acc = -aj * (mom[MOM_11_B * ms] - bi * s11) - gj * (mom[MOM_12_B * ms] - bi * s12)
                  + aj * (mom[MOM_12_K * ms] - kki * s12) + gj * (mom[MOM_22_K * ms] - kki * s22);
@@ -615,7 +615,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
     const double bi = M.cb[k + 1], kki = M.ck[k + 1];
     const int ms = even_up(T + 1);
     const double* mom = M.K + min(k + 2, T);
-    const double qs = dt * (M.ca[k] * mom[MOM_WX * ms] + M.wD[k] * mom[MOM_WY * ms]) + dt * M.grad[k + 1];
+    const double qs = dt * (M.alp[k] * mom[MOM_WX * ms] + M.wD[k] * mom[MOM_WY * ms]) + dt * M.grad[k + 1];
     double qd = 0.0;
     for (int t = k + 1; t <= T; ++t)
       qd += gk * (-(M.cb[t] - bi) * M.WeX[t] + (M.ck[t] - kki) * M.WeY[t]) + gk * M.epsi[t];
@@ -740,8 +740,8 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       if (gl == 0) wup = 0.0;
       const double w0n = __shfl_down_sync(gm, w[0], 1, G);          // acceleration row of the next stage (0 behind the horizon)
       // A' W A is tridiagonal in both blocks: the diagonal terms (wA: s block, wD: steering block) and the
-      // sub-diagonal ones (SW: -w0_k at (k, k-1); wR: -w2_{k-1} at (T+k, T+k-1))
-      if (gl < T) { M.wA[gl] = w[0] + w0n + w3; M.SW[gl] = w[0]; M.wD[gl] = w[1] + w2 + wup; M.wR[gl] = w2; }
+      // sub-diagonal ones (wS: -w0_k at (k, k-1); wR: -w2_{k-1} at (T+k, T+k-1))
+      if (gl < T) { M.wA[gl] = w[0] + w0n + w3; M.wS[gl] = w[0]; M.wD[gl] = w[1] + w2 + wup; M.wR[gl] = w2; }
     }
     mu = grp_sum<G>(mu, gm) * inv_rows;
     double ra_p, rd_p;                              // A' (predictor row terms)
@@ -759,7 +759,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     for (int r = 0; r < 4; ++r) t4[r] = lh[r] - ll[r];
     double ra, rd;
     rows_apply_T<G>(t4, gl, gm, ra, rd);
-    // gradient of the Lagrangian (dual residual), kept in registers: g0 for a_gl, g1 for delta_gl
+    // gradient of the Lagrangian (dual residual), kept in registers: g0 for s_gl, g1 for delta_gl
     const double g0 = (gl < T) ? pu0 + M.q[gl] + ra : 0.0, g1 = (gl < T) ? pu1 + M.q[T + gl] + rd : 0.0;
     __syncwarp(gm);                               // every lane is done reading P before K is assembled in place
     JMPC_TOCK(ts_, 2);
@@ -768,7 +768,7 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
       const int i = T + gl;
       M.K[elem_off(gl, gl)] += M.wA[gl];
       M.K[elem_off(i, i)] += M.wD[gl];
-      if (gl >= 1) { M.K[elem_off(gl, gl - 1)] -= M.SW[gl]; M.K[elem_off(i, i - 1)] -= M.wR[gl - 1]; }
+      if (gl >= 1) { M.K[elem_off(gl, gl - 1)] -= M.wS[gl]; M.K[elem_off(i, i - 1)] -= M.wR[gl - 1]; }
     }
     // The exit tests only compare the largest primal / dual residual of the group with three thresholds each, so the
     // lanes compare their own maxima and vote (six votes) instead of reducing two maxima over the group (ten
@@ -1178,7 +1178,7 @@ __global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_k
   }
   // block-shared task table of the Cholesky trailing update, behind the instances' regions
   chol_task* lut = reinterpret_cast<chol_task*>(smem + (size_t)warps_per_block * NG * inst_smem_doubles(T));
-  chol_lut_build(lut, nblk(n), threadIdx.x, blockDim.x);        // rows m <= nb: the K assembly uses m = ceil(T / 4) <= nb
+  chol_lut_build(lut, nblk(n), threadIdx.x, blockDim.x);
   __syncthreads();
   for (;;) {
     // the warp takes NG consecutive tickets: with the longest-first order neighbours in the queue have similar
