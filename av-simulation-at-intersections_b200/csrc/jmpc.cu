@@ -78,7 +78,13 @@ struct jmpc_handle_s {
   struct HostBlock { char* base; size_t bytes; char* dev; };
   std::vector<HostBlock> host_blocks;   // page-locked blocks from jmpc_host_alloc (+ h_stage) with their device mapping
   // launch geometry of the step kernel per horizon, resolved once (function attributes, occupancy)
-  struct Geom { bool ready = false; void (*kernel)(const jmpc::StepArgs) = nullptr; int groups = 1, wpb = 0, per_sm = 0; size_t smem = 0; };
+  struct Geom {
+    bool ready = false;
+    void (*kernel)(const jmpc::StepArgs) = nullptr;
+    void (*kernel_lat)(const jmpc::StepArgs) = nullptr;      // low-latency variant, one warp per block
+    int groups = 1, wpb = 0, per_sm = 0;
+    size_t smem = 0, smem_lat = 0;
+  };
   Geom geom[JMPC_MAX_T + 1];
 };
 
@@ -91,18 +97,23 @@ using StepKernel = void (*)(const jmpc::StepArgs);
 
 // Horizons with a compile-time specialisation; anything else runs a generic kernel.  Horizons up to 15 (T + 1 <= 16
 // horizon points) run two instances per warp, one per half (jmpc_step.cuh).
-StepKernel step_kernel_for(int T, int* groups) {
-  *groups = 32 / jmpc::group_lanes_for(T);
+// `lat`: the low-latency variant (jmpc_step.cuh), for launches of a handful of instances.
+template <bool LAT>
+StepKernel step_kernel_variant(int T, int groups) {
 #ifdef JMPC_EXPERIMENT
-  if (getenv("JMPC_GENERIC")) return *groups == 2 ? jmpc::mpc_step_kernel<0, 16> : jmpc::mpc_step_kernel<0, 32>;
+  if (getenv("JMPC_GENERIC")) return groups == 2 ? jmpc::mpc_step_kernel<0, 16, LAT> : jmpc::mpc_step_kernel<0, 32, LAT>;
 #endif
   switch (T) {
-    case 8: return jmpc::mpc_step_kernel<8, 16>;
-    case 13: return jmpc::mpc_step_kernel<13, 16>;
-    case 20: return jmpc::mpc_step_kernel<20, 32>;
-    case 25: return jmpc::mpc_step_kernel<25, 32>;
-    default: return *groups == 2 ? jmpc::mpc_step_kernel<0, 16> : jmpc::mpc_step_kernel<0, 32>;
+    case 8: return jmpc::mpc_step_kernel<8, 16, LAT>;
+    case 13: return jmpc::mpc_step_kernel<13, 16, LAT>;
+    case 20: return jmpc::mpc_step_kernel<20, 32, LAT>;
+    case 25: return jmpc::mpc_step_kernel<25, 32, LAT>;
+    default: return groups == 2 ? jmpc::mpc_step_kernel<0, 16, LAT> : jmpc::mpc_step_kernel<0, 32, LAT>;
   }
+}
+StepKernel step_kernel_for(int T, int* groups, bool lat = false) {
+  *groups = 32 / jmpc::group_lanes_for(T);
+  return lat ? step_kernel_variant<true>(T, *groups) : step_kernel_variant<false>(T, *groups);
 }
 
 // Function attributes and occupancy are resolved once per (handle, T): the single-ego call runs this path every
@@ -147,10 +158,24 @@ int step_geometry(jmpc_handle h, int B, int T, StepGeom* g, StepKernel* kernel) 
         else carve = pct;
       }
     }
-    c.kernel = k; c.groups = groups; c.wpb = wpb; c.per_sm = per_sm; c.smem = smem; c.ready = true;
+    // the low-latency variant runs one warp per block, so that a handful of instances spread over as many SMs
+    StepKernel kl = step_kernel_for(T, &groups, true);
+    const size_t smem_lat = jmpc::step_block_smem_bytes(T, 1, groups);
+    CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(kl, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    c.kernel = k; c.kernel_lat = kl; c.groups = groups; c.wpb = wpb; c.per_sm = per_sm; c.smem = smem; c.smem_lat = smem_lat;
+    c.ready = true;
     if (getenv("JMPC_DEBUG"))
       fprintf(stderr, "[jmpc] step geometry: T=%d %d instance(s) per warp, %d blocks per SM x %d warps, smem/block=%zu, carve-out %d\n",
               T, groups, per_sm, wpb, smem, carve);
+  }
+  // A launch of at most two warps per SM is latency-bound on single warps: it gets the low-latency kernel, one warp
+  // per block (a single ego's step: 0.274 -> LAT_MS ms at T = 20).  Everything else is throughput-bound.
+  if ((long long)B <= 2ll * h->sm_count * c.groups && h->opt.warps_per_sm <= 0) {
+    const int blocks = (B + c.groups - 1) / c.groups;
+    g->blocks = blocks; g->threads = 32; g->smem = c.smem_lat; g->groups_total = blocks * c.groups;
+    *kernel = c.kernel_lat;
+    return 0;
   }
   int blocks = h->sm_count * c.per_sm;
   const int per_block = c.wpb * c.groups;

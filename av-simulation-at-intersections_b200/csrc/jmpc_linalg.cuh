@@ -292,6 +292,125 @@ __device__ inline void solve_backward_tiles(const double* K, double* b, int nb, 
   }
 }
 
+// ---- triangular sweeps with the vector in registers (the low-latency kernels) ------------------------------------
+// Lane gl of the group owns entries gl (lo) and gl + G (hi) of the right-hand side (4 nb <= 2 G), for the whole sweep.
+// Block J's four entries reach every lane by shuffle from their owners, every lane multiplies them by the inverted
+// diagonal block redundantly and updates its own rows from the factor (read-only here), and the owners replace their
+// entries by the block's solution.  Nothing goes through shared memory but the factor, so a sweep needs no
+// __syncwarp at all; the shared-memory version above pays, per block column, a store -> synchronise -> load round
+// trip for the block, a load / store of every row's entry and two synchronisations.  Measured (T = 20): on a warp that
+// runs alone the three sweeps of an interior-point iteration drop from 14.3 k to 8.7 k cycles (iteration 46.2 k ->
+// 41.5 k); on a full batch the kernel gets 3-6 % slower (more shuffles and redundant loads, and with four warps per
+// scheduler one warp's dependency chains are not the limit).  So these sweeps serve the launches that leave the SMs
+// nearly empty (a single ego's step) and the shared-memory ones everything else; both produce the same bits (the
+// arithmetic per entry is the same sequence of FMAs, checked by the self-test kernel).
+// One block column is branch-free: a lane without a row to update loads from the block's own diagonal tile instead
+// (always a valid address) and its result is dropped by a select, the owners pick their component by selects.  The
+// warp issues in order, so a divergent `if` around the loads is not just a branch: it ends the basic block, and ptxas
+// can then no longer start the factor's loads in the shadow of the shuffles (750 instead of 290 cycles per block
+// column with branches).
+template <int G>
+__device__ __forceinline__ void sweep_load(const double* b, int n4, int gl, double& lo, double& hi) {
+  lo = (gl < n4) ? b[gl] : 0.0;
+  hi = (gl + G < n4) ? b[gl + G] : 0.0;
+}
+template <int G>
+__device__ __forceinline__ void sweep_store(double* b, int n4, int gl, double lo, double hi) {
+  if (gl < n4) b[gl] = lo;
+  if (gl + G < n4) b[gl + G] = hi;
+}
+// the inverse of L's diagonal block J (lower triangular, row major in the diagonal tile)
+struct DiagInv { double m00, m10, m11, m20, m21, m22, m30, m31, m32, m33; };
+__device__ __forceinline__ DiagInv load_diag_inv(const double* Mw) {
+  DiagInv d;
+  d.m00 = Mw[0];
+  const double2 r1 = *reinterpret_cast<const double2*>(Mw + 4);
+  d.m10 = r1.x; d.m11 = r1.y;
+  double pad;
+  ld4(Mw + 8, d.m20, d.m21, d.m22, pad); ld4(Mw + 12, d.m30, d.m31, d.m32, d.m33);
+  (void)pad;
+  return d;
+}
+template <int G, bool HI>
+__device__ __forceinline__ void forward_block(const double* K, int J, int n4, int gl, unsigned gm, const double* row_lo,
+                                              const double* row_hi, double& lo, double& hi) {
+  double& own = HI ? hi : lo;                      // the register that holds block J's entries on their owners
+  const int l0 = (J << 2) & (G - 1);
+  const double* Mw = K + tile_off(J, J);
+  const int first = (J + 1) << 2;                  // rows below the block
+  const bool act_lo = !HI && gl >= first && gl < n4, act_hi = gl + G >= first && gl + G < n4;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, c0, c1, c2, c3;
+  if (!HI) ld4(act_lo ? row_lo + J * kTS : Mw, a0, a1, a2, a3);
+  ld4(act_hi ? row_hi + J * kTS : Mw, c0, c1, c2, c3);
+  const DiagInv d = load_diag_inv(Mw);
+  const double e0 = __shfl_sync(gm, own, l0, G), e1 = __shfl_sync(gm, own, l0 + 1, G);
+  const double e2 = __shfl_sync(gm, own, l0 + 2, G), e3 = __shfl_sync(gm, own, l0 + 3, G);
+  const double y0 = d.m00 * e0, y1 = fma(d.m11, e1, d.m10 * e0), y2 = fma(d.m22, e2, fma(d.m21, e1, d.m20 * e0));
+  const double y3 = fma(d.m33, e3, fma(d.m32, e2, fma(d.m31, e1, d.m30 * e0)));
+  if (!HI) {
+    const double v = fma(-a3, y3, fma(-a2, y2, fma(-a1, y1, fma(-a0, y0, lo))));
+    lo = act_lo ? v : lo;
+  }
+  {
+    const double v = fma(-c3, y3, fma(-c2, y2, fma(-c1, y1, fma(-c0, y0, hi))));
+    hi = act_hi ? v : hi;
+  }
+  const double s01 = (gl & 1) ? y1 : y0, s23 = (gl & 1) ? y3 : y2, mine = (gl & 2) ? s23 : s01;
+  own = ((gl >> 2) == (l0 >> 2)) ? mine : own;
+}
+// L y = b
+template <int G>
+__device__ __forceinline__ void solve_forward_regs(const double* K, int nb, int gl, unsigned gm, double& lo, double& hi) {
+  const int n4 = nb << 2;
+  const double* row_lo = K + tile_off(gl >> 2, 0) + ((gl & 3) << 2);
+  const double* row_hi = K + tile_off((gl + G) >> 2, 0) + ((gl & 3) << 2);
+  const int nlo = nb < G / 4 ? nb : G / 4;
+#pragma unroll 1
+  for (int J = 0; J < nlo; ++J) forward_block<G, false>(K, J, n4, gl, gm, row_lo, row_hi, lo, hi);
+#pragma unroll 1
+  for (int J = G / 4; J < nb; ++J) forward_block<G, true>(K, J, n4, gl, gm, row_lo, row_hi, lo, hi);
+}
+template <int G, bool HI>
+__device__ __forceinline__ void backward_block(const double* K, int J, int n4, int gl, unsigned gm, int col_lo, int col_hi,
+                                               double& lo, double& hi) {
+  double& own = HI ? hi : lo;
+  const int l0 = (J << 2) & (G - 1);
+  const double* Krow = K + tile_off(J, 0);          // block row J of the factor
+  const double* Mw = Krow + J * kTS;
+  const int below = J << 2;                          // entries above the block: i < 4 J
+  const bool act_lo = gl < below && gl < n4, act_hi = HI && gl + G < below;
+  const double* pa = act_lo ? Krow + col_lo : Mw;
+  const double a0 = pa[0], a1 = pa[4], a2 = pa[8], a3 = pa[12];
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+  if (HI) { const double* pc = act_hi ? Krow + col_hi : Mw; c0 = pc[0]; c1 = pc[4]; c2 = pc[8]; c3 = pc[12]; }
+  const DiagInv d = load_diag_inv(Mw);
+  const double y0 = __shfl_sync(gm, own, l0, G), y1 = __shfl_sync(gm, own, l0 + 1, G);
+  const double y2 = __shfl_sync(gm, own, l0 + 2, G), y3 = __shfl_sync(gm, own, l0 + 3, G);
+  const double x3 = d.m33 * y3, x2 = fma(d.m32, y3, d.m22 * y2), x1 = fma(d.m31, y3, fma(d.m21, y2, d.m11 * y1));
+  const double x0 = fma(d.m30, y3, fma(d.m20, y2, fma(d.m10, y1, d.m00 * y0)));
+  {
+    const double v = fma(-a3, x3, fma(-a2, x2, fma(-a1, x1, fma(-a0, x0, lo))));
+    lo = act_lo ? v : lo;
+  }
+  if (HI) {
+    const double v = fma(-c3, x3, fma(-c2, x2, fma(-c1, x1, fma(-c0, x0, hi))));
+    hi = act_hi ? v : hi;
+  }
+  const double s01 = (gl & 1) ? x1 : x0, s23 = (gl & 1) ? x3 : x2, mine = (gl & 2) ? s23 : s01;
+  own = ((gl >> 2) == (l0 >> 2)) ? mine : own;
+}
+// L' x = y
+template <int G>
+__device__ __forceinline__ void solve_backward_regs(const double* K, int nb, int gl, unsigned gm, double& lo, double& hi) {
+  const int n4 = nb << 2;
+  const int col_lo = (gl >> 2) * kTS + (gl & 3), col_hi = ((gl + G) >> 2) * kTS + (gl & 3);
+#pragma unroll 1
+  for (int J = nb - 1; J >= G / 4; --J) backward_block<G, true>(K, J, n4, gl, gm, col_lo, col_hi, lo, hi);
+  const int nlo = nb < G / 4 ? nb : G / 4;
+#pragma unroll 1
+  for (int J = nlo - 1; J >= 0; --J) backward_block<G, false>(K, J, n4, gl, gm, col_lo, col_hi, lo, hi);
+}
+
 // y = P x for a symmetric P on tiles (diagonal tiles stored full); lane owns rows lane and lane + 32.
 __device__ inline void symv_tiles(const double* P, const double* x, int nb, int lane,
                                   double& y0, double& y1) {
@@ -325,14 +444,8 @@ __device__ inline void symv_tiles(const double* P, const double* x, int nb, int 
 
 // ---- rows k and T + k per lane ------------------------------------------------------------------------------------
 // The stage rows keep their part of an n = 2T vector in registers: lane k < T owns entries k (the acceleration part)
-// and T + k (the steering part).  The symmetric matvec below produces its result in that layout.  (Triangular
-// sweeps with the vector in registers -- block entries fetched by shuffle, no __syncwarp -- were measured twice.
-// Round 1, in this layout: 20 % shorter for a warp that runs alone, 2.3x the instructions, 12 % slower on a full
-// batch.  Round 2, cyclic layout (lane -> entries gl, gl + G), branch-free block steps so that the factor's loads
-// start in the shadow of the shuffles: the three sweeps of an iteration drop from 14.3 k to 8.7 k cycles on a warp
-// that runs alone (iteration 46.2 k -> 41.5 k), but a full batch is 3-6 % slower at T = 13 / 25 and no faster at
-// T = 20: with four warps per scheduler the kernel is bound by instruction issue and the shared-memory pipe, not by
-// one warp's dependency chains.  Dropped both times.)
+// and T + k (the steering part).  The symmetric matvec below produces its result in that layout.  (The
+// triangular sweeps with the vector in registers further up serve the low-latency kernels only.)
 template <int G>
 __device__ inline void solve_tiles(const double* K, double* b, int nb, int gl, unsigned gm) {
   solve_forward_tiles<G>(K, b, nb, gl, gm);
@@ -407,7 +520,20 @@ __global__ void linalg_selftest_kernel(int n, int which, const double* __restric
     __syncwarp(gm);
   }
   const bool good = chol_tiles<G>(K, nb, gl, gm, lut);
-  solve_tiles<G>(K, rhs, nb, gl, gm);
+  {
+    // the solve through shared memory; then the same solve with the vector in registers must give the same bits
+    // (NaN is reported otherwise)
+    double lo, hi, lo2, hi2;
+    sweep_load<G>(rhs, n4, gl, lo2, hi2);
+    solve_tiles<G>(K, rhs, nb, gl, gm);
+    __syncwarp(gm);
+    sweep_load<G>(rhs, n4, gl, lo, hi);
+    solve_forward_regs<G>(K, nb, gl, gm, lo2, hi2);
+    solve_backward_regs<G>(K, nb, gl, gm, lo2, hi2);
+    const bool same = (lo == lo2 || (lo != lo && lo2 != lo2)) && (hi == hi2 || (hi != hi && hi2 != hi2));
+    __syncwarp(gm);
+    sweep_store<G>(rhs, n4, gl, same ? lo : nan(""), same ? hi : nan(""));
+  }
   __syncwarp(gm);
   if (report) {
     for (int i = gl; i < n; i += G) sol[i] = rhs[i];

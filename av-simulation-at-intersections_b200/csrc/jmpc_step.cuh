@@ -651,7 +651,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
 // Returns the group's iteration count; `converged_out` says whether its KKT tolerances were met.  The groups of a
 // warp iterate in lock step until all of them are done; a group that is done (or never active) keeps executing on
 // its own data with its commits switched off, so the iterate it reports is the one it was done with.
-template <int TT, int G>
+template <int TT, int G, bool LAT>
 __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* smem_base, const double* pscr, int gl,
                                        bool& converged_out, unsigned& tma_parity, const chol_task* lut) {
   // The groups of a warp go through this whole phase in lock step (uniform control flow, see above), so its
@@ -822,6 +822,8 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
     for (int phase = 0; phase < 2; ++phase) {
       // complementarity targets: predictor rc = l s ; corrector rc = l s + ds_aff dl_aff - sigma mu
       double rph[4], rpl[4];
+      double sw_lo = 0.0, sw_hi = 0.0;
+      (void)sw_lo; (void)sw_hi;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         rph[r] = (gl < T) ? stash[r * T + gl] : 0.0; rpl[r] = (gl < T) ? stash[(4 + r) * T + gl] : 0.0;
@@ -842,13 +844,27 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
         if (gl < T) { M.rhs[gl] = -g0 - ra; M.rhs[T + gl] = -g1 - rd; }
         __syncwarp(gm);
         JMPC_TOCK(ts_, 5);
-        solve_forward_tiles<G>(M.K, M.rhs, nb, gl, gm);
+        if constexpr (LAT) {
+          sweep_load<G>(M.rhs, nb << 2, gl, sw_lo, sw_hi);
+          solve_forward_regs<G>(M.K, nb, gl, gm, sw_lo, sw_hi);
+        } else {
+          solve_forward_tiles<G>(M.K, M.rhs, nb, gl, gm);
+        }
       } else {
+        if constexpr (LAT) sweep_load<G>(M.rhs, nb << 2, gl, sw_lo, sw_hi);   // the forward substitution rode along with the factorisation
 #pragma unroll
         for (int r = 0; r < 4; ++r) { dlh[r] = lh[r] * sh[r]; dll[r] = ll[r] * sl[r]; }
         JMPC_TOCK(ts_, 5);
       }
-      solve_backward_tiles<G>(M.K, M.rhs, nb, gl, gm);
+      if constexpr (LAT) {
+        // low-latency kernels: the sweeps keep the vector in registers in a cyclic layout (lane -> entries gl, gl + G);
+        // the stage rows want entries gl and T + gl, so it takes one trip through shared memory
+        solve_backward_regs<G>(M.K, nb, gl, gm, sw_lo, sw_hi);
+        __syncwarp(gm);
+        sweep_store<G>(M.rhs, nb << 2, gl, sw_lo, sw_hi);
+      } else {
+        solve_backward_tiles<G>(M.K, M.rhs, nb, gl, gm);
+      }
       __syncwarp(gm);
       if (phase == 1 && gl == 0 && it + 1 < A.max_iters) tma_load_1d(M.K, pscr, (unsigned)(ntd * sizeof(double)), M.mbar);
       const double du0 = (gl < T) ? M.rhs[gl] : 0.0, du1 = (gl < T) ? M.rhs[T + gl] : 0.0;
@@ -1035,7 +1051,7 @@ __device__ __noinline__ bool step_output(const StepArgs& A, int b, bool active, 
 // (every shared-memory offset and tile count becomes an immediate); TT == 0 is the generic runtime-T version.  The
 // three phases are separate functions so that the solver's register allocation is not burdened by the values the
 // preparation and the epilogue need; they communicate through the group's shared memory.
-template <int TT, int G>
+template <int TT, int G, bool LAT>
 __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, bool active, double* smem_base, double* pscr,
                                                   int gl, unsigned gm, unsigned& tma_parity, const chol_task* lut) {
   const int T = (TT > 0) ? TT : A.T;
@@ -1058,7 +1074,7 @@ __device__ __forceinline__ void mpc_step_instance(const StepArgs& A, int b, bool
     if (G == 32 ? !active : !__any_sync(kFull, active)) return;
     JMPC_TOCK(ti_, 10);
     bool converged = false;
-    total_iters += step_solve<TT, G>(A, active, smem_base, pscr, gl, converged, tma_parity, lut);
+    total_iters += step_solve<TT, G, LAT>(A, active, smem_base, pscr, gl, converged, tma_parity, lut);
     JMPC_TOCK(ti_, 11);
     const bool finished = step_output<TT, G>(A, b, active, smem_base, gl, gm, lin == A.lin_iters - 1, converged, target,
                                              idx, end_mask, total_iters, oa_k, od_k, ov_k);
@@ -1156,8 +1172,13 @@ __global__ void __launch_bounds__(kSchedThreads) schedule_place_kernel(int B, co
 constexpr int step_min_blocks(int TT) {
   return TT == 8 ? JMPC_T8_BLOCKS : (TT == 25 && JMPC_MINBLOCKS > 3) ? 3 : JMPC_MINBLOCKS;
 }
-template <int TT, int G>
-__global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_kernel(
+// LAT selects the low-latency solve phase (triangular sweeps with the vector in registers, jmpc_linalg.cuh): for
+// launches that leave the SMs nearly empty -- a single ego's step -- where one warp's dependency chains are the whole
+// kernel time.  Same results bit for bit.
+// The low-latency kernels are launched with one warp per block and no occupancy target, so they get the full 255
+// registers (no spills: the 128-register budget of the throughput kernels costs a warp that runs alone ~20 %).
+template <int TT, int G, bool LAT = false>
+__global__ void __launch_bounds__(LAT ? 32 : 32 * JMPC_WPB, LAT ? 1 : step_min_blocks(TT)) mpc_step_kernel(
     const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(16) double smem[];
   constexpr int NG = 32 / G;                       // instances per warp
@@ -1193,7 +1214,7 @@ __global__ void __launch_bounds__(32 * JMPC_WPB, step_min_blocks(TT)) mpc_step_k
     if (A.order) b = (unsigned)A.order[b];
     if (A.skip && A.skip[b] != 0) active = false;
     if (!__any_sync(kFull, active)) continue;
-    mpc_step_instance<TT, G>(A, (int)b, active, base, pscr, gl, gm, tma_parity, lut);
+    mpc_step_instance<TT, G, LAT>(A, (int)b, active, base, pscr, gl, gm, tma_parity, lut);
     __syncwarp();
   }
   // Fused all-gather, completion signal: the block that retires last has (through the fences and the counter) every

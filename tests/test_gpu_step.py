@@ -415,3 +415,27 @@ def test_half_warp_pairs_are_independent(jm):
         assert np.array_equal(getattr(out, key)[solved[perm]], getattr(ref, key)[perm][solved[perm]]), key
     refs = oracle_batch(w, range(0, 257, 4))
     compare_step(ref, refs, range(0, 257, 4))
+
+
+@pytest.mark.parametrize("config,T", [(2, 20), (3, 13), (5, 8), (5, 25), (5, 10)])
+def test_low_latency_kernels_give_the_same_bits(jm, config, T):
+    """Launches of a handful of instances (at most two warps per SM) run the low-latency kernels: one warp per block,
+    full register budget, triangular sweeps with the vector in registers (jmpc_linalg.cuh).  They must reproduce the
+    throughput kernels bit for bit, so a result never depends on how many instances share its launch: 48 instances
+    alone (low-latency kernel), the same 48 inside a batch of 2048 (throughput kernel), and alone on an engine with a
+    fixed warp count (which switches the low-latency path off)."""
+    synth, BatchedMPC = jm
+    w = synth.make_workload(config, B=2048) if config != 5 else synth.make_sweep_sample(T, 2048)
+    assert w["T"] == T
+    small = np.arange(0, 2048, 43)[:48]
+    mpc, big = _run(BatchedMPC, w)
+    prm = None if w["params"] is None else w["params"][small]
+    lat = mpc.step_host(w["state"][small], w["target_ind"][small], w["oa"][small], w["od"][small],
+                        course_len=w["course_len"][small], params=prm)
+    mpc.close()
+    mpc2, fixed = _run(BatchedMPC, w, idx=small, warps_per_sm=16)
+    mpc2.close()
+    assert (big.status[small] == 0).sum() >= 40
+    for key in ["oa", "od", "ox", "oy", "ov", "oyaw", "cost", "status", "iters", "target_ind", "xref"]:
+        assert np.array_equal(getattr(lat, key), getattr(big, key)[small], equal_nan=True), key
+        assert np.array_equal(getattr(lat, key), getattr(fixed, key), equal_nan=True), key
