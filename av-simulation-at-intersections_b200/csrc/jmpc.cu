@@ -169,9 +169,15 @@ int step_geometry(jmpc_handle h, int B, int T, StepGeom* g, StepKernel* kernel) 
       fprintf(stderr, "[jmpc] step geometry: T=%d %d instance(s) per warp, %d blocks per SM x %d warps, smem/block=%zu, carve-out %d\n",
               T, groups, per_sm, wpb, smem, carve);
   }
-  // A launch of at most two warps per SM is latency-bound on single warps: it gets the low-latency kernel, one warp
-  // per block (a single ego's step: 0.274 -> LAT_MS ms at T = 20).  Everything else is throughput-bound.
-  if ((long long)B <= 2ll * h->sm_count * c.groups && h->opt.warps_per_sm <= 0) {
+  // A launch of at most eight warps per SM is latency-bound on single warps: it gets the low-latency kernel, one warp
+  // per block (a single ego's step at T = 20: 0.27 -> 0.24 ms; 2368 instances at T = 13: 0.43 -> 0.33 ms; from twelve
+  // warps per SM on its ~190 registers cost a second wave and the throughput kernel wins:
+  // profiles/r2_lat_threshold.txt).
+  long long lat_warps_per_sm = 8;
+#ifdef JMPC_EXPERIMENT
+  if (const char* e = getenv("JMPC_LAT_WARPS_PER_SM")) lat_warps_per_sm = atoll(e);
+#endif
+  if ((long long)B <= lat_warps_per_sm * h->sm_count * c.groups && h->opt.warps_per_sm <= 0) {
     const int blocks = (B + c.groups - 1) / c.groups;
     g->blocks = blocks; g->threads = 32; g->smem = c.smem_lat; g->groups_total = blocks * c.groups;
     *kernel = c.kernel_lat;

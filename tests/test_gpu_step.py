@@ -419,15 +419,15 @@ def test_half_warp_pairs_are_independent(jm):
 
 @pytest.mark.parametrize("config,T", [(2, 20), (3, 13), (5, 8), (5, 25), (5, 10)])
 def test_low_latency_kernels_give_the_same_bits(jm, config, T):
-    """Launches of a handful of instances (at most two warps per SM) run the low-latency kernels: one warp per block,
-    full register budget, triangular sweeps with the vector in registers (jmpc_linalg.cuh).  They must reproduce the
-    throughput kernels bit for bit, so a result never depends on how many instances share its launch: 48 instances
-    alone (low-latency kernel), the same 48 inside a batch of 2048 (throughput kernel), and alone on an engine with a
-    fixed warp count (which switches the low-latency path off)."""
+    """Small launches (at most eight warps per SM) run the low-latency kernels: one warp per block, full register
+    budget, triangular sweeps with the vector in registers (jmpc_linalg.cuh).  They must reproduce the throughput
+    kernels bit for bit, so a result never depends on how many instances share its launch: 48 instances alone
+    (low-latency kernel), the same 48 inside a batch of 6144 (throughput kernel), and alone on an engine with a fixed
+    warp count (which switches the low-latency path off)."""
     synth, BatchedMPC = jm
-    w = synth.make_workload(config, B=2048) if config != 5 else synth.make_sweep_sample(T, 2048)
+    w = synth.make_workload(config, B=6144) if config != 5 else synth.make_sweep_sample(T, 6144)
     assert w["T"] == T
-    small = np.arange(0, 2048, 43)[:48]
+    small = np.arange(0, 6144, 127)[:48]
     mpc, big = _run(BatchedMPC, w)
     prm = None if w["params"] is None else w["params"][small]
     lat = mpc.step_host(w["state"][small], w["target_ind"][small], w["oa"][small], w["od"][small],
