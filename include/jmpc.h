@@ -86,7 +86,7 @@ typedef struct {
   int32_t linearisation_iters;/* MAX_ITER of mpc_config.json (default 1)                     mpc.py:231   */
   double  mu_tol;             /* complementarity target (default 1e-13)                                    */
   int32_t warps_per_sm;       /* resident solver warps per SM, 0 = auto (auto also picks the low-latency
-                                 kernels for launches of at most two warps per SM; same results)          */
+                                 kernels for launches of at most eight warps per SM; same results)          */
   double  du_th;              /* > 0: leave the linearisation loop once sum|oa - poa| + sum|od - pod| <= du_th;
                                  the exit the reference left commented out at mpc.py:236-240 (DU_TH of
                                  mpc_config.json).  Default 0 = off, as in the reference.                  */
