@@ -6,7 +6,8 @@
 //   2. reference sampling xref / reaches_end      main/lib/mpc.py:89-112
 //   3. operating-point rollout xbar               main/lib/mpc.py:115-129, main/lib/simulation.py:35-47,
 //                                                 main/bicycle/main.py:28-41
-//   4. linearisation + exact condensing           main/lib/mpc.py:61-82,132-138,151-194  (states eliminated)
+//   4. linearisation + exact condensing           main/lib/mpc.py:61-82,132-138,151-194  (states eliminated; the
+//      unknowns are the cumulative accelerations s_k = a_0 + .. + a_k and the steering angles: see step_prep)
 //   5. QP solve: Mehrotra predictor-corrector interior point on the n = 2T condensed problem; the normal
 //      matrix K = P + A' diag(w) A lives in shared memory, its Cholesky factor overwrites it in place
 //      (replaces cvxpy + ECOS, mpc.py:196-197)
@@ -22,8 +23,13 @@
 // The kernel is therefore a template on G, the lanes per instance: G = 16 packs two independent instances into a
 // warp (one per half), G = 32 is the whole warp (T >= 16).  The groups of a warp run in lock step: every phase is
 // uniform control flow (a group that is finished, failed or has no instance left keeps executing on its own
-// shared-memory region with its commits switched off), but all shuffles and synchronisations are group-scoped,
-// so correctness never depends on the halves being converged.
+// shared-memory region with its commits switched off).  Phases A and C have group-uniform early exits, so their
+// shuffles and synchronisations are group-scoped and never depend on the halves being converged; the solve phase has
+// none and names the whole warp (step_solve).
+//
+// Two instantiations per horizon: the throughput kernel (four warps per block, 128 registers, sweeps through shared
+// memory) and the low-latency kernel for launches of at most eight warps per SM (one warp per block, ~190 registers,
+// sweeps with the vector in registers).  Same results bit for bit.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
