@@ -1175,8 +1175,11 @@ __global__ void __launch_bounds__(kSchedThreads) schedule_place_kernel(int B, co
 #ifndef JMPC_T8_BLOCKS
 #define JMPC_T8_BLOCKS ((JMPC_MINBLOCKS * 3) / 2)
 #endif
+// At T = 13 three blocks (168 registers, no spills, 24 resident instances) have overtaken four (128 registers, 32
+// instances) since the solver loop lost a third of its instructions: +2 % (profiles/r2_ab_variants.txt, session mb3);
+// at T = 20 the two are equal and four stay.
 constexpr int step_min_blocks(int TT) {
-  return TT == 8 ? JMPC_T8_BLOCKS : (TT == 25 && JMPC_MINBLOCKS > 3) ? 3 : JMPC_MINBLOCKS;
+  return TT == 8 ? JMPC_T8_BLOCKS : ((TT == 25 || TT == 13) && JMPC_MINBLOCKS > 3) ? 3 : JMPC_MINBLOCKS;
 }
 // LAT selects the low-latency solve phase (triangular sweeps with the vector in registers, jmpc_linalg.cuh): for
 // launches that leave the SMs nearly empty -- a single ego's step -- where one warp's dependency chains are the whole
