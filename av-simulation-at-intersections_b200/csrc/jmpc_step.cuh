@@ -547,7 +547,7 @@ __device__ __noinline__ int step_prep(const StepArgs& A, int b, bool active, dou
   }
   {
     // Three passes, one per block type (s x s, steer x s, steer x steer): a single pass over the packed
-    // triangle mixed steer x accel and steer x steer entries in every group of lanes, so the warp executed both paths.
+    // triangle mixed steer x s and steer x steer entries in every group of lanes, so the warp executed both paths.
     const int ms = even_up(T + 1);
     // S(W; F, G)(F0, G0) = sum_{t >= t0} W_t (F_t - F0)(G_t - G0) from the suffix moments
     auto S = [&](const double* mom, int mW, int mWF, int mWG, int mWFG, double F0, double G0) -> double {
@@ -670,8 +670,8 @@ __device__ __noinline__ int step_solve(const StepArgs& A, bool active, double* s
   WarpMem M(smem_base, T);
   auto P = [&](int k) -> double { return M.prm[k]; };
   // ---------------- 5. interior-point solve -------------------------------------------------------
-  // Stage k = lane owns four two-sided rows: r = 0 accel box, 1 steer box, 2 steer rate k -> k+1, 3 speed
-  // (running sum of a up to k).  Only slacks and multipliers stay in registers across the factorisation;
+  // Stage k = lane owns four two-sided rows: r = 0 acceleration box (on s_k - s_{k-1}), 1 steer box, 2 steer rate
+  // k -> k+1, 3 speed (a box on s_k, the running sum of a up to k).  Only slacks and multipliers stay in registers across the factorisation;
   // bounds are rebuilt from the parameter block when needed.
   // Dead rows (lanes beyond the horizon; the rate row of the last stage) keep lambda = 0 and ds = dl = 0 exactly for
   // the whole solve, so every product with their multipliers vanishes by itself: only the quantities that would
