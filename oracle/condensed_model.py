@@ -247,10 +247,48 @@ def _assemble_K(T, P, w):
     return K
 
 
-def ipm_solve(c: CondensedQP, max_iter: int = 40, mu_tol: float = 1e-13, s_min: float = 1e-2, lam0: float = 1.0):
-    """Returns (u, iterations, converged)."""
+# the same three structure functions in the unknowns [s; delta] of the CUDA kernel (s_k = a_0 + ... + a_k): the
+# acceleration row is s_k - s_{k-1}, the speed row s_k itself, and A' W A is tridiagonal in both blocks
+def _rows_apply_cum(T, u):
+    s, d = u[:T], u[T:]
+    rate = np.zeros(T)
+    rate[:T - 1] = d[1:] - d[:-1]
+    return np.stack([s - np.concatenate([[0.0], s[:-1]]), d, rate, s])
+
+
+def _rows_apply_T_cum(T, t):
+    out = np.zeros(2 * T)
+    out[:T] = t[0] - np.append(t[0][1:], 0.0) + t[3]
+    out[T:] = t[1]
+    out[T:2 * T - 1] -= t[2][:T - 1]
+    out[T + 1:] += t[2][:T - 1]
+    return out
+
+
+def _assemble_K_cum(T, P, w):
+    K = P.copy()
+    idx = np.arange(T)
+    K[idx, idx] += w[0] + np.append(w[0][1:], 0.0) + w[3]
+    K[T + idx, T + idx] += w[1]
+    for k in range(1, T):
+        K[k, k - 1] -= w[0][k]
+        K[k - 1, k] -= w[0][k]
+    for k in range(T - 1):
+        K[T + k, T + k] += w[2][k]
+        K[T + k + 1, T + k + 1] += w[2][k]
+        K[T + k, T + k + 1] -= w[2][k]
+        K[T + k + 1, T + k] -= w[2][k]
+    return K
+
+
+def ipm_solve(c: CondensedQP, max_iter: int = 40, mu_tol: float = 1e-13, s_min: float = 1e-2, lam0: float = 1.0,
+              cumulative: bool = False):
+    """Returns (u, iterations, converged).  `cumulative`: iterate in the kernel's unknowns [s; delta] (c.P, c.q must
+    then be the Hessian / linear term in those unknowns); the result is still returned as controls [a; delta]."""
     T = len(c.q) // 2
     n = 2 * T
+    _rows_apply, _rows_apply_T, _assemble_K = ((_rows_apply_cum, _rows_apply_T_cum, _assemble_K_cum) if cumulative else
+                                               (globals()["_rows_apply"], globals()["_rows_apply_T"], globals()["_assemble_K"]))
     hi = np.stack([c.hi[:T], c.hi[T:2 * T], np.append(c.hi[2 * T:3 * T - 1], 1.0), c.hi[3 * T - 1:]])
     lo = np.stack([c.lo[:T], c.lo[T:2 * T], np.append(c.lo[2 * T:3 * T - 1], -1.0), c.lo[3 * T - 1:]])
     live = np.ones((4, T), bool)
@@ -312,4 +350,6 @@ def ipm_solve(c: CondensedQP, max_iter: int = 40, mu_tol: float = 1e-13, s_min: 
         u = u + alpha * du
         sh, sl = sh + alpha * dsh, sl + alpha * dsl
         lh, ll = lh + alpha * dlh, ll + alpha * dll
+    if cumulative:
+        u = cumulative_transform(T) @ u
     return u, it, ok

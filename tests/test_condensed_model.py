@@ -88,3 +88,20 @@ def test_cumulative_acceleration_form(cases):
         u_ref = np.concatenate([r.oa, r.od])
         s_ref = np.linalg.solve(E, u_ref)
         np.testing.assert_allclose(s_ref[:p.T], np.cumsum(r.oa), rtol=0, atol=1e-12)
+
+
+def test_interior_point_iterates_do_not_depend_on_the_unknowns(cases):
+    """A linear change of unknowns leaves the rows, the slacks and the multipliers alone, so the predictor-corrector
+    iteration in [s; delta] takes the same number of iterations and ends in the same controls as in [a; delta]
+    (the kernel changed unknowns without changing a single iteration count on config 2)."""
+    import dataclasses
+    for p, x0, r in cases:
+        cq = CM.condense(p, r.xref, r.xbar, x0, r.reaches_end)
+        u_a, it_a, ok_a = CM.ipm_solve(cq)
+        P, q = CM.condense_cumulative(p, r.xref, r.xbar, x0, r.reaches_end)
+        u_s, it_s, ok_s = CM.ipm_solve(dataclasses.replace(cq, P=P, q=q), cumulative=True)
+        assert ok_a and ok_s
+        assert abs(it_a - it_s) <= 1                      # roundoff may move an exit by one iteration
+        np.testing.assert_allclose(u_s, u_a, rtol=0, atol=1e-7)
+        T = p.T
+        assert scaled_err(u_s[:T], r.oa) <= 1.0 and scaled_err(u_s[T:], r.od) <= 1.0
